@@ -1,0 +1,80 @@
+// C ABI wrappers for the loss kernels and the kernel-level test entry points (include/dad_b200.h).
+#include "../../include/dad_b200.h"
+
+#include "elementwise.h"
+#include "gemm.h"
+#include "losses.h"
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int dad_abi_version(void) { return 1; }
+
+size_t dad_loss_workspace_bytes(int rows, int num_contexts) { return dad::loss_workspace_bytes(rows, num_contexts); }
+
+int dad_masked_shift_and_scale(const float* pred, const float* gt, const uint8_t* mask, int rows, int64_t L,
+                               float* pred_aligned, float* gt_aligned, void* ws, size_t wsb, void* stream) {
+    if (!pred_aligned || !gt_aligned) return dad::set_error(DAD_ERR_INVALID, "masked_shift_and_scale: null output");
+    return dad::masked_shift_and_scale(pred, gt, mask, rows, L, pred_aligned, gt_aligned, ws, wsb, ST(stream));
+}
+
+int dad_ssi_loss(const float* pred, const float* gt, const uint8_t* mask, int rows, int64_t L, float* dense_out,
+                 float* out_scalar, double* partials, void* ws, size_t wsb, void* stream) {
+    return dad::ssi_loss(pred, gt, mask, rows, L, dense_out, out_scalar, partials, ws, wsb, ST(stream));
+}
+
+int dad_contexts_dr(int level, const float* gt, const uint8_t* mask, int B, int64_t L, uint8_t* ctx_out, void* ws,
+                    size_t wsb, void* stream) {
+    return dad::contexts_dr(level, gt, mask, B, L, ctx_out, ws, wsb, ST(stream));
+}
+
+int dad_hdn_loss_dr(int level, const float* pred, const float* gt, const uint8_t* mask, int B, int64_t L,
+                    float* out_scalar, double* partials, void* ws, size_t wsb, void* stream) {
+    return dad::hdn_loss_dr(level, pred, gt, mask, B, L, out_scalar, partials, ws, wsb, ST(stream));
+}
+
+int dad_hdn_loss(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, int64_t L, float* out_scalar,
+                 double* partials, void* ws, size_t wsb, void* stream) {
+    if (!ctx) return dad::set_error(DAD_ERR_INVALID, "hdn_loss: null contexts");
+    return dad::hdn_loss_ctx(pred, gt, ctx, K, B, L, out_scalar, partials, ws, wsb, ST(stream));
+}
+
+int dad_grad_loss(const float* depth, int B, int H, int W, float* out_scalar, double* partials, void* ws, size_t wsb,
+                  void* stream) {
+    return dad::grad_loss(depth, B, H, W, out_scalar, partials, ws, wsb, ST(stream));
+}
+
+int dad_feat_cos_loss(const float* s, const float* t, int B, int N, int Ds, int Dt, float* out_scalar, double* partials,
+                      void* ws, size_t wsb, void* stream) {
+    return dad::feat_cos_loss(s, t, B, N, Ds, Dt, out_scalar, partials, ws, wsb, ST(stream));
+}
+
+int dad_distill_loss(const float* student, const float* teacher, int strategy, int num_segments, int B, int64_t L,
+                     float* out_scalar, double* partials, float* norm_student, float* norm_teacher, void* ws,
+                     size_t wsb, void* stream) {
+    return dad::distill_loss(student, teacher, strategy, num_segments, B, L, out_scalar, partials, norm_student,
+                             norm_teacher, ws, wsb, ST(stream));
+}
+
+int dad_gemm(const void* A, const void* W, const float* bias, float* out, int M, int N, int K, int mode, void* stream) {
+    dad::GemmProblem p;
+    p.A = A; p.M = M; p.K = K; p.lda = K; p.Wt = W; p.N = N; p.Kp = K;
+    p.epi.bias = bias; p.epi.out = out; p.epi.ldc = N;
+    return mode == 0 ? dad::gemm_tc(p, ST(stream)) : dad::gemm_simt(p, ST(stream));
+}
+
+int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
+                  int Co, int taps, int mode, void* stream) {
+    dad::GemmProblem p;
+    p.A = in; p.conv = 1; p.B = B; p.H = H; p.W = W; p.C = C; p.taps = taps; p.ldp = C;
+    p.Wt = Wpacked; p.N = Co; p.Kp = taps * dad::cdiv(C, 64) * 64;
+    p.epi.bias = bias; p.epi.out = out; p.epi.ldc = Co;
+    return mode == 0 ? dad::gemm_tc(p, ST(stream)) : dad::gemm_simt(p, ST(stream));
+}
+
+int dad_attention(const void* qkv, void* out, int B, int N, int heads, int mode, void* stream) {
+    return dad::attention(qkv, out, mode == 0, B, N, heads, ST(stream));
+}
+
+}  // extern "C"

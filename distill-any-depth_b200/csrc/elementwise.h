@@ -1,0 +1,21 @@
+// Internal C++ interface of the HBM-bound helper kernels and the attention kernels.
+#pragma once
+#include "common.h"
+
+namespace dad {
+
+int patch_im2col(const float* x, void* A, int is_bf16, int B, int H, int W, int Kp, cudaStream_t st);
+// rows = output rows; input row = (r / out_period) * in_period + in_offset + r % out_period
+int layernorm(const float* in, const float* w, const float* b, void* out, int is_bf16, float* out_f32, long long rows,
+              int D, int out_period, int in_period, int in_offset, float eps, cudaStream_t st);
+int bilinear_nhwc(const void* in, void* out, int is_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st);
+int im2col_s2(const void* in, void* A, int is_bf16, int B, int H, int W, int C, int Cp, cudaStream_t st);
+int head1x1(const float* in, const float* w, float bias, float* out, long long P, cudaStream_t st);
+int pos_table(const float* pos, const float* cls, const float* pbias, float* tab, int D, int H, int W, cudaStream_t st);
+int pack_linear(const float* w, void* out, int is_bf16, int N, int K, int Kp, int scale_rows, float scale, cudaStream_t st);
+int pack_conv(const float* w, void* out, int is_bf16, int Co, int Ci, int taps, int Cp, cudaStream_t st);
+int pack_convT(const float* w, void* out, int is_bf16, int Ci, int Co, int k, int CoP, int Kp, cudaStream_t st);
+int copy_scale(const float* in, float* out, long long n, long long scale_n, float scale, cudaStream_t st);
+int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, cudaStream_t st);
+
+}  // namespace dad

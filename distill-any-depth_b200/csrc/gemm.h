@@ -1,0 +1,63 @@
+// Internal interface of the GEMM / implicit-GEMM-convolution engine.
+//
+//   D[row, col] = epilogue( sum_k A[row, k] * Wt[col, k] )
+//
+// A is either a plain row-major matrix ("linear") or an NHWC activation tensor
+// read as a 3x3 / 1x1 stride-1 zero-padded convolution window ("conv").  Wt is
+// the K-major weight matrix ([N, Kp]); for conv, Kp = taps * cchunks * 64 with
+// each tap's channels zero-padded to a multiple of 64.
+//
+// Two engines implement it:
+//   gemm_tc   - bf16 operands, tcgen05.mma + TMEM accumulators, TMA-fed (bf16 mode)
+//   gemm_simt - fp32 operands, FFMA, gather loads (fp32 verification mode)
+// Both share the epilogue in epilogue.cuh.
+#pragma once
+#include "common.h"
+
+namespace dad {
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+struct Epilogue {
+    const float* bias = nullptr;     // [N] (indexed by output channel)
+    const float* gamma = nullptr;    // [N] LayerScale, applied after bias/act
+    const float* rowtab = nullptr;   // [rowtab_period, N] table added per (row % period)
+    int rowtab_period = 0;
+    int act = ACT_NONE;
+    const void* res1 = nullptr;      // residual inputs, same indexing as out
+    const void* res2 = nullptr;
+    int res1_bf16 = 0, res2_bf16 = 0;
+    void* out = nullptr;
+    int out_bf16 = 0;
+    long long ldc = 0;               // elements between output rows
+    void* out_relu = nullptr;        // optional copy with ReLU applied (same dtype / indexing as out)
+    // ConvTranspose k=s (non-overlapping): column = (ky*k + kx) * CoP + co,
+    // input row = (b, y, x) over scat_H x scat_W; out[b, k*y+ky, k*x+kx, co].
+    int scat_k = 0, scat_CoP = 0, scat_Co = 0, scat_H = 0, scat_W = 0;
+    // Fused output head (N == 32): out_head[row] = relu(dot(relu(acc+bias), head_w) + head_b)
+    const float* head_w = nullptr;
+    float head_b = 0.f;
+    float* head_out = nullptr;
+};
+
+struct GemmProblem {
+    // A operand
+    const void* A = nullptr;  // bf16 (tc) or fp32 (simt)
+    int conv = 0;             // 0 linear, 1 conv
+    // linear
+    int M = 0, K = 0;
+    long long lda = 0;        // elements between rows
+    // conv (stride 1, "same" zero padding): NHWC with `ldp` elements between pixels
+    int B = 0, H = 0, W = 0, C = 0, taps = 1;
+    long long ldp = 0;
+    // weights
+    const void* Wt = nullptr; // [N, Kp] K-major; bf16 (tc) or fp32 (simt)
+    int N = 0;
+    int Kp = 0;               // padded K (row length of Wt)
+    Epilogue epi;
+};
+
+int gemm_tc(const GemmProblem& p, cudaStream_t stream);
+int gemm_simt(const GemmProblem& p, cudaStream_t stream);
+
+}  // namespace dad

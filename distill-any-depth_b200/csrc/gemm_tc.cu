@@ -1,0 +1,369 @@
+// bf16 GEMM / implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a).
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0 (one lane)  TMA producer: A tile (128 x 64 bf16) and B tile (BN x 64 bf16) per k-block,
+//                      SWIZZLE_128B, through a STAGES-deep mbarrier ring
+//   warp 1 (one lane)  tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16, fp32 accumulate in TMEM);
+//                      tcgen05.commit frees smem stages and publishes finished accumulators
+//   warps 2-5          epilogue: tcgen05.ld (32 lanes x 32 columns) -> fused epilogue -> global
+// TMEM holds two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1.
+//
+// Convolution (3x3 / 1x1, stride 1, zero "same" padding) is an implicit GEMM: the M tile is a
+// TH x TW patch of output pixels and each k-block is one (tap, 64-channel chunk); its A tile is a
+// 4-D TMA box of the NHWC input at the tap-shifted coordinate, with out-of-bounds rows/channels
+// zero-filled by the TMA unit (that is the padding).
+#include <cuda.h>
+
+#include "epilogue.cuh"
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace dad {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int NUM_THREADS = 192;
+
+struct TcArgs {
+    Epilogue epi;
+    int M, N;
+    int num_k_blocks;
+    int conv, taps, cchunks, pad;
+    int B, H, W;
+    int tw_log2, th;        // spatial tile (conv): TW = 1 << tw_log2, TH = 128 / TW
+    int tiles_x, tiles_y;
+    int num_m_tiles, num_n_tiles;
+};
+
+template <int BN>
+struct Cfg {
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TcArgs g) {
+    using C = Cfg<BN>;
+    constexpr int STAGES = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < STAGES; ++i) {
+                ptx::mbar_init(&full[i], 1);
+                ptx::mbar_init(&empty[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(&tfull[i], 1);
+                ptx::mbar_init(&tempty[i], 128);
+            }
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+    const int nkb = g.num_k_blocks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = tile / g.num_n_tiles;
+                const int n0 = (tile - mt * g.num_n_tiles) * BN;
+                int b = 0, y0 = 0, x0 = 0;
+                if (g.conv) {
+                    const int per_img = g.tiles_x * g.tiles_y;
+                    b = mt / per_img;
+                    const int r = mt - b * per_img;
+                    const int ty = r / g.tiles_x;
+                    y0 = ty * g.th;
+                    x0 = (r - ty * g.tiles_x) << g.tw_log2;
+                }
+                for (int kb = 0; kb < nkb; ++kb) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                    if (g.conv) {
+                        const int tap = kb / g.cchunks;
+                        const int cc = kb - tap * g.cchunks;
+                        int dy = 0, dx = 0;
+                        if (g.taps == 9) { dy = tap / 3; dx = tap - dy * 3; }
+                        ptx::tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], cc * BK,
+                                         x0 + dx - g.pad, y0 + dy - g.pad, b);
+                    } else {
+                        ptx::tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, mt * BM);
+                    }
+                    ptx::tma_load_2d(sB + stage * C::B_STAGE_BYTES, &tmB, &full[stage], kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(sA + stage * A_STAGE_BYTES);
+                    const uint32_t b_addr = ptx::smem_u32(sB + stage * C::B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ad = ptx::make_smem_desc_sw128(a_addr + k * 32);
+                        const uint64_t bd = ptx::make_smem_desc_sw128(b_addr + k * 32);
+                        ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tfull[as]);
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+            }
+        }
+    } else {
+        // ---------------------------------------------------- epilogue (warps 2..5)
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int r = quarter * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile / g.num_n_tiles;
+            const int n0 = (tile - mt * g.num_n_tiles) * BN;
+            long long grow;
+            bool valid;
+            if (g.conv) {
+                const int per_img = g.tiles_x * g.tiles_y;
+                const int b = mt / per_img;
+                const int rr = mt - b * per_img;
+                const int ty = rr / g.tiles_x;
+                const int y = ty * g.th + (r >> g.tw_log2);
+                const int x = ((rr - ty * g.tiles_x) << g.tw_log2) + (r & ((1 << g.tw_log2) - 1));
+                valid = (y < g.H) && (x < g.W);
+                grow = (static_cast<long long>(b) * g.H + y) * g.W + x;
+            } else {
+                grow = static_cast<long long>(mt) * BM + r;
+                valid = grow < g.M;
+            }
+            ptx::mbar_wait(&tfull[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+            if (g.epi.head_out != nullptr) {
+                if constexpr (BN == 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_row, v);
+                    ptx::tmem_ld_wait();
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float a = __uint_as_float(v[j]) + g.epi.bias[j];
+                        s = fmaf(fmaxf(a, 0.f), g.epi.head_w[j], s);
+                    }
+                    if (valid) g.epi.head_out[grow] = fmaxf(s + g.epi.head_b, 0.f);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_row + c * 32, v);
+                    ptx::tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const int col = n0 + c * 32 + j;
+                            if (col < g.N) {
+                                float f[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
+                                epilogue_store4(g.epi, g.N, grow, grow, col, f);
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty[as]);
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+              const cuuint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+        return set_error(DAD_ERR_INVALID, "TMA base address %p not 16-byte aligned", base);
+    for (int i = 0; i < rank - 1; ++i)
+        if (strides_bytes[i] % 16 != 0)
+            return set_error(DAD_ERR_INVALID, "TMA stride %llu not a multiple of 16 bytes",
+                             (unsigned long long)strides_bytes[i]);
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return DAD_OK;
+}
+
+template <int BN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg<BN>::SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles = a.num_m_tiles * a.num_n_tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int pick_bn(int N) {
+    const int cands[4] = {256, 128, 64, 32};
+    for (int i = 0; i < 4; ++i) {
+        const int bn = cands[i];
+        if (N % bn == 0 || N >= 8 * bn) return bn;
+    }
+    return 32;
+}
+
+}  // namespace
+
+int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
+    DAD_REQUIRE(p.A && p.Wt && p.N > 0, "gemm_tc: null operand or N<=0");
+    DAD_REQUIRE(p.N % 8 == 0, "gemm_tc: N=%d must be a multiple of 8", p.N);
+    DAD_REQUIRE(p.Kp % 8 == 0, "gemm_tc: Kp=%d must be a multiple of 8", p.Kp);
+    TcArgs a{};
+    a.epi = p.epi;
+    a.N = p.N;
+    a.conv = p.conv;
+    int bn = pick_bn(p.N);
+    if (p.epi.head_out) {
+        DAD_REQUIRE(p.N == 32 && p.epi.bias && p.epi.head_w, "gemm_tc: fused head needs N == 32, bias and head_w");
+        bn = 32;
+    }
+    if (p.epi.scat_k) DAD_REQUIRE(p.epi.scat_CoP % 32 == 0, "gemm_tc: scatter needs CoP %% 32 == 0");
+    a.num_n_tiles = cdiv(p.N, bn);
+
+    CUtensorMap tmA, tmB;
+    if (p.conv) {
+        DAD_REQUIRE(p.taps == 1 || p.taps == 9, "gemm_tc: taps must be 1 or 9");
+        DAD_REQUIRE(p.C % 8 == 0 && p.ldp % 8 == 0, "gemm_tc: conv C/ldp must be multiples of 8");
+        a.taps = p.taps;
+        a.pad = p.taps == 9 ? 1 : 0;
+        a.cchunks = cdiv(p.C, BK);
+        a.num_k_blocks = a.taps * a.cchunks;
+        DAD_REQUIRE(p.Kp == a.num_k_blocks * BK, "gemm_tc: conv weights must be packed to Kp=%d (got %d)",
+                    a.num_k_blocks * BK, p.Kp);
+        a.B = p.B; a.H = p.H; a.W = p.W;
+        a.M = p.B * p.H * p.W;
+        // choose the spatial tile (TH x TW = 128) with the least padded area
+        long long best = -1;
+        for (int l2 = 3; l2 <= 7; ++l2) {
+            const int tw = 1 << l2, th = BM / tw;
+            const long long area = static_cast<long long>(cdiv(p.W, tw)) * tw * cdiv(p.H, th) * th;
+            if (best < 0 || area < best) { best = area; a.tw_log2 = l2; a.th = th; }
+        }
+        const int tw = 1 << a.tw_log2;
+        a.tiles_x = cdiv(p.W, tw);
+        a.tiles_y = cdiv(p.H, a.th);
+        a.num_m_tiles = p.B * a.tiles_x * a.tiles_y;
+        const cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+        const cuuint64_t strides[3] = {(cuuint64_t)p.ldp * 2, (cuuint64_t)p.ldp * 2 * p.W,
+                                       (cuuint64_t)p.ldp * 2 * p.W * p.H};
+        const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)tw, (cuuint32_t)a.th, 1};
+        DAD_TRY(make_tmap(&tmA, p.A, 4, dims, strides, box));
+    } else {
+        DAD_REQUIRE(p.M > 0 && p.K > 0 && p.lda >= p.K && p.lda % 8 == 0, "gemm_tc: bad linear dims M=%d K=%d lda=%lld",
+                    p.M, p.K, p.lda);
+        a.M = p.M;
+        a.num_k_blocks = cdiv(p.K, BK);
+        a.num_m_tiles = cdiv(p.M, BM);
+        const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+        const cuuint64_t strides[1] = {(cuuint64_t)p.lda * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+        DAD_TRY(make_tmap(&tmA, p.A, 2, dims, strides, box));
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)p.Kp, (cuuint64_t)p.N};
+        const cuuint64_t strides[1] = {(cuuint64_t)p.Kp * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
+        DAD_TRY(make_tmap(&tmB, p.Wt, 2, dims, strides, box));
+    }
+    switch (bn) {
+        case 256: return launch<256>(tmA, tmB, a, stream);
+        case 128: return launch<128>(tmA, tmB, a, stream);
+        case 64: return launch<64>(tmA, tmB, a, stream);
+        default: return launch<32>(tmA, tmB, a, stream);
+    }
+}
+
+}  // namespace dad

@@ -1,0 +1,844 @@
+// Distillation-loss reductions (fp32, exact selection), all on the caller's stream with no host
+// sync and no per-image host loop.  Reference: tools/train_distillation.py:173-707.
+//
+// Exact lower medians (nanmedian / torch.median semantics) use an MSB-first 4 x 8-bit radix select
+// on the order-preserving uint32 image of fp32: each pass histograms one digit of every member
+// element whose higher digits match the prefix found so far (shared-memory histograms with
+// warp-aggregated atomics, flushed to a per-row global histogram), then a one-warp-per-row scan
+// picks the bin holding the wanted rank.  A "row" is (array in {pred, gt}) x image x context; the
+// HDN-DR path computes each pixel's context membership on the fly from the per-image min/max
+// (no [7,B,1,H,W] mask tensor, no 7x replicated maps).
+#include <cfloat>
+
+#include "common.h"
+#include "losses.h"
+
+namespace dad {
+
+namespace {
+
+constexpr int MODE_MASK = 0;  // K = 1: optional u8 mask [B, L]
+constexpr int MODE_DR = 1;    // K = 2^level - 1 depth-range contexts from gt + optional mask
+constexpr int MODE_CTX = 2;   // K explicit u8 contexts [K, B, L]
+constexpr int MAX_K = 21;
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    return __uint_as_float(u);
+}
+
+struct SelArgs {
+    const float* pred;     // [B, L]
+    const float* gt;       // [B, L]
+    const uint8_t* mask;   // [B, L] or null
+    const uint8_t* ctx;    // [K, B, L] (MODE_CTX)
+    int B, K, level, narr; // narr = 2 (pred, gt) or 1 (pred only)
+    long long L;
+    int chunk;             // pixels per CTA
+    // workspace
+    uint32_t* minmax;      // [B][2] keys over valid gt (MODE_DR)
+    uint32_t* hist;        // [4][R][256]
+    uint32_t* prefix;      // [R]
+    uint32_t* krank;       // [R]
+    uint32_t* count;       // [R]
+    float* t;              // [R] medians
+    double* madsum;        // [R]
+    float* s;              // [R] scales
+    double* acc;           // [0] numerator, [1] (as double) denominator count
+    int R;
+};
+
+__device__ __forceinline__ int row_of(const SelArgs& a, int arr, int b, int k) { return (arr * a.B + b) * a.K + k; }
+
+// Depth-range thresholds, reference op order (tools/train_distillation.py:562-569):
+//   lo = min + ((max - min) * i) * bin ;  hi = (min + ((max - min) * (i + 1)) * bin) + 1e-30
+__device__ __forceinline__ void dr_thresholds(int level, int k, float mn, float mx, float& lo, float& hi) {
+    int lvl = 0, first = 0;  // contexts ordered finest level first: 2^(level-1) bins, ..., 1 bin
+    int nb = 1 << (level - 1);
+    while (k >= first + nb) { first += nb; nb >>= 1; ++lvl; }
+    const int i = k - first;
+    const float bin = 1.0f / static_cast<float>(nb);
+    const float range = __fsub_rn(mx, mn);
+    lo = __fadd_rn(mn, __fmul_rn(__fmul_rn(range, static_cast<float>(i)), bin));
+    hi = __fadd_rn(__fadd_rn(mn, __fmul_rn(__fmul_rn(range, static_cast<float>(i + 1)), bin)), 1e-30f);
+    (void)lvl;
+}
+
+template <int MODE>
+__device__ __forceinline__ uint32_t member_bits(const SelArgs& a, int b, long long i, float g, const float* lo,
+                                                const float* hi, bool has_valid) {
+    if (MODE == MODE_MASK) {
+        return a.mask ? (a.mask[static_cast<long long>(b) * a.L + i] != 0 ? 1u : 0u) : 1u;
+    } else if (MODE == MODE_DR) {
+        const bool valid = a.mask ? a.mask[static_cast<long long>(b) * a.L + i] != 0 : true;
+        if (!valid || !has_valid) return 0u;
+        uint32_t bits = 0;
+        for (int k = 0; k < a.K; ++k) bits |= (g >= lo[k] && g < hi[k]) ? (1u << k) : 0u;
+        return bits;
+    } else {
+        uint32_t bits = 0;
+        for (int k = 0; k < a.K; ++k)
+            bits |= a.ctx[(static_cast<long long>(k) * a.B + b) * a.L + i] != 0 ? (1u << k) : 0u;
+        return bits;
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ bool setup_thresholds(const SelArgs& a, int b, float* lo, float* hi) {
+    bool has_valid = true;
+    if (MODE == MODE_DR) {
+        const uint32_t kmn = a.minmax[2 * b], kmx = a.minmax[2 * b + 1];
+        has_valid = kmn <= kmx;
+        if (threadIdx.x < a.K && has_valid)
+            dr_thresholds(a.level, threadIdx.x, key2f(kmn), key2f(kmx), lo[threadIdx.x], hi[threadIdx.x]);
+        __syncthreads();
+    }
+    return has_valid;
+}
+
+// ---------------------------------------------------------------- min / max over valid gt
+__global__ void __launch_bounds__(THREADS) minmax_kernel(const float* x, const uint8_t* mask, long long L, int chunk,
+                                                         uint32_t* minmax) {
+    const int b = blockIdx.y;
+    const long long start = static_cast<long long>(blockIdx.x) * chunk;
+    const long long end = min(start + chunk, L);
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        if (mask && mask[b * L + i] == 0) continue;
+        const uint32_t k = f2key(x[b * L + i]);
+        mn = min(mn, k);
+        mx = max(mx, k);
+    }
+    for (int o = 16; o; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mn != 0xFFFFFFFFu) atomicMin(&minmax[2 * b], mn);
+        if (mx != 0u || mn != 0xFFFFFFFFu) atomicMax(&minmax[2 * b + 1], mx);
+    }
+}
+
+__global__ void init_minmax_kernel(uint32_t* minmax, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) { minmax[2 * i] = 0xFFFFFFFFu; minmax[2 * i + 1] = 0u; }
+}
+
+// ---------------------------------------------------------------- radix-select histogram pass
+__device__ __forceinline__ void agg_inc(uint32_t* h, bool ok, uint32_t digit, int lane) {
+    if (__ballot_sync(0xffffffffu, ok) == 0u) return;
+    const uint32_t m = __match_any_sync(0xffffffffu, ok ? digit : 0xFFFFFFFFu);
+    if (ok && (__ffs(m) - 1) == lane) atomicAdd(&h[digit], __popc(m));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) sel_hist_kernel(const SelArgs a, int pass) {
+    extern __shared__ uint32_t sm[];
+    const int nrow = a.narr * a.K;
+    uint32_t* h = sm;                                        // [narr*K][256]
+    uint32_t* pref = sm + nrow * 256;                        // [narr*K]
+    float* lo = reinterpret_cast<float*>(pref + nrow);       // [K]
+    float* hi = lo + a.K;                                    // [K]
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < nrow * 256; i += THREADS) h[i] = 0;
+    if (threadIdx.x < nrow) {
+        const int arr = threadIdx.x / a.K, k = threadIdx.x - arr * a.K;
+        pref[threadIdx.x] = a.prefix[row_of(a, arr, b, k)];
+    }
+    __syncthreads();
+    const bool has_valid = setup_thresholds<MODE>(a, b, lo, hi);
+    const int shift = 24 - 8 * pass;
+    const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
+    const long long end = min(start + a.chunk, a.L);
+    for (long long base = start + (threadIdx.x & ~31); base < end; base += THREADS) {
+        const long long i = base + lane;
+        const bool inb = i < end;
+        float p = 0.f, g = 0.f;
+        if (inb) {
+            p = a.pred[b * a.L + i];
+            if (a.narr == 2 || MODE == MODE_DR) g = a.gt[b * a.L + i];
+        }
+        const uint32_t bits = inb ? member_bits<MODE>(a, b, i, g, lo, hi, has_valid) : 0u;
+        if (__ballot_sync(0xffffffffu, bits != 0u) == 0u) continue;
+        const uint32_t kp = f2key(p), kg = f2key(g);
+        for (int k = 0; k < a.K; ++k) {
+            const bool in = (bits >> k) & 1u;
+            {
+                const bool ok = in && (pass == 0 || (kp >> (shift + 8)) == (pref[k] >> (shift + 8)));
+                agg_inc(h + k * 256, ok, (kp >> shift) & 255u, lane);
+            }
+            if (a.narr == 2) {
+                const bool ok = in && (pass == 0 || (kg >> (shift + 8)) == (pref[a.K + k] >> (shift + 8)));
+                agg_inc(h + (a.K + k) * 256, ok, (kg >> shift) & 255u, lane);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t* gh = a.hist + static_cast<long long>(pass) * a.R * 256;
+    for (int i = threadIdx.x; i < nrow * 256; i += THREADS) {
+        const uint32_t v = h[i];
+        if (v) {
+            const int r = i >> 8, arr = r / a.K, k = r - arr * a.K;
+            atomicAdd(&gh[static_cast<long long>(row_of(a, arr, b, k)) * 256 + (i & 255)], v);
+        }
+    }
+}
+
+// one warp per row: locate the bin that holds rank k, extend the prefix
+__global__ void __launch_bounds__(THREADS) sel_scan_kernel(const SelArgs a, int pass) {
+    const int r = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= a.R) return;
+    const uint32_t* h = a.hist + (static_cast<long long>(pass) * a.R + r) * 256;
+    uint32_t c[8], local = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = h[lane * 8 + j]; local += c[j]; }
+    uint32_t incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t k;
+    if (pass == 0) {
+        k = total ? (total - 1) / 2 : 0;  // lower median rank
+        if (lane == 0) a.count[r] = total;
+    } else {
+        k = a.krank[r];
+    }
+    const uint32_t excl = incl - local;
+    const bool mine = total != 0 && k >= excl && k < incl;
+    if (mine) {
+        uint32_t cum = excl;
+        int bin = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (k >= cum + c[j]) { cum += c[j]; bin = j + 1; }
+            else break;
+        }
+        const int shift = 24 - 8 * pass;
+        const uint32_t np = (pass == 0 ? 0u : a.prefix[r]) | (static_cast<uint32_t>(lane * 8 + bin) << shift);
+        a.prefix[r] = np;
+        a.krank[r] = k - cum;
+        if (pass == 3) a.t[r] = key2f(np);
+    }
+    if (total == 0 && lane == 0) {
+        a.prefix[r] = 0;
+        a.krank[r] = 0;
+        if (pass == 3) a.t[r] = 0.f;  // nanmedian of an all-NaN row -> NaN -> 0 (reference :490)
+    }
+}
+
+// ---------------------------------------------------------------- sum |x - t| over members
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) mad_kernel(const SelArgs a) {
+    extern __shared__ uint32_t sm[];
+    const int nrow = a.narr * a.K;
+    float* tt = reinterpret_cast<float*>(sm);  // [nrow]
+    float* lo = tt + nrow;
+    float* hi = lo + a.K;
+    float* red = hi + a.K;                     // [nrow][8 warps]
+    const int b = blockIdx.y;
+    if (threadIdx.x < nrow) {
+        const int arr = threadIdx.x / a.K, k = threadIdx.x - arr * a.K;
+        tt[threadIdx.x] = a.t[row_of(a, arr, b, k)];
+    }
+    __syncthreads();
+    const bool has_valid = setup_thresholds<MODE>(a, b, lo, hi);
+    float accp[MAX_K], accg[MAX_K];
+#pragma unroll
+    for (int j = 0; j < MAX_K; ++j) { accp[j] = 0.f; accg[j] = 0.f; }
+    const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
+    const long long end = min(start + a.chunk, a.L);
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        const float p = a.pred[b * a.L + i];
+        const float g = (a.narr == 2 || MODE == MODE_DR) ? a.gt[b * a.L + i] : 0.f;
+        const uint32_t bits = member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
+        if (!bits) continue;
+#pragma unroll
+        for (int k = 0; k < MAX_K; ++k) {
+            if (k < a.K && ((bits >> k) & 1u)) {
+                accp[k] += fabsf(p - tt[k]);
+                if (a.narr == 2) accg[k] += fabsf(g - tt[a.K + k]);
+            }
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < MAX_K; ++k) {
+        if (k < a.K) {
+            float v = accp[k], w = accg[k];
+            for (int o = 16; o; o >>= 1) {
+                v += __shfl_xor_sync(0xffffffffu, v, o);
+                w += __shfl_xor_sync(0xffffffffu, w, o);
+            }
+            if (lane == 0) {
+                red[k * 8 + warp] = v;
+                if (a.narr == 2) red[(a.K + k) * 8 + warp] = w;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < nrow) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += static_cast<double>(red[threadIdx.x * 8 + w]);
+        const int arr = threadIdx.x / a.K, k = threadIdx.x - arr * a.K;
+        if (v != 0.0) atomicAdd(&a.madsum[row_of(a, arr, b, k)], v);
+    }
+}
+
+// s = sum / (n + 1)  (reference :470,:495)   or   sum / L  (global_normalize :177)
+__global__ void scale_kernel(const SelArgs a, int mean_over_all) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    const float sum = static_cast<float>(a.madsum[r]);
+    a.s[r] = mean_over_all ? sum / static_cast<float>(a.L) : sum / static_cast<float>(a.count[r] + 1u);
+}
+
+// ---------------------------------------------------------------- final pass
+// per pixel: v = sum_k in_k * |pa_k - ga_k| / (#contexts containing the pixel)
+struct FinalArgs {
+    float* aligned_pred;  // optional [B, L] (K == 1)
+    float* aligned_gt;    // optional [B, L]
+    float* dense;         // optional [B, L] dense map (K == 1: in * |pa - ga|)
+    int accumulate;       // add sum / valid count into acc[0] / acc[1]
+    int all_pixels;       // 1: every pixel is a member for the loss (global-normalised L1: mean over all)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) final_kernel(const SelArgs a, const FinalArgs f) {
+    extern __shared__ uint32_t sm[];
+    const int nrow = 2 * a.K;
+    float* tt = reinterpret_cast<float*>(sm);  // [2K]
+    float* inv = tt + nrow;                    // [2K] 1 / (s + 1e-6) is NOT used: keep the division exact
+    float* lo = inv + nrow;
+    float* hi = lo + a.K;
+    __shared__ double red_sum[8];
+    __shared__ unsigned long long red_cnt[8];
+    const int b = blockIdx.y;
+    if (threadIdx.x < nrow) {
+        const int arr = threadIdx.x / a.K, k = threadIdx.x - arr * a.K;
+        tt[threadIdx.x] = a.t[row_of(a, arr, b, k)];
+        inv[threadIdx.x] = a.s[row_of(a, arr, b, k)] + 1e-6f;
+    }
+    __syncthreads();
+    const bool has_valid = setup_thresholds<MODE>(a, b, lo, hi);
+    float sum = 0.f;
+    unsigned long long cnt = 0;
+    const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
+    const long long end = min(start + a.chunk, a.L);
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        const float p = a.pred[b * a.L + i];
+        const float g = a.gt[b * a.L + i];
+        const uint32_t bits = f.all_pixels ? 1u : member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
+        if (a.K == 1) {
+            const float pa = (p - tt[0]) / inv[0];
+            const float ga = (g - tt[1]) / inv[1];
+            if (f.aligned_pred) f.aligned_pred[b * a.L + i] = pa;
+            if (f.aligned_gt) f.aligned_gt[b * a.L + i] = ga;
+            const float e = bits ? fabsf(pa - ga) : 0.f;
+            if (f.dense) f.dense[b * a.L + i] = e;
+            sum += e;
+            cnt += bits ? 1u : 0u;
+        } else if (bits) {
+            float e = 0.f;
+            for (int k = 0; k < a.K; ++k) {
+                if ((bits >> k) & 1u) {
+                    const float pa = (p - tt[k]) / inv[k];
+                    const float ga = (g - tt[a.K + k]) / inv[a.K + k];
+                    e += fabsf(pa - ga);
+                }
+            }
+            sum += e / static_cast<float>(__popc(bits));
+            cnt += 1u;
+        }
+    }
+    if (!f.accumulate) return;
+    double ds = static_cast<double>(sum);
+    for (int o = 16; o; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red_sum[warp] = ds; red_cnt[warp] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        unsigned long long c = 0;
+        for (int w = 0; w < 8; ++w) { s += red_sum[w]; c += red_cnt[w]; }
+        atomicAdd(&a.acc[0], s);
+        atomicAdd(&a.acc[1], static_cast<double>(c));
+    }
+}
+
+// out = num / (den + eps); partials (num, den) exported for the multi-GPU all-reduce
+__global__ void ratio_kernel(const double* acc, double eps, float* out, double* partials, int one_minus) {
+    const double v = acc[0] / (acc[1] + eps);
+    if (out) *out = static_cast<float>(one_minus ? 1.0 - v : v);
+    if (partials) { partials[0] = acc[0]; partials[1] = acc[1]; }
+}
+
+// ---------------------------------------------------------------- workspace carving
+struct Carver {
+    uint8_t* p;
+    size_t used = 0, cap;
+    Carver(void* base, size_t cap_) : p(reinterpret_cast<uint8_t*>(base)), cap(cap_) {}
+    template <typename T>
+    T* take(size_t n) {
+        used = (used + 255) & ~size_t(255);
+        T* r = reinterpret_cast<T*>(p + used);
+        used += n * sizeof(T);
+        return r;
+    }
+};
+
+size_t select_ws_bytes(int B, int K) {
+    const size_t R = static_cast<size_t>(2) * B * K;
+    return 4096 + R * (4 * 256 * 4 + 4 + 4 + 4 + 4 + 8 + 4 + 6 * 256) + static_cast<size_t>(B) * 8 + 256;
+}
+
+int carve(SelArgs& a, void* ws, size_t ws_bytes, size_t* zero_bytes) {
+    const size_t need = select_ws_bytes(a.B, a.K);
+    if (!ws || ws_bytes < need)
+        return set_error(DAD_ERR_WORKSPACE, "loss workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return set_error(DAD_ERR_INVALID, "workspace must be 256-byte aligned");
+    Carver c(ws, ws_bytes);
+    a.R = a.narr * a.B * a.K;
+    // zero-initialised region first
+    a.acc = c.take<double>(2);
+    a.madsum = c.take<double>(a.R);
+    a.hist = c.take<uint32_t>(static_cast<size_t>(4) * a.R * 256);
+    a.prefix = c.take<uint32_t>(a.R);
+    a.krank = c.take<uint32_t>(a.R);
+    a.count = c.take<uint32_t>(a.R);
+    *zero_bytes = c.used;
+    a.t = c.take<float>(a.R);
+    a.s = c.take<float>(a.R);
+    a.minmax = c.take<uint32_t>(static_cast<size_t>(2) * a.B);
+    return DAD_OK;
+}
+
+int pick_chunk(long long L, int B) {
+    // enough CTAs to fill 148 SMs a few times, at least 2048 pixels each
+    long long want = cdivl(L * B, 148LL * 8);
+    if (want < 2048) want = 2048;
+    want = cdivl(want, THREADS) * THREADS;
+    return static_cast<int>(want > L ? cdivl(L, THREADS) * THREADS : want);
+}
+
+template <int MODE>
+int run_select(SelArgs& a, int mean_over_all, cudaStream_t st) {
+    const dim3 grid(static_cast<unsigned>(cdivl(a.L, a.chunk)), a.B);
+    const int nrow = a.narr * a.K;
+    const size_t sm_hist = static_cast<size_t>(nrow) * 256 * 4 + nrow * 4 + 2 * a.K * 4;
+    if (sm_hist > 48 * 1024) {
+        static bool done = false;
+        if (!done) {
+            DAD_CHECK_CUDA(cudaFuncSetAttribute(sel_hist_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            done = true;
+        }
+    }
+    if (MODE == MODE_DR) {
+        init_minmax_kernel<<<cdiv(a.B, 128), 128, 0, st>>>(a.minmax, a.B);
+        minmax_kernel<<<grid, THREADS, 0, st>>>(a.gt, a.mask, a.L, a.chunk, a.minmax);
+        DAD_CHECK_LAUNCH();
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+        sel_hist_kernel<MODE><<<grid, THREADS, sm_hist, st>>>(a, pass);
+        sel_scan_kernel<<<cdiv(a.R, THREADS / 32), THREADS, 0, st>>>(a, pass);
+        DAD_CHECK_LAUNCH();
+    }
+    const size_t sm_mad = static_cast<size_t>(nrow) * 4 + 2 * a.K * 4 + static_cast<size_t>(nrow) * 8 * 4;
+    mad_kernel<MODE><<<grid, THREADS, sm_mad, st>>>(a);
+    scale_kernel<<<cdiv(a.R, 128), 128, 0, st>>>(a, mean_over_all);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+template <int MODE>
+int run_final(const SelArgs& a, const FinalArgs& f, cudaStream_t st) {
+    const dim3 grid(static_cast<unsigned>(cdivl(a.L, a.chunk)), a.B);
+    const size_t sm = static_cast<size_t>(4) * a.K * 4 + 2 * a.K * 4;
+    final_kernel<MODE><<<grid, THREADS, sm, st>>>(a, f);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int ssi_common(int mode, const float* pred, const float* gt, const uint8_t* mask, const uint8_t* ctx, int K, int level,
+               int B, long long L, float* aligned_pred, float* aligned_gt, float* dense, float* out_scalar,
+               double* partials, int mean_over_all, int all_pixels, void* ws, size_t ws_bytes, cudaStream_t st) {
+    DAD_REQUIRE(pred && gt, "loss: null input");
+    DAD_REQUIRE(B > 0 && L > 0, "loss: empty input (B=%d, L=%lld)", B, L);
+    DAD_REQUIRE(K >= 1 && K <= MAX_K, "loss: K=%d contexts unsupported (max %d)", K, MAX_K);
+    SelArgs a{};
+    a.pred = pred; a.gt = gt; a.mask = mask; a.ctx = ctx;
+    a.B = B; a.K = K; a.level = level; a.narr = 2; a.L = L;
+    a.chunk = pick_chunk(L, B);
+    size_t zero_bytes = 0;
+    DAD_TRY(carve(a, ws, ws_bytes, &zero_bytes));
+    DAD_CHECK_CUDA(cudaMemsetAsync(ws, 0, zero_bytes, st));
+    FinalArgs f{};
+    f.aligned_pred = aligned_pred; f.aligned_gt = aligned_gt; f.dense = dense;
+    f.accumulate = (out_scalar || partials) ? 1 : 0;
+    f.all_pixels = all_pixels;
+    if (mode == MODE_MASK) { DAD_TRY(run_select<MODE_MASK>(a, mean_over_all, st)); DAD_TRY(run_final<MODE_MASK>(a, f, st)); }
+    else if (mode == MODE_DR) { DAD_TRY(run_select<MODE_DR>(a, mean_over_all, st)); DAD_TRY(run_final<MODE_DR>(a, f, st)); }
+    else { DAD_TRY(run_select<MODE_CTX>(a, mean_over_all, st)); DAD_TRY(run_final<MODE_CTX>(a, f, st)); }
+    if (f.accumulate) {
+        ratio_kernel<<<1, 1, 0, st>>>(a.acc, all_pixels ? 0.0 : 1e-6, out_scalar, partials, 0);
+        DAD_CHECK_LAUNCH();
+    }
+    return DAD_OK;
+}
+
+// ---------------------------------------------------------------- HDN-DR context export (bool [K,B,L])
+__global__ void __launch_bounds__(THREADS) contexts_dr_kernel(const SelArgs a, uint8_t* out) {
+    __shared__ float lo[MAX_K], hi[MAX_K];
+    const int b = blockIdx.y;
+    const bool has_valid = setup_thresholds<MODE_DR>(a, b, lo, hi);
+    const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
+    const long long end = min(start + a.chunk, a.L);
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        const uint32_t bits = member_bits<MODE_DR>(a, b, i, a.gt[b * a.L + i], lo, hi, has_valid);
+        for (int k = 0; k < a.K; ++k) out[(static_cast<long long>(k) * a.B + b) * a.L + i] = (bits >> k) & 1u;
+    }
+}
+
+// ---------------------------------------------------------------- Sobel gradient loss
+__global__ void __launch_bounds__(THREADS) sobel_kernel(const float* d, int H, int W, double* acc) {
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y0 = blockIdx.y * 64 + (threadIdx.x >> 5) * 8;
+    const float* img = d + static_cast<long long>(b) * H * W;
+    float sum = 0.f;
+    if (x < W) {
+        auto at = [&](int yy, int xx) -> float {
+            return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? img[static_cast<long long>(yy) * W + xx] : 0.f;
+        };
+        // sliding 3-row window down 8 rows
+        float r0[3], r1[3], r2[3];
+        for (int j = 0; j < 3; ++j) { r0[j] = at(y0 - 1, x - 1 + j); r1[j] = at(y0, x - 1 + j); }
+        for (int yy = y0; yy < y0 + 8 && yy < H; ++yy) {
+            for (int j = 0; j < 3; ++j) r2[j] = at(yy + 1, x - 1 + j);
+            const float gx = (r0[2] - r0[0]) + 2.f * (r1[2] - r1[0]) + (r2[2] - r2[0]);
+            const float gy = (r2[0] - r0[0]) + 2.f * (r2[1] - r0[1]) + (r2[2] - r0[2]);
+            sum += expf(-sqrtf(gx * gx + gy * gy + 1e-6f));
+            for (int j = 0; j < 3; ++j) { r0[j] = r1[j]; r1[j] = r2[j]; }
+        }
+    }
+    __shared__ float red[8];
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        atomicAdd(&acc[0], s);
+    }
+}
+
+__global__ void set_den_kernel(double* acc, double den) { acc[1] = den; }
+
+// ---------------------------------------------------------------- feature cosine loss
+// s [B,N,Ds], t [B,N,Dt]; D = min(Ds, Dt); wider tensor nearest-resized along channels.
+__global__ void __launch_bounds__(THREADS) featcos_kernel(const float* s, const float* t, int N, int Ds, int Dt, int D,
+                                                          double* acc) {
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int warp = threadIdx.x >> 5;
+    float st = 0.f, ss = 0.f, tt = 0.f;
+    if (c < D) {
+        // F.interpolate(mode='nearest'): src = min(floor(dst * (in / out)), in - 1), scale in fp32
+        const int cs = (Ds == D) ? c : min(static_cast<int>(floorf(c * (static_cast<float>(Ds) / D))), Ds - 1);
+        const int ct = (Dt == D) ? c : min(static_cast<int>(floorf(c * (static_cast<float>(Dt) / D))), Dt - 1);
+        const float* sp = s + static_cast<long long>(b) * N * Ds + cs;
+        const float* tp = t + static_cast<long long>(b) * N * Dt + ct;
+        for (int n = warp; n < N; n += 8) {
+            const float a = sp[static_cast<long long>(n) * Ds], v = tp[static_cast<long long>(n) * Dt];
+            st = fmaf(a, v, st); ss = fmaf(a, a, ss); tt = fmaf(v, v, tt);
+        }
+    }
+    __shared__ float red[3][8][32];
+    red[0][warp][threadIdx.x & 31] = st; red[1][warp][threadIdx.x & 31] = ss; red[2][warp][threadIdx.x & 31] = tt;
+    __syncthreads();
+    if (warp == 0) {
+        float a = 0.f, q = 0.f, r = 0.f;
+        for (int w = 0; w < 8; ++w) { a += red[0][w][threadIdx.x]; q += red[1][w][threadIdx.x]; r += red[2][w][threadIdx.x]; }
+        float cosv = 0.f;
+        if (c < D) {
+            // F.normalize(eps=1e-12) on both, then cosine_similarity(eps=1e-8) of the unit vectors
+            const float ns = fmaxf(sqrtf(q), 1e-12f), nt = fmaxf(sqrtf(r), 1e-12f);
+            const float dot = a / (ns * nt);
+            const float n1 = sqrtf(q) / ns, n2 = sqrtf(r) / nt;
+            cosv = dot / fmaxf(n1 * n2, 1e-8f);
+        }
+        for (int o = 16; o; o >>= 1) cosv += __shfl_xor_sync(0xffffffffu, cosv, o);
+        if (threadIdx.x == 0) atomicAdd(&acc[0], static_cast<double>(cosv));
+    }
+}
+
+// ---------------------------------------------------------------- plain / hybrid-normalised L1
+__global__ void __launch_bounds__(THREADS) l1_kernel(const float* a, const float* b, long long n, double* acc) {
+    float sum = 0.f;
+    for (long long i = static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * THREADS)
+        sum += fabsf(a[i] - b[i]);
+    __shared__ float red[8];
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        atomicAdd(&acc[0], s);
+    }
+}
+
+constexpr int MAX_SEG = 8;
+struct HybArgs {
+    const float* x[2];   // student, teacher [B, L]
+    int B, nseg;
+    long long L;
+    int chunk;
+    uint32_t* minmax;    // [2][B][2]
+    double* segsum;      // [2][B][nseg]
+    double* segcnt;      // [2][B][nseg]
+    double* segmad;      // [2][B][nseg]
+    double* acc;
+    float* norm_out[2];  // optional normalised maps
+};
+
+// segment bounds, reference op order (:198): bound_i = min + (i / nseg) * range
+__device__ __forceinline__ void seg_bounds(float mn, float mx, int nseg, float* bnd) {
+    const float range = __fsub_rn(mx, mn);
+    for (int i = 0; i <= nseg; ++i)
+        bnd[i] = __fadd_rn(mn, __fmul_rn(static_cast<float>(static_cast<double>(i) / nseg), range));
+}
+
+__global__ void __launch_bounds__(THREADS) hyb_stats_kernel(const HybArgs h, int phase) {
+    // phase 0: per-segment sum and count; phase 1: per-segment sum |d - mean|
+    const int b = blockIdx.y, arr = blockIdx.z;
+    __shared__ float bnd[MAX_SEG + 1], mean[MAX_SEG];
+    __shared__ float red[2][MAX_SEG][8];
+    if (threadIdx.x == 0) {
+        seg_bounds(key2f(h.minmax[(arr * h.B + b) * 2]), key2f(h.minmax[(arr * h.B + b) * 2 + 1]), h.nseg, bnd);
+        for (int s = 0; s < h.nseg; ++s) {
+            const long long o = (static_cast<long long>(arr) * h.B + b) * h.nseg + s;
+            mean[s] = static_cast<float>(h.segsum[o]) / (static_cast<float>(h.segcnt[o]) + 1e-6f);
+        }
+    }
+    __syncthreads();
+    float a0[MAX_SEG], a1[MAX_SEG];
+#pragma unroll
+    for (int s = 0; s < MAX_SEG; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
+    const float* x = h.x[arr] + static_cast<long long>(b) * h.L;
+    const long long start = static_cast<long long>(blockIdx.x) * h.chunk;
+    const long long end = min(start + h.chunk, h.L);
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        const float d = x[i];
+#pragma unroll
+        for (int s = 0; s < MAX_SEG; ++s) {
+            if (s < h.nseg && d >= bnd[s] && d <= bnd[s + 1]) {
+                if (phase == 0) { a0[s] += d; a1[s] += 1.f; }
+                else a0[s] += fabsf(d - mean[s]);
+            }
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < MAX_SEG; ++s) {
+        if (s < h.nseg) {
+            float v0 = a0[s], v1 = a1[s];
+            for (int o = 16; o; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+            if (lane == 0) { red[0][s][warp] = v0; red[1][s][warp] = v1; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < h.nseg) {
+        double v0 = 0.0, v1 = 0.0;
+        for (int w = 0; w < 8; ++w) { v0 += red[0][threadIdx.x][w]; v1 += red[1][threadIdx.x][w]; }
+        const long long o = (static_cast<long long>(arr) * h.B + b) * h.nseg + threadIdx.x;
+        if (phase == 0) { atomicAdd(&h.segsum[o], v0); atomicAdd(&h.segcnt[o], v1); }
+        else atomicAdd(&h.segmad[o], v0);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) hyb_final_kernel(const HybArgs h) {
+    const int b = blockIdx.y;
+    __shared__ float bnd[2][MAX_SEG + 1], mean[2][MAX_SEG], den[2][MAX_SEG];
+    __shared__ int present[2][MAX_SEG];
+    if (threadIdx.x < 2) {
+        const int arr = threadIdx.x;
+        seg_bounds(key2f(h.minmax[(arr * h.B + b) * 2]), key2f(h.minmax[(arr * h.B + b) * 2 + 1]), h.nseg, bnd[arr]);
+        for (int s = 0; s < h.nseg; ++s) {
+            const long long o = (static_cast<long long>(arr) * h.B + b) * h.nseg + s;
+            const float cnt = static_cast<float>(h.segcnt[o]) + 1e-6f;
+            mean[arr][s] = static_cast<float>(h.segsum[o]) / cnt;
+            den[arr][s] = static_cast<float>(h.segmad[o]) / cnt + 1e-6f;
+        }
+    }
+    __syncthreads();
+    float sum = 0.f;
+    const long long start = static_cast<long long>(blockIdx.x) * h.chunk;
+    const long long end = min(start + h.chunk, h.L);
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        float nv[2];
+#pragma unroll
+        for (int arr = 0; arr < 2; ++arr) {
+            const float d = h.x[arr][static_cast<long long>(b) * h.L + i];
+            float v = 0.f;
+            for (int s = 0; s < h.nseg; ++s)  // later segment wins on shared boundaries (:247)
+                if (d >= bnd[arr][s] && d <= bnd[arr][s + 1]) v = (d - mean[arr][s]) / den[arr][s];
+            nv[arr] = v;
+            if (h.norm_out[arr]) h.norm_out[arr][static_cast<long long>(b) * h.L + i] = v;
+        }
+        sum += fabsf(nv[0] - nv[1]);
+    }
+    __shared__ float red[8];
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        atomicAdd(&h.acc[0], s);
+    }
+    (void)present;
+}
+
+}  // namespace
+
+// ================================================================== public (internal C++) API
+size_t loss_workspace_bytes(int B, int K) {
+    const size_t sel = select_ws_bytes(B, K < 1 ? 1 : K);
+    const size_t hyb = 4096 + static_cast<size_t>(B) * (2 * 2 * 4 + 3 * 2 * MAX_SEG * 8) + 1024;
+    return (sel > hyb ? sel : hyb) + 1024;
+}
+
+int masked_shift_and_scale(const float* pred, const float* gt, const uint8_t* mask, int rows, long long L,
+                           float* pred_aligned, float* gt_aligned, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return ssi_common(MODE_MASK, pred, gt, mask, nullptr, 1, 0, rows, L, pred_aligned, gt_aligned, nullptr, nullptr,
+                      nullptr, 0, 0, ws, ws_bytes, st);
+}
+
+int ssi_loss(const float* pred, const float* gt, const uint8_t* mask, int rows, long long L, float* dense_out,
+             float* out_scalar, double* partials, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return ssi_common(MODE_MASK, pred, gt, mask, nullptr, 1, 0, rows, L, nullptr, nullptr, dense_out, out_scalar,
+                      partials, 0, 0, ws, ws_bytes, st);
+}
+
+int hdn_loss_dr(int level, const float* pred, const float* gt, const uint8_t* mask, int B, long long L, float* out_scalar,
+                double* partials, void* ws, size_t ws_bytes, cudaStream_t st) {
+    DAD_REQUIRE(level >= 1 && level <= 4, "hdn_loss_dr: level=%d unsupported (1..4)", level);
+    return ssi_common(MODE_DR, pred, gt, mask, nullptr, (1 << level) - 1, level, B, L, nullptr, nullptr, nullptr,
+                      out_scalar, partials, 0, 0, ws, ws_bytes, st);
+}
+
+int hdn_loss_ctx(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, long long L, float* out_scalar,
+                 double* partials, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return ssi_common(MODE_CTX, pred, gt, nullptr, ctx, K, 0, B, L, nullptr, nullptr, nullptr, out_scalar, partials, 0,
+                      0, ws, ws_bytes, st);
+}
+
+int contexts_dr(int level, const float* gt, const uint8_t* mask, int B, long long L, uint8_t* ctx_out, void* ws,
+                size_t ws_bytes, cudaStream_t st) {
+    DAD_REQUIRE(level >= 1 && level <= 4, "contexts_dr: level=%d unsupported (1..4)", level);
+    DAD_REQUIRE(gt && ctx_out && B > 0 && L > 0, "contexts_dr: bad arguments");
+    SelArgs a{};
+    a.gt = gt; a.pred = gt; a.mask = mask; a.B = B; a.K = (1 << level) - 1; a.level = level; a.narr = 2; a.L = L;
+    a.chunk = pick_chunk(L, B);
+    size_t zero_bytes = 0;
+    DAD_TRY(carve(a, ws, ws_bytes, &zero_bytes));
+    const dim3 grid(static_cast<unsigned>(cdivl(L, a.chunk)), B);
+    init_minmax_kernel<<<cdiv(B, 128), 128, 0, st>>>(a.minmax, B);
+    minmax_kernel<<<grid, THREADS, 0, st>>>(gt, mask, L, a.chunk, a.minmax);
+    contexts_dr_kernel<<<grid, THREADS, 0, st>>>(a, ctx_out);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int grad_loss(const float* depth, int B, int H, int W, float* out_scalar, double* partials, void* ws, size_t ws_bytes,
+              cudaStream_t st) {
+    DAD_REQUIRE(depth && B > 0 && H > 0 && W > 0, "grad_loss: bad arguments");
+    DAD_REQUIRE(ws && ws_bytes >= 256, "grad_loss: workspace too small");
+    double* acc = reinterpret_cast<double*>(ws);
+    DAD_CHECK_CUDA(cudaMemsetAsync(acc, 0, 16, st));
+    const dim3 grid(cdiv(W, 32), cdiv(H, 64), B);
+    sobel_kernel<<<grid, THREADS, 0, st>>>(depth, H, W, acc);
+    set_den_kernel<<<1, 1, 0, st>>>(acc, static_cast<double>(B) * H * W);
+    ratio_kernel<<<1, 1, 0, st>>>(acc, 0.0, out_scalar, partials, 0);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int feat_cos_loss(const float* s, const float* t, int B, int N, int Ds, int Dt, float* out_scalar, double* partials,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+    DAD_REQUIRE(s && t && B > 0 && N > 0 && Ds > 0 && Dt > 0, "feat_cos_loss: bad arguments");
+    DAD_REQUIRE(ws && ws_bytes >= 256, "feat_cos_loss: workspace too small");
+    const int D = Ds < Dt ? Ds : Dt;
+    double* acc = reinterpret_cast<double*>(ws);
+    DAD_CHECK_CUDA(cudaMemsetAsync(acc, 0, 16, st));
+    featcos_kernel<<<dim3(cdiv(D, 32), B), THREADS, 0, st>>>(s, t, N, Ds, Dt, D, acc);
+    set_den_kernel<<<1, 1, 0, st>>>(acc, static_cast<double>(B) * D);
+    ratio_kernel<<<1, 1, 0, st>>>(acc, 0.0, out_scalar, partials, 1);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int distill_loss(const float* student, const float* teacher, int strategy, int num_segments, int B, long long L,
+                 float* out_scalar, double* partials, float* norm_student, float* norm_teacher, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+    DAD_REQUIRE(student && teacher && B > 0 && L > 0, "distill_loss: bad arguments");
+    DAD_REQUIRE(ws && ws_bytes >= loss_workspace_bytes(B, 1), "distill_loss: workspace too small");
+    if (strategy == 0) {  // none
+        double* acc = reinterpret_cast<double*>(ws);
+        DAD_CHECK_CUDA(cudaMemsetAsync(acc, 0, 16, st));
+        const long long n = static_cast<long long>(B) * L;
+        const int grid = static_cast<int>(cdivl(n, THREADS * 8) < 148 * 8 ? cdivl(n, THREADS * 8) : 148 * 8);
+        l1_kernel<<<grid < 1 ? 1 : grid, THREADS, 0, st>>>(student, teacher, n, acc);
+        set_den_kernel<<<1, 1, 0, st>>>(acc, static_cast<double>(n));
+        ratio_kernel<<<1, 1, 0, st>>>(acc, 0.0, out_scalar, partials, 0);
+        DAD_CHECK_LAUNCH();
+        return DAD_OK;
+    }
+    if (strategy == 1) {  // global: (d - median) / (mean|d - median| + 1e-6), then mean L1 over all pixels
+        DAD_TRY(ssi_common(MODE_MASK, student, teacher, nullptr, nullptr, 1, 0, B, L, norm_student, norm_teacher,
+                           nullptr, out_scalar, partials, 1, 1, ws, ws_bytes, st));
+        return DAD_OK;
+    }
+    DAD_REQUIRE(strategy == 2, "distill_loss: unknown strategy %d", strategy);
+    DAD_REQUIRE(num_segments >= 1 && num_segments <= MAX_SEG, "distill_loss: num_segments=%d unsupported (1..%d)",
+                num_segments, MAX_SEG);
+    HybArgs h{};
+    h.x[0] = student; h.x[1] = teacher; h.B = B; h.nseg = num_segments; h.L = L;
+    h.chunk = pick_chunk(L, B);
+    h.norm_out[0] = norm_student; h.norm_out[1] = norm_teacher;
+    Carver c(ws, ws_bytes);
+    h.acc = c.take<double>(2);
+    h.segsum = c.take<double>(static_cast<size_t>(2) * B * num_segments);
+    h.segcnt = c.take<double>(static_cast<size_t>(2) * B * num_segments);
+    h.segmad = c.take<double>(static_cast<size_t>(2) * B * num_segments);
+    const size_t zero_bytes = c.used;
+    h.minmax = c.take<uint32_t>(static_cast<size_t>(4) * B);
+    DAD_CHECK_CUDA(cudaMemsetAsync(ws, 0, zero_bytes, st));
+    const dim3 grid(static_cast<unsigned>(cdivl(L, h.chunk)), B);
+    init_minmax_kernel<<<cdiv(2 * B, 128), 128, 0, st>>>(h.minmax, 2 * B);
+    minmax_kernel<<<grid, THREADS, 0, st>>>(student, nullptr, L, h.chunk, h.minmax);
+    minmax_kernel<<<grid, THREADS, 0, st>>>(teacher, nullptr, L, h.chunk, h.minmax + 2 * B);
+    const dim3 grid2(grid.x, B, 2);
+    hyb_stats_kernel<<<grid2, THREADS, 0, st>>>(h, 0);
+    hyb_stats_kernel<<<grid2, THREADS, 0, st>>>(h, 1);
+    hyb_final_kernel<<<grid, THREADS, 0, st>>>(h);
+    set_den_kernel<<<1, 1, 0, st>>>(h.acc, static_cast<double>(B) * L);
+    ratio_kernel<<<1, 1, 0, st>>>(h.acc, 0.0, out_scalar, partials, 0);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+}  // namespace dad

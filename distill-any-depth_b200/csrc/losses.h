@@ -1,0 +1,29 @@
+// Internal C++ interface of the loss kernels (see losses.cu).  All pointers are device pointers;
+// `ws` is a caller-owned, 256-byte aligned scratch buffer of at least loss_workspace_bytes(B, K).
+#pragma once
+#include "common.h"
+
+namespace dad {
+
+size_t loss_workspace_bytes(int B, int K);
+
+int masked_shift_and_scale(const float* pred, const float* gt, const uint8_t* mask, int rows, long long L,
+                           float* pred_aligned, float* gt_aligned, void* ws, size_t ws_bytes, cudaStream_t st);
+int ssi_loss(const float* pred, const float* gt, const uint8_t* mask, int rows, long long L, float* dense_out,
+             float* out_scalar, double* partials, void* ws, size_t ws_bytes, cudaStream_t st);
+int hdn_loss_dr(int level, const float* pred, const float* gt, const uint8_t* mask, int B, long long L, float* out_scalar,
+                double* partials, void* ws, size_t ws_bytes, cudaStream_t st);
+int hdn_loss_ctx(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, long long L, float* out_scalar,
+                 double* partials, void* ws, size_t ws_bytes, cudaStream_t st);
+int contexts_dr(int level, const float* gt, const uint8_t* mask, int B, long long L, uint8_t* ctx_out, void* ws,
+                size_t ws_bytes, cudaStream_t st);
+int grad_loss(const float* depth, int B, int H, int W, float* out_scalar, double* partials, void* ws, size_t ws_bytes,
+              cudaStream_t st);
+int feat_cos_loss(const float* s, const float* t, int B, int N, int Ds, int Dt, float* out_scalar, double* partials,
+                  void* ws, size_t ws_bytes, cudaStream_t st);
+// strategy: 0 none, 1 global, 2 hybrid/local
+int distill_loss(const float* student, const float* teacher, int strategy, int num_segments, int B, long long L,
+                 float* out_scalar, double* partials, float* norm_student, float* norm_teacher, void* ws,
+                 size_t ws_bytes, cudaStream_t st);
+
+}  // namespace dad

@@ -1,0 +1,286 @@
+"""Host-side mirror of the reference's loss functions (``tools/train_distillation.py:173-707``):
+same names, positional signatures and return conventions, computed by the sm_100a kernels in
+``csrc/losses.cu`` through the C ABI.  No host sync, no per-image Python loop; every function
+returns device tensors.  CUDA tensors only - there is no CPU fallback.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_STRATEGY = {"none": 0, "global": 1, "hybrid": 2, "local": 2}
+_ws_cache = {}
+
+
+def _workspace(device, rows, K):
+    need = int(_lib.load().dad_loss_workspace_bytes(int(rows), int(K)))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)  # one scratch buffer per stream
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the B200 loss path has no CPU fallback")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _mask_u8(m, like, name="mask_valid"):
+    if m is None:
+        return None
+    if m.shape != like.shape:
+        m = m.expand_as(like)
+    if m.dtype == torch.bool:
+        return m.contiguous().view(torch.uint8)
+    return (m != 0).contiguous().view(torch.uint8)
+
+
+def _rows_L(t):
+    if t.dim() < 3:
+        raise ValueError("expected a [B, C, H, W] map")
+    rows = 1
+    for s in t.shape[:-2]:
+        rows *= s
+    return rows, t.shape[-2] * t.shape[-1]
+
+
+def _new_scalar(device):
+    return torch.empty((), dtype=torch.float32, device=device)
+
+
+def _new_partials(device, want):
+    return torch.empty(2, dtype=torch.float64, device=device) if want else None
+
+
+# ------------------------------------------------------------------------------------------ SSI
+def masked_shift_and_scale(depth_preds, depth_gt, mask_valid):
+    """``:449-533`` - per (b, c) lower-median / mean-absolute-deviation alignment.
+    Returns ``(depth_pred_aligned, depth_gt_aligned)``."""
+    p, g = _f32(depth_preds, "depth_preds"), _f32(depth_gt, "depth_gt")
+    rows, L = _rows_L(p)
+    m = _mask_u8(mask_valid, p)
+    pa, ga = torch.empty_like(p), torch.empty_like(g)
+    ws = _workspace(p.device, rows, 1)
+    lib = _lib.load()
+    _lib.check(lib.dad_masked_shift_and_scale(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), rows, L, _lib.ptr(pa),
+                                              _lib.ptr(ga), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+               "masked_shift_and_scale")
+    return pa, ga
+
+
+def masked_l1_loss(preds, target, mask_valid, dense=False):
+    """``:535-542`` (elementwise; kept in torch ops on the device - it is a single fused pass when
+    reached through :class:`SSILoss`)."""
+    e = (preds - target).abs() * mask_valid
+    if dense:
+        return e
+    return e.sum() / (mask_valid.sum() + 1e-6)
+
+
+def _ssi(depth_preds, depth_gt, mask_valid, dense, want_partials=False):
+    p, g = _f32(depth_preds, "depth_preds"), _f32(depth_gt, "depth_gt")
+    rows, L = _rows_L(p)
+    m = _mask_u8(mask_valid, p)
+    ws = _workspace(p.device, rows, 1)
+    lib = _lib.load()
+    dense_out = torch.empty_like(p) if dense else None
+    out = None if dense else _new_scalar(p.device)
+    part = _new_partials(p.device, want_partials and not dense)
+    _lib.check(lib.dad_ssi_loss(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), rows, L, _lib.ptr(dense_out), _lib.ptr(out),
+                                _lib.ptr(part), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "SSILoss")
+    return (dense_out if dense else out), part
+
+
+class SSILoss(nn.Module):
+    """Scale-shift-invariant MAE (``:675-684``); ``window_size`` is stored and unused, as upstream."""
+
+    def __init__(self, window_size=11):
+        super().__init__()
+        self.window_size = window_size
+
+    def forward(self, depth_preds, depth_gt, mask_valid, dense=False):
+        return _ssi(depth_preds, depth_gt, mask_valid, dense)[0]
+
+
+# ------------------------------------------------------------------------------------------ HDN
+def get_contexts_dr(level, depth_gt, mask_valid):
+    """``:544-576`` -> bool ``[2**level - 1, B, 1, H, W]``.  The returned tensor remembers how it was
+    made so :func:`compute_hdn_loss` can take the fused path that never reads it."""
+    g = _f32(depth_gt, "depth_gt")
+    if g.dim() != 4 or g.shape[1] != 1:
+        raise ValueError("get_contexts_dr expects depth_gt of shape [B, 1, H, W]")
+    B, L = g.shape[0], g.shape[2] * g.shape[3]
+    m = _mask_u8(mask_valid, g)
+    K = 2 ** level - 1
+    out = torch.empty((K,) + tuple(g.shape), dtype=torch.uint8, device=g.device)
+    ws = _workspace(g.device, B, K)
+    _lib.check(_lib.load().dad_contexts_dr(level, _lib.ptr(g), _lib.ptr(m), B, L, _lib.ptr(out), _lib.ptr(ws),
+                                           ws.numel(), _lib.stream_ptr()), "get_contexts_dr")
+    ctx = out.view(torch.bool)
+    ctx._dad_dr = (level, depth_gt.data_ptr(), depth_gt._version, tuple(depth_gt.shape),
+                   None if mask_valid is None else (mask_valid.data_ptr(), mask_valid._version), mask_valid)
+    return ctx
+
+
+def _hdn(depth_preds, depth_gt, mask_valid_list, want_partials=False):
+    p, g = _f32(depth_preds, "depth_preds"), _f32(depth_gt, "depth_gt")
+    if p.dim() != 4 or p.shape[1] != 1:
+        raise ValueError("compute_hdn_loss expects maps of shape [B, 1, H, W]")
+    B, L = p.shape[0], p.shape[2] * p.shape[3]
+    lib = _lib.load()
+    out = _new_scalar(p.device)
+    part = _new_partials(p.device, want_partials)
+    tag = getattr(mask_valid_list, "_dad_dr", None)
+    if tag is not None and tag[1] == depth_gt.data_ptr() and tag[2] == depth_gt._version \
+            and tag[3] == tuple(depth_gt.shape) \
+            and (tag[4] is None or tag[4] == (tag[5].data_ptr(), tag[5]._version)):
+        level, m = tag[0], _mask_u8(tag[5], g)
+        ws = _workspace(p.device, B, 2 ** level - 1)
+        _lib.check(lib.dad_hdn_loss_dr(level, _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), B, L, _lib.ptr(out),
+                                       _lib.ptr(part), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "compute_hdn_loss")
+        return out, part
+    ctx = mask_valid_list
+    K = ctx.shape[0]
+    if tuple(ctx.shape[1:]) != tuple(p.shape):
+        raise ValueError("mask_valid_list must be [K, B, 1, H, W]")
+    c8 = _mask_u8(ctx, ctx)
+    ws = _workspace(p.device, B, K)
+    _lib.check(lib.dad_hdn_loss(_lib.ptr(p), _lib.ptr(g), _lib.ptr(c8), K, B, L, _lib.ptr(out), _lib.ptr(part),
+                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "compute_hdn_loss")
+    return out, part
+
+
+def compute_hdn_loss(ssi_loss, depth_preds, depth_gt, mask_valid_list):
+    """``:686-707``.  ``ssi_loss`` is accepted for signature parity (the kernel *is* SSI-MAE)."""
+    return _hdn(depth_preds, depth_gt, mask_valid_list)[0]
+
+
+def hdn_loss_dr(depth_preds, depth_gt, mask_valid=None, level=3, want_partials=False):
+    """Fused ``compute_hdn_loss(SSILoss(), p, g, get_contexts_dr(level, g, mask))`` (training call
+    site ``:1547-1553``) without materialising the contexts."""
+    p, g = _f32(depth_preds, "depth_preds"), _f32(depth_gt, "depth_gt")
+    B, L = p.shape[0], p.shape[2] * p.shape[3]
+    m = _mask_u8(mask_valid, g)
+    out = _new_scalar(p.device)
+    part = _new_partials(p.device, want_partials)
+    ws = _workspace(p.device, B, 2 ** level - 1)
+    _lib.check(_lib.load().dad_hdn_loss_dr(level, _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), B, L, _lib.ptr(out),
+                                           _lib.ptr(part), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "hdn_loss_dr")
+    return (out, part) if want_partials else out
+
+
+def get_contexts_dp(level, depth_gt, mask_valid):
+    raise NotImplementedError("HDN-DP contexts (tools/train_distillation.py:578-644) are outside the hot path "
+                              "(train() only wires 'dr', :1547); build them with the reference and pass the bool "
+                              "tensor to compute_hdn_loss")
+
+
+def get_contexts_ds(level, mask_valid):
+    raise NotImplementedError("HDN-DS contexts (tools/train_distillation.py:646-673) are outside the hot path; "
+                              "pass an explicit [K,B,1,H,W] bool tensor to compute_hdn_loss")
+
+
+# ------------------------------------------------------------------------------------------ Sobel
+def _grad(depth, want_partials=False):
+    d = _f32(depth, "depth")
+    if d.dim() != 4 or d.shape[1] != 1:
+        raise ValueError("gradient_preservation_loss expects [B, 1, H, W]")
+    out, part = _new_scalar(d.device), _new_partials(d.device, want_partials)
+    ws = _workspace(d.device, 1, 1)
+    _lib.check(_lib.load().dad_grad_loss(_lib.ptr(d), d.shape[0], d.shape[2], d.shape[3], _lib.ptr(out),
+                                         _lib.ptr(part), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+               "gradient_preservation_loss")
+    return out, part
+
+
+def gradient_preservation_loss(depth):
+    """``:430-446``."""
+    return _grad(depth)[0]
+
+
+# ------------------------------------------------------------------------------------------ feature cosine
+def _feat(student_features, teacher_features, want_partials=False):
+    s, t = _f32(student_features, "student_features"), _f32(teacher_features, "teacher_features")
+    if s.dim() != 3 or t.dim() != 3 or s.shape[0] != t.shape[0]:
+        raise NotImplementedError("feature_distillation_loss: only [B,N,Ds] vs [B,N,Dt] tensors are on the hot path")
+    if s.shape[1] != t.shape[1]:
+        raise NotImplementedError("feature_distillation_loss: token counts differ; the reference would draw fresh "
+                                  "random projections every call (tools/train_distillation.py:363-377)")
+    out, part = _new_scalar(s.device), _new_partials(s.device, want_partials)
+    ws = _workspace(s.device, 1, 1)
+    _lib.check(_lib.load().dad_feat_cos_loss(_lib.ptr(s), _lib.ptr(t), s.shape[0], s.shape[1], s.shape[2], t.shape[2],
+                                             _lib.ptr(out), _lib.ptr(part), _lib.ptr(ws), ws.numel(),
+                                             _lib.stream_ptr()), "feature_distillation_loss")
+    return out, part
+
+
+def feature_distillation_loss(student_features, teacher_features, device=None):
+    """``:284-428``: tensor branch, or lists averaged over non-None pairs (``:415-428``)."""
+    if isinstance(student_features, (list, tuple)) or isinstance(teacher_features, (list, tuple)):
+        tot, n = None, 0
+        for s, t in zip(student_features, teacher_features):
+            if s is None or t is None:
+                continue
+            v = _feat(s, t)[0]
+            tot = v if tot is None else tot + v
+            n += 1
+        if tot is None:
+            return torch.tensor(0.0, device=device)
+        return tot / max(n, 1)
+    return _feat(student_features, teacher_features)[0]
+
+
+# ------------------------------------------------------------------------------------------ normalised L1
+def _distill(student_depth, teacher_depth, norm_strategy, num_segments=4, want_partials=False, want_norm=False):
+    if norm_strategy not in _STRATEGY:
+        raise ValueError(f"Unknown normalization strategy: {norm_strategy}")
+    s, t = _f32(student_depth, "student_depth"), _f32(teacher_depth, "teacher_depth")
+    if s.shape != t.shape or s.dim() != 4:
+        raise ValueError("distillation_loss expects two [B, C, H, W] maps of equal shape")
+    B, L = s.shape[0], s.shape[1] * s.shape[2] * s.shape[3]
+    out, part = _new_scalar(s.device), _new_partials(s.device, want_partials)
+    ns = torch.empty_like(s) if want_norm else None
+    nt = torch.empty_like(t) if want_norm else None
+    ws = _workspace(s.device, B, 1)
+    _lib.check(_lib.load().dad_distill_loss(_lib.ptr(s), _lib.ptr(t), _STRATEGY[norm_strategy], int(num_segments), B, L,
+                                            _lib.ptr(out), _lib.ptr(part), _lib.ptr(ns), _lib.ptr(nt), _lib.ptr(ws),
+                                            ws.numel(), _lib.stream_ptr()), "distillation_loss")
+    return out, part, ns, nt
+
+
+def distillation_loss(student_depth, teacher_depth, norm_strategy, num_segments=4):
+    """``:271-282``."""
+    return _distill(student_depth, teacher_depth, norm_strategy, num_segments)[0]
+
+
+def global_normalize(depth):
+    """``:173-181``."""
+    return _distill(depth, depth, "global", want_norm=True)[2]
+
+
+def hybrid_normalize(depth, num_segments):
+    """``:217-249``."""
+    return _distill(depth, depth, "hybrid", num_segments, want_norm=True)[2]
+
+
+def local_normalize(depth, num_segments):
+    """``:251-254``."""
+    return hybrid_normalize(depth, num_segments)
+
+
+def normalize_depth(depth, strategy, num_segments=4):
+    """``:256-267``."""
+    if strategy == "global":
+        return global_normalize(depth)
+    if strategy in ("hybrid", "local"):
+        return hybrid_normalize(depth, num_segments)
+    if strategy == "none":
+        return depth
+    raise ValueError(f"Unknown normalization strategy: {strategy}")

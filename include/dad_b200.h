@@ -1,0 +1,126 @@
+/*
+ * dad_b200.h - C ABI of libdad_b200.so: the B200-native (sm_100a) implementation of the
+ * Distill-Any-Depth hot path.
+ *
+ * The reference has no FFI layer: its "operator boundary" is a set of Python signatures
+ * (SURVEY.md 8b).  Each entry point below names the reference symbol it replaces
+ * (paths relative to the reference tree).  The Python host side
+ * (distill-any-depth_b200/{dpt,dam,losses}.py) binds these with ctypes and keeps the reference's
+ * class / function names, argument meaning and error behaviour.
+ *
+ * Conventions
+ *   - every pointer except names / descriptors is a DEVICE pointer owned by the caller;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream); no entry point synchronises the host except dad_model_prepare();
+ *   - no entry point allocates device memory except dad_model_set_weight() / dad_model_prepare();
+ *     scratch space is the caller's `workspace` (256-byte aligned for losses, 1024-byte for forward);
+ *   - returns 0 on success, negative on error (message: dad_last_error(), thread-local);
+ *   - masks / contexts are 1 byte per element (torch.bool layout), non-zero = true;
+ *   - `partials` (optional, may be NULL) receives {numerator, denominator} as two doubles so that
+ *     ranks of a data-parallel job can all-reduce them and form the full-batch loss
+ *     (loss = num / (den + eps); for dad_feat_cos_loss loss = 1 - num / den).
+ */
+#ifndef DAD_B200_H
+#define DAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAD_OK 0
+#define DAD_ERR_INVALID (-1)     /* invalid argument (maps to ValueError / AssertionError) */
+#define DAD_ERR_UNSUPPORTED (-2) /* configuration outside the hot path (NotImplementedError) */
+#define DAD_ERR_CUDA (-3)        /* CUDA runtime / driver error (RuntimeError) */
+#define DAD_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define DAD_MODE_BF16 0 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate / residual / LN / softmax */
+#define DAD_MODE_FP32 1 /* fp32 FFMA verification mode (no tensor cores, no TF32) */
+
+const char* dad_last_error(void);
+/* ABI version of this library (bumped on any signature change). */
+int dad_abi_version(void);
+
+/* ------------------------------------------------------------------ model
+ * Replaces DepthAnythingV2.__init__/forward (distillanydepth/depth_anything_v2/dpt.py:187-225)
+ * and DepthAnything.forward (distillanydepth/modeling/archs/dam/dam.py:396-419): DINOv2 ViT
+ * encoder (dinov2.py:212-321, dinov2_layers/{patch_embed,attention,block,mlp,layer_scale}.py)
+ * feeding DPTHead.forward (dpt.py:150-184, util/blocks.py:29-148). */
+typedef struct dad_model dad_model;
+
+typedef struct dad_model_desc {
+    int embed_dim;       /* 384 / 768 / 1024 (= num_heads * 64)        dinov2.py:339-378 */
+    int depth;           /* 12 / 12 / 24 transformer blocks                              */
+    int num_heads;       /* 6 / 12 / 16                                                  */
+    int taps[4];         /* intermediate_layer_idx                     dpt.py:198-203    */
+    int features;        /* DPT head width                             dpt.py:190        */
+    int out_channels[4]; /* reassemble widths                          dpt.py:191        */
+} dad_model_desc;
+
+int dad_model_create(const dad_model_desc* desc, dad_model** out);
+void dad_model_destroy(dad_model* m);
+/* Copy one fp32 parameter (student state-dict key, e.g. "pretrained.blocks.0.attn.qkv.weight";
+ * nn.Module.load_state_dict, tools/train_distillation.py:771) into the model. */
+int dad_model_set_weight(dad_model* m, const char* name, const float* dev_ptr, int64_t numel, void* stream);
+/* Pack weights for `mode` and build the positional table for (H, W) (interpolate_pos_encoding,
+ * dinov2.py:179-210).  Idempotent; must precede dad_forward for that (mode, H, W). */
+int dad_model_prepare(dad_model* m, int mode, int H, int W, void* stream);
+size_t dad_forward_workspace_bytes(dad_model* m, int B, int H, int W, int mode);
+/* x [B,3,H,W] fp32 NCHW -> depth_out [B,1,H,W] fp32, feat_out [B,(H/14)(W/14),D] fp32 (may be NULL). */
+int dad_forward(dad_model* m, const float* x, int B, int H, int W, int mode, float* depth_out, float* feat_out,
+                void* workspace, size_t workspace_bytes, void* stream);
+/* Test hook: copy a named intermediate (as fp32) into dst during the next forwards
+ * ("tokens", "block0", "block_last", "layer_rn1".."layer_rn4", "path_4", "path_1"); dst = NULL clears. */
+int dad_model_debug_capture(dad_model* m, const char* name, float* dst, int64_t numel);
+
+/* ------------------------------------------------------------------ losses
+ * All maps are fp32 [rows, L] (rows = B*C images, L = H*W pixels). */
+size_t dad_loss_workspace_bytes(int rows, int num_contexts);
+
+/* masked_shift_and_scale(depth_preds, depth_gt, mask_valid)  tools/train_distillation.py:449-533 */
+int dad_masked_shift_and_scale(const float* pred, const float* gt, const uint8_t* mask /*NULL = all valid*/, int rows,
+                               int64_t L, float* pred_aligned, float* gt_aligned, void* workspace,
+                               size_t workspace_bytes, void* stream);
+/* SSILoss.forward(pred, gt, mask, dense) = masked_l1_loss(masked_shift_and_scale(...))  :535-542, :675-684.
+ * dense_out (may be NULL) receives the [rows, L] loss map; out_scalar (may be NULL) the reduced loss. */
+int dad_ssi_loss(const float* pred, const float* gt, const uint8_t* mask, int rows, int64_t L, float* dense_out,
+                 float* out_scalar, double* partials, void* workspace, size_t workspace_bytes, void* stream);
+/* get_contexts_dr(level, depth_gt, mask_valid) -> bool [2^level - 1, B, L]               :544-576 */
+int dad_contexts_dr(int level, const float* gt, const uint8_t* mask, int B, int64_t L, uint8_t* ctx_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* compute_hdn_loss(SSILoss(), pred, gt, get_contexts_dr(level, gt, mask)) fused: contexts are never
+ * materialised.                                                                          :544-576, :686-707 */
+int dad_hdn_loss_dr(int level, const float* pred, const float* gt, const uint8_t* mask, int B, int64_t L,
+                    float* out_scalar, double* partials, void* workspace, size_t workspace_bytes, void* stream);
+/* compute_hdn_loss(SSILoss(), pred, gt, mask_valid_list) with explicit contexts [K, B, L], K <= 21  :686-707 */
+int dad_hdn_loss(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, int64_t L, float* out_scalar,
+                 double* partials, void* workspace, size_t workspace_bytes, void* stream);
+/* gradient_preservation_loss(depth [B,1,H,W])                                            :430-446 */
+int dad_grad_loss(const float* depth, int B, int H, int W, float* out_scalar, double* partials, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* feature_distillation_loss(student [B,N,Ds], teacher [B,N,Dt]) tensor branch, equal N    :284-413 */
+int dad_feat_cos_loss(const float* student, const float* teacher, int B, int N, int Ds, int Dt, float* out_scalar,
+                      double* partials, void* workspace, size_t workspace_bytes, void* stream);
+/* distillation_loss(student, teacher, norm_strategy, num_segments)                        :173-282
+ * strategy: 0 'none', 1 'global', 2 'hybrid' / 'local'.  norm_student / norm_teacher (may be NULL)
+ * receive the normalised maps (global_normalize / hybrid_normalize). */
+int dad_distill_loss(const float* student, const float* teacher, int strategy, int num_segments, int B, int64_t L,
+                     float* out_scalar, double* partials, float* norm_student, float* norm_teacher, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ kernel-level test entry points
+ * out[M,N] (fp32) = A[M,K] (bf16 bits / fp32) * W[N,K]^T through the tcgen05 (mode 0) or FFMA (mode 1)
+ * engine with an optional bias[N]; used by the parity tests to bisect the GEMM engine alone. */
+int dad_gemm(const void* A, const void* W, const float* bias, float* out, int M, int N, int K, int mode, void* stream);
+/* conv3x3 / 1x1 (stride 1, zero padding) on NHWC input [B,H,W,C] with packed weights [Co, taps*Cp]. */
+int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
+                  int Co, int taps, int mode, void* stream);
+/* attention over qkv [B*N, 3*heads*64] (q pre-scaled) -> out [B*N, heads*64]; bf16 bits (mode 0) or fp32. */
+int dad_attention(const void* qkv, void* out, int B, int N, int heads, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAD_B200_H */
