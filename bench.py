@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of the DepthAnythingV2 ViT-L 518x518 forward + SSI / HDN-DR loss
+reductions (BASELINE.json metric) on N B200s, one process per GPU.
+
+  python bench.py --gpus 1 --steps K --warmup W                  # this repo's CUDA path
+  torchrun ... bench.py --gpus N --steps K --warmup W            # N ranks, images sharded by rank (weak scaling)
+  python bench.py --impl reference --gpus N --steps K --warmup W # reference algorithm on the host CPU cores
+                                                                 # (oracle port; rank 0 only)
+
+One "step" = one batch of B synthetic images through forward + SSILoss + fused HDN-DR loss against a
+synthetic teacher map.  `value` times the step with inputs resident in HBM; `e2e` times the same
+step through the public Python API with the images starting in pinned HOST memory (H2D copy of the
+batch and D2H read of the two loss scalars inside the timed region).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec at 518x518 ViT-L fwd+SSI/HDN loss, 1/2/4/8 B200; % of roofline"
+PROF_CLASSES = ["gemm_tc", "gemm_simt", "attention", "layernorm", "elementwise", "loss"]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (BASELINE configs[2]: 32)")
+    ap.add_argument("--encoder", default="vitl", choices=["vits", "vitb", "vitl"])
+    ap.add_argument("--size", type=int, default=518)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"DepthAnythingV2 {a.encoder} {a.size}x{a.size} batch {a.batch}/GPU {a.precision} forward + "
+            f"SSI + HDN-DR(level 3) loss, synthetic images, random-init weights (BASELINE configs[2] + loss)")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ---------------------------------------------------------------------------------- CPU reference arm
+def cpu_step_factory(a, B):
+    """The reference algorithm on the host: oracle forward + SSI + HDN-DR, fp32, all host threads."""
+    import torch
+    import oracle
+    from distill_any_depth_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    kw = synthetic.MODEL_PRESETS[a.encoder]
+    sd = synthetic.make_state_dict(seed=1, **kw)
+    x = synthetic.make_images(B, a.size, a.size, seed=1234)
+    _, gt, _ = synthetic.make_depth_pair(B, a.size, a.size, seed=7)
+    ssi = oracle.SSILoss()
+    full = torch.ones_like(gt, dtype=torch.bool)
+
+    def step():
+        with torch.no_grad():
+            depth, _ = oracle.depth_anything_forward(x, sd, kw["encoder"])
+            l1 = ssi(depth, gt, full)
+            l2 = oracle.compute_hdn_loss(ssi, depth, gt, oracle.get_contexts_dr(3, gt, None))
+        return float(l1), float(l2)
+    return step, torch.get_num_threads()
+
+
+def cpu_baseline(a):
+    step, cores = cpu_step_factory(a, 1)
+    step()
+    best = 1e30
+    for _ in range(2):
+        t = time.perf_counter()
+        step()
+        best = min(best, time.perf_counter() - t)
+    return dict(value=1.0 / best, unit="images/s", cores=cores, kind="port",
+                sample="B=1 of the same workload (oracle fp32 forward + SSI + HDN-DR on host threads), best of 2 after 1 warm-up")
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, cores = cpu_step_factory(a, 1)
+    for _ in range(max(1, min(a.warmup, 2))):
+        step()
+    steps = max(1, min(a.steps, 8))  # bounded sample: B=1 per step, <= 8 steps (a ViT-L step is seconds on CPU)
+    t = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t
+    v = steps / dt
+    line = dict(metric=METRIC, value=v, unit="images/s", n_gpus=a.gpus, steps=steps, warmup=a.warmup,
+                ms_per_step=dt / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload=workload_name(a), note="reference algorithm (oracle port of the PyTorch fp32 path) "
+                            "on the host CPU, B=1 per step"),
+                cpu_baseline=dict(value=v, unit="images/s", cores=cores, kind="port",
+                                  sample=f"{steps} steps of B=1 of the same workload on {cores} host threads"),
+                e2e=dict(value=v, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(s))
+
+
+# ---------------------------------------------------------------------------------- B200 arm
+def run_b200(a):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import distill_any_depth_b200 as d
+    from distill_any_depth_b200 import synthetic, _lib, losses
+    from distill_any_depth_b200.dist import finish_losses
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (impl b200) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    lib.dad_launch_count.restype = ctypes.c_longlong
+    lib.dad_profile_get.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_longlong)]
+
+    B, H = a.batch, a.size
+    kw = synthetic.MODEL_PRESETS[a.encoder]
+    model = d.DepthAnythingV2(**kw)
+    model.load_state_dict(synthetic.make_state_dict(seed=1, **kw), strict=True)
+    model = model.to(dev).eval()
+    model.precision = a.precision
+    x_host = synthetic.make_images(B, H, H, seed=1234 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    _, gt, _ = synthetic.make_depth_pair(B, H, H, seed=7 + rank)
+    gt = gt.to(dev)
+    full = torch.ones_like(gt, dtype=torch.bool)
+    copy_stream = torch.cuda.Stream(dev)
+    x_stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+
+    def losses_of(depth):
+        ssi, p1 = losses._ssi(depth, gt, full, False, want_partials=True)
+        hdn, p2 = losses.hdn_loss_dr(depth, gt, None, 3, want_partials=True)
+        if world > 1:  # full-batch losses: ONE all-reduce of the (num, den) partials
+            out = finish_losses({"ssi": ("ssi", p1), "hdn": ("hdn", p2)})
+            return torch.stack([out["ssi"], out["hdn"]])
+        return torch.stack([ssi, hdn])
+
+    def step_device():
+        depth, _ = model(x_dev)
+        return losses_of(depth)
+
+    def step_e2e(i):
+        buf = x_stage[i & 1]
+        with torch.cuda.stream(copy_stream):  # H2D of this step's batch from pinned host memory
+            buf.copy_(x_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        torch.cuda.current_stream().wait_event(ev)
+        depth, _ = model(buf)
+        return losses_of(depth).cpu()  # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            out = fn(i)
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = torch.tensor([e0.elapsed_time(e1), wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms[0].item(), ms[1].item(), out
+
+    for i in range(max(a.warmup, 3)):
+        step_device()
+        step_e2e(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.dad_launch_count()
+    ms_dev, _, last = timed(lambda i: step_device(), a.steps)
+    launches = (lib.dad_launch_count() - l0)
+    ms_e2e, wall_e2e, last_e2e = timed(step_e2e, a.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- per-kernel-class device times (separate pass so the events do not perturb the timed loops)
+    lib.dad_profile_enable(1)
+    psteps = max(1, min(a.steps, 3))
+    for _ in range(psteps):
+        step_device()
+    torch.cuda.synchronize()
+    prof = {}
+    for ci, name in enumerate(PROF_CLASSES):
+        ms_, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        _lib.check(lib.dad_profile_get(ci, ctypes.byref(ms_), ctypes.byref(work), ctypes.byref(n)))
+        if n.value:
+            prof[name] = dict(ms_per_step=ms_.value / psteps, launches_per_step=n.value / psteps,
+                              work_per_step=work.value / psteps, avg_launch_ms=ms_.value / n.value)
+    lib.dad_profile_enable(0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    imgs = B * world * a.steps
+    value = imgs / ms_dev * 1e3
+    e2e_value = imgs / max(ms_e2e, wall_e2e if world == 1 else ms_e2e) * 1e3
+    gt_ = prof.get("gemm_tc")
+    roofline = None
+    if gt_:
+        # dominant kernel: gemm_tc (tcgen05 GEMM / implicit-GEMM conv).  achieved = algorithmic FLOPs of all its
+        # launches in a step / their summed CUDA-event durations; peak = sustained cuBLAS bf16 (kernel timed
+        # inside a long step), from MEASURED_PEAKS.json.
+        ach = gt_["work_per_step"] / (gt_["ms_per_step"] * 1e-3) / 1e12
+        roofline = dict(bound="tensor", achieved=ach, peak=pk["tf_sustained"], unit="TFLOP/s", frac=ach / pk["tf_sustained"],
+                        traffic=None, kernel="gemm_tc_kernel (all launches of a step)", peak_source=pk["src"] + " sustained bf16",
+                        launches_per_step=gt_["launches_per_step"], avg_launch_ms=gt_["avg_launch_ms"],
+                        share_of_step=gt_["ms_per_step"] / (ms_dev / a.steps))
+    line = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
+                ms_per_step=ms_dev / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=a.precision, data="synthetic",
+                config=dict(workload=workload_name(a), global_batch=B * world, per_gpu_batch=B,
+                            parallelism=f"dp{world} (images sharded by rank; one all-reduce of loss partials per step)",
+                            l2="working set (activations ~9 GB/step at B=32) >> 126 MB L2; no explicit flush",
+                            losses=[float(v) for v in last.cpu()]),
+                e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=int(x_host.numel() * 4),
+                         d2h_bytes_per_step=8, ms_per_step=ms_e2e / a.steps),
+                gpu_launches=int(launches), clocks=sampler.result(), roofline=roofline, kernel_breakdown=prof)
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(FQ) attention_f32_kernel(const float* qkv, flo
 int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, cudaStream_t st) {
     DAD_REQUIRE(qkv && out && B > 0 && N > 0 && heads > 0, "attention: bad arguments");
     const int D = heads * HD;
+    ProfScope prof(PROF_ATTN, 4.0 * B * static_cast<double>(N) * N * D, st);
     if (is_bf16) {
         const dim3 grid(cdiv(N, BQ), heads, B);
         attention_mma_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), N, D);

@@ -19,6 +19,10 @@ typedef __nv_bfloat16 bf16;
 int set_error(int code, const char* fmt, ...);
 const char* last_error();
 int num_sms();
+void profile_enable(int on);
+int profile_get(int cls, double* ms, double* work, long long* launches);
+long long launch_count();
+void debug_label(const char* s);  // no-op unless DAD_DEBUG_SYNC is set
 
 #define DAD_CHECK_CUDA(expr)                                                                          \
     do {                                                                                              \
@@ -46,6 +50,18 @@ int num_sms();
         int _r = (expr);                                                                              \
         if (_r != DAD_OK) return _r;                                                                  \
     } while (0)
+
+// ---- launch counting and optional per-kernel-class device timing (bench.py's roofline numbers)
+enum { PROF_GEMM_TC = 0, PROF_GEMM_SIMT, PROF_ATTN, PROF_LN, PROF_ELEM, PROF_LOSS, PROF_NCLASS };
+// RAII around one (or `launches`) kernel launch(es): always bumps the launch counter; when profiling
+// is enabled it also brackets the launch with CUDA events on `st` and books `work`
+// (algorithmic FLOPs for tensor-bound classes, algorithmic bytes for HBM-bound ones).
+struct ProfScope {
+    int idx;
+    cudaStream_t st;
+    ProfScope(int cls, double work, cudaStream_t stream, int launches = 1);
+    ~ProfScope();
+};
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long long cdivl(long long a, long long b) { return (a + b - 1) / b; }

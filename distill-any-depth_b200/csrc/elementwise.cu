@@ -273,6 +273,7 @@ int grid_for(long long total, int per_block = 256) {
 int patch_im2col(const float* x, void* A, int is_bf16, int B, int H, int W, int Kp, cudaStream_t st) {
     DAD_REQUIRE(H % 14 == 0 && W % 14 == 0 && Kp >= 588, "patch_im2col: bad dims");
     const long long rows = static_cast<long long>(B) * (1 + (H / 14) * (W / 14));
+    ProfScope prof(PROF_ELEM, static_cast<double>(B) * 3 * H * W * 4 + static_cast<double>(rows) * Kp * (is_bf16 ? 2 : 4), st);
     DISPATCH_T(is_bf16, (patch_im2col_kernel<T><<<static_cast<unsigned>(rows), 256, 0, st>>>(x, reinterpret_cast<T*>(A), B, H, W, Kp)));
     DAD_CHECK_LAUNCH();
     return DAD_OK;
@@ -282,6 +283,7 @@ int layernorm(const float* in, const float* w, const float* b, void* out, int is
               int D, int out_period, int in_period, int in_offset, float eps, cudaStream_t st) {
     DAD_REQUIRE(D % 4 == 0 && D <= 2048, "layernorm: D=%d unsupported", D);
     const unsigned grid = static_cast<unsigned>(cdivl(rows, 8));
+    ProfScope prof(PROF_LN, static_cast<double>(rows) * D * (4 + (out ? (is_bf16 ? 2 : 4) : 0) + (out_f32 ? 4 : 0)), st);
     const int vpt = cdiv(D, 128);
 #define LN_LAUNCH(V)                                                                                              \
     DISPATCH_T(is_bf16, (layernorm_kernel<T, V><<<grid, 256, 0, st>>>(in, w, b, reinterpret_cast<T*>(out), out_f32, \
@@ -300,6 +302,7 @@ int bilinear_nhwc(const void* in, void* out, int is_bf16, int B, int Hi, int Wi,
     // ATen: scale = (in - 1) / (out - 1) in fp32 (0 when out == 1)
     const float sh = Ho > 1 ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.f;
     const float sw = Wo > 1 ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.f;
+    ProfScope prof(PROF_ELEM, static_cast<double>(B) * C * (is_bf16 ? 2 : 4) * (static_cast<double>(Hi) * Wi + static_cast<double>(Ho) * Wo), st);
     if (is_bf16) {
         const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
         bilinear_kernel<bf16, 8><<<grid_for(total), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out),
@@ -316,6 +319,7 @@ int bilinear_nhwc(const void* in, void* out, int is_bf16, int B, int Hi, int Wi,
 int im2col_s2(const void* in, void* A, int is_bf16, int B, int H, int W, int C, int Cp, cudaStream_t st) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long rows = static_cast<long long>(B) * Ho * Wo;
+    ProfScope prof(PROF_ELEM, (static_cast<double>(B) * H * W * C + static_cast<double>(rows) * 9 * Cp) * (is_bf16 ? 2 : 4), st);
     DISPATCH_T(is_bf16, (im2col_s2_kernel<T><<<static_cast<unsigned>(rows), 256, 0, st>>>(
                             reinterpret_cast<const T*>(in), reinterpret_cast<T*>(A), B, H, W, C, Cp, Ho, Wo)));
     DAD_CHECK_LAUNCH();
@@ -323,6 +327,7 @@ int im2col_s2(const void* in, void* A, int is_bf16, int B, int H, int W, int C, 
 }
 
 int head1x1(const float* in, const float* w, float bias, float* out, long long P, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(P) * 33 * 4, st);
     head1x1_kernel<<<static_cast<unsigned>(cdivl(P, 256)), 256, 0, st>>>(in, w, bias, out, P);
     DAD_CHECK_LAUNCH();
     return DAD_OK;

@@ -128,6 +128,7 @@ int gemm_simt(const GemmProblem& p, cudaStream_t stream) {
     // grid.y limit is 65535; fold larger M by looping launches
     const int max_rows = 65535 * SBM;
     if (a.M <= max_rows) {
+        ProfScope prof(PROF_GEMM_SIMT, 2.0 * a.M * p.N * (p.conv ? static_cast<double>(p.taps) * p.C : p.K), stream);
         gemm_simt_kernel<<<grid, 256, 0, stream>>>(a);
         DAD_CHECK_LAUNCH();
         return DAD_OK;

@@ -37,6 +37,7 @@ struct TcArgs {
     int tw_log2, th;        // spatial tile (conv): TW = 1 << tw_log2, TH = 128 / TW
     int tiles_x, tiles_y;
     int num_m_tiles, num_n_tiles;
+    double flops;           // algorithmic 2*M*N*K of this launch (host-side bookkeeping only)
 };
 
 template <int BN>
@@ -281,6 +282,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cuda
     }
     const int tiles = a.num_m_tiles * a.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    ProfScope prof(PROF_GEMM_TC, a.flops, stream);
     gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
@@ -325,6 +327,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
                     a.num_k_blocks * BK, p.Kp);
         a.B = p.B; a.H = p.H; a.W = p.W;
         a.M = p.B * p.H * p.W;
+        a.flops = 2.0 * a.M * p.N * (static_cast<double>(p.taps) * p.C);
         // choose the spatial tile (TH x TW = 128) with the least padded area
         long long best = -1;
         for (int l2 = 3; l2 <= 7; ++l2) {
@@ -345,6 +348,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         DAD_REQUIRE(p.M > 0 && p.K > 0 && p.lda >= p.K && p.lda % 8 == 0, "gemm_tc: bad linear dims M=%d K=%d lda=%lld",
                     p.M, p.K, p.lda);
         a.M = p.M;
+        a.flops = 2.0 * p.M * p.N * static_cast<double>(p.K);
         a.num_k_blocks = cdiv(p.K, BK);
         a.num_m_tiles = cdiv(p.M, BM);
         const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};

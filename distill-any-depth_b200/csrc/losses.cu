@@ -482,6 +482,9 @@ int ssi_common(int mode, const float* pred, const float* gt, const uint8_t* mask
     a.chunk = pick_chunk(L, B);
     size_t zero_bytes = 0;
     DAD_TRY(carve(a, ws, ws_bytes, &zero_bytes));
+    // algorithmic bytes: pred + gt fp32 (+ 1-byte mask / K-byte contexts) per pixel
+    ProfScope prof(PROF_LOSS, static_cast<double>(B) * L * (8.0 + (mask ? 1 : 0) + (ctx ? K : 0)), st,
+                   (mode == MODE_DR ? 2 : 0) + 8 + 2 + 1 + ((out_scalar || partials) ? 1 : 0));
     DAD_CHECK_CUDA(cudaMemsetAsync(ws, 0, zero_bytes, st));
     FinalArgs f{};
     f.aligned_pred = aligned_pred; f.aligned_gt = aligned_gt; f.dense = dense;
@@ -770,6 +773,7 @@ int grad_loss(const float* depth, int B, int H, int W, float* out_scalar, double
     double* acc = reinterpret_cast<double*>(ws);
     DAD_CHECK_CUDA(cudaMemsetAsync(acc, 0, 16, st));
     const dim3 grid(cdiv(W, 32), cdiv(H, 64), B);
+    ProfScope prof(PROF_LOSS, static_cast<double>(B) * H * W * 4, st, 3);
     sobel_kernel<<<grid, THREADS, 0, st>>>(depth, H, W, acc);
     set_den_kernel<<<1, 1, 0, st>>>(acc, static_cast<double>(B) * H * W);
     ratio_kernel<<<1, 1, 0, st>>>(acc, 0.0, out_scalar, partials, 0);
@@ -784,6 +788,7 @@ int feat_cos_loss(const float* s, const float* t, int B, int N, int Ds, int Dt, 
     const int D = Ds < Dt ? Ds : Dt;
     double* acc = reinterpret_cast<double*>(ws);
     DAD_CHECK_CUDA(cudaMemsetAsync(acc, 0, 16, st));
+    ProfScope prof(PROF_LOSS, 4.0 * B * N * (static_cast<double>(Ds) + Dt), st, 3);
     featcos_kernel<<<dim3(cdiv(D, 32), B), THREADS, 0, st>>>(s, t, N, Ds, Dt, D, acc);
     set_den_kernel<<<1, 1, 0, st>>>(acc, static_cast<double>(B) * D);
     ratio_kernel<<<1, 1, 0, st>>>(acc, 0.0, out_scalar, partials, 1);
@@ -796,6 +801,12 @@ int distill_loss(const float* student, const float* teacher, int strategy, int n
                  size_t ws_bytes, cudaStream_t st) {
     DAD_REQUIRE(student && teacher && B > 0 && L > 0, "distill_loss: bad arguments");
     DAD_REQUIRE(ws && ws_bytes >= loss_workspace_bytes(B, 1), "distill_loss: workspace too small");
+    if (strategy == 1) {  // global: (d - median) / (mean|d - median| + 1e-6), then mean L1 over all pixels
+        DAD_TRY(ssi_common(MODE_MASK, student, teacher, nullptr, nullptr, 1, 0, B, L, norm_student, norm_teacher,
+                           nullptr, out_scalar, partials, 1, 1, ws, ws_bytes, st));
+        return DAD_OK;
+    }
+    ProfScope prof(PROF_LOSS, static_cast<double>(B) * L * 8, st, strategy == 0 ? 3 : 8);
     if (strategy == 0) {  // none
         double* acc = reinterpret_cast<double*>(ws);
         DAD_CHECK_CUDA(cudaMemsetAsync(acc, 0, 16, st));
@@ -805,11 +816,6 @@ int distill_loss(const float* student, const float* teacher, int strategy, int n
         set_den_kernel<<<1, 1, 0, st>>>(acc, static_cast<double>(n));
         ratio_kernel<<<1, 1, 0, st>>>(acc, 0.0, out_scalar, partials, 0);
         DAD_CHECK_LAUNCH();
-        return DAD_OK;
-    }
-    if (strategy == 1) {  // global: (d - median) / (mean|d - median| + 1e-6), then mean L1 over all pixels
-        DAD_TRY(ssi_common(MODE_MASK, student, teacher, nullptr, nullptr, 1, 0, B, L, norm_student, norm_teacher,
-                           nullptr, out_scalar, partials, 1, 1, ws, ws_bytes, st));
         return DAD_OK;
     }
     DAD_REQUIRE(strategy == 2, "distill_loss: unknown strategy %d", strategy);

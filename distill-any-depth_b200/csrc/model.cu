@@ -7,6 +7,7 @@
 //   mode 0 (bf16)  bf16 K-major weight matrices for the tcgen05 GEMM / implicit-GEMM conv engine
 //   mode 1 (fp32)  the same matrices in fp32 for the FFMA verification engine
 // Activations live in a caller-provided workspace (bump-allocated, no cudaMalloc / sync in forward).
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -44,10 +45,12 @@ struct Arena {    // bump allocator over the caller's workspace (dry run: only s
     size_t cap, used = 0;
     bool dry;
     Arena(void* b, size_t c, bool d) : base(reinterpret_cast<uint8_t*>(b)), cap(c), dry(d) {}
+    bool overflow = false;
     void* take(size_t bytes) {
         used = (used + 1023) & ~size_t(1023);
         void* p = dry ? nullptr : base + used;
         used += bytes;
+        if (!dry && used > cap) { overflow = true; p = nullptr; }
         return p;
     }
 };
@@ -239,6 +242,12 @@ public:
 
     int gemm(int mode, const GemmProblem& p, bool dry, cudaStream_t st) {
         if (dry) return DAD_OK;
+        {
+            char lab[128];
+            snprintf(lab, sizeof(lab), "gemm conv=%d M=%d K=%d N=%d Kp=%d B=%d H=%d W=%d C=%d taps=%d scat=%d", p.conv, p.M,
+                     p.K, p.N, p.Kp, p.B, p.H, p.W, p.C, p.taps, p.epi.scat_k);
+            debug_label(lab);
+        }
         return mode == 0 ? gemm_tc(p, st) : gemm_simt(p, st);
     }
 
@@ -263,19 +272,25 @@ public:
 
     // one FeatureFusionBlock (util/blocks.py:129-146); x0 = upsampled path (may be null), x1 = lateral
     // `lat` / `lat_relu`: the tensor entering the first RCU and its ReLU copy.
-    int fusion(int mode, int r, const void* path, const void* lat, const void* lat_relu, int B, int H, int W, int Ho,
+    int fusion(int mode, int r, bool has_path, const void* path, const void* lat, const void* lat_relu, int B, int H, int W, int Ho,
                int Wo, void** out, Arena& ar, bool dry, cudaStream_t st) {
         const int F = desc.features;
         const size_t es = mode == 0 ? 2 : 4;
         const int bf = mode == 0;
         const size_t n = static_cast<size_t>(B) * H * W * F;
         const std::string q = "depth_head.scratch.refinenet" + std::to_string(r + 1) + ".";
+        // all scratch of this block up front (identical in the dry run), then launch
+        const size_t no = static_cast<size_t>(B) * Ho * Wo * F;
         void* t1 = ar.take(n * es);
+        void* s = has_path ? ar.take(n * es) : nullptr;
+        void* sr = has_path ? ar.take(n * es) : nullptr;
+        void* u = ar.take(n * es);
+        void* res = ar.take(no * es);
+        void* tmp = ar.take((mode == 0 ? n : no) * es);  // bf16: 1x1 conv output at low res; fp32: upsampled map
+        DAD_REQUIRE(!ar.overflow, "forward: workspace arena overflow in fusion block %d", r + 1);
         const void* sum = lat;
         const void* sum_relu = lat_relu;
-        if (path) {  // output = path + RCU1(lat)
-            void* s = ar.take(n * es);
-            void* sr = ar.take(n * es);
+        if (has_path) {  // output = path + RCU1(lat)
             Epilogue e1; e1.bias = P(q + "resConfUnit1.conv1.bias"); e1.act = ACT_RELU; e1.out = t1; e1.out_bf16 = bf;
             DAD_TRY(conv(mode, lat_relu, B, H, W, F, rcu[r][0][0], 9, e1, dry, st));
             Epilogue e2; e2.bias = P(q + "resConfUnit1.conv2.bias"); e2.res1 = lat; e2.res1_bf16 = bf; e2.res2 = path;
@@ -283,7 +298,6 @@ public:
             DAD_TRY(conv(mode, t1, B, H, W, F, rcu[r][0][1], 9, e2, dry, st));
             sum = s; sum_relu = sr;
         }
-        void* u = ar.take(n * es);
         {
             Epilogue e1; e1.bias = P(q + "resConfUnit2.conv1.bias"); e1.act = ACT_RELU; e1.out = t1; e1.out_bf16 = bf;
             DAD_TRY(conv(mode, sum_relu, B, H, W, F, rcu[r][1][0], 9, e1, dry, st));
@@ -291,21 +305,19 @@ public:
             e2.out_bf16 = bf;
             DAD_TRY(conv(mode, t1, B, H, W, F, rcu[r][1][1], 9, e2, dry, st));
         }
-        const size_t no = static_cast<size_t>(B) * Ho * Wo * F;
-        void* res = ar.take(no * es);
         Epilogue eo; eo.bias = P(q + "out_conv.bias"); eo.out_bf16 = bf;
         if (mode == 0) {
             // 1x1 conv commutes with bilinear resampling (both linear; weights sum to 1): conv at the low
             // resolution (4x fewer FLOPs), then resample.  fp32 mode keeps the reference order.
-            void* lo = ar.take(n * es);
-            eo.out = lo;
+            eo.out = tmp;
             DAD_TRY(conv(mode, u, B, H, W, F, out_conv[r], 1, eo, dry, st));
-            if (!dry) DAD_TRY(bilinear_nhwc(lo, res, bf, B, H, W, Ho, Wo, F, st));
+            debug_label("fusion bilinear (bf16 order)");
+            if (!dry) DAD_TRY(bilinear_nhwc(tmp, res, bf, B, H, W, Ho, Wo, F, st));
         } else {
-            void* up = ar.take(no * es);
-            if (!dry) DAD_TRY(bilinear_nhwc(u, up, bf, B, H, W, Ho, Wo, F, st));
+            debug_label("fusion bilinear (reference order)");
+            if (!dry) DAD_TRY(bilinear_nhwc(u, tmp, bf, B, H, W, Ho, Wo, F, st));
             eo.out = res;
-            DAD_TRY(conv(mode, up, B, Ho, Wo, F, out_conv[r], 1, eo, dry, st));
+            DAD_TRY(conv(mode, tmp, B, Ho, Wo, F, out_conv[r], 1, eo, dry, st));
         }
         *out = res;
         return DAD_OK;
@@ -349,7 +361,9 @@ public:
         void* hid = ar.take(M * 4 * Dm * es);
         void* tapbuf[4];
         for (int j = 0; j < 4; ++j) tapbuf[j] = ar.take(Mp * Dm * es);
+        DAD_REQUIRE(!ar.overflow, "forward: workspace arena overflow (encoder)");
         if (!dry) {
+            debug_label("patch_im2col");
             DAD_TRY(patch_im2col(x, ape, bf, B, H, W, PATCH_KP, st));
             Epilogue e; e.rowtab = pos_tables[std::make_pair(H, W)]; e.rowtab_period = T; e.out = xres;
             DAD_TRY(linear(mode, ape, M, PATCH_KP, patch, e, dry, st));
@@ -357,12 +371,15 @@ public:
             int tj = 0;
             for (int i = 0; i < L; ++i) {
                 const std::string b = p + "blocks." + std::to_string(i) + ".";
+                debug_label(("block " + std::to_string(i) + " ln/attn").c_str());
                 DAD_TRY(layernorm(xres, P(b + "norm1.weight"), P(b + "norm1.bias"), ln, bf, nullptr, M, Dm, 1, 1, 0, LN_EPS, st));
                 Epilogue eq; eq.bias = bqkv_scaled + static_cast<long long>(i) * 3 * Dm; eq.out = qkvb; eq.out_bf16 = bf;
                 DAD_TRY(linear(mode, ln, M, Dm, qkv[i], eq, dry, st));
+                debug_label(("block " + std::to_string(i) + " attention").c_str());
                 DAD_TRY(attention(qkvb, att, bf, B, T, heads, st));
                 Epilogue ep; ep.bias = P(b + "attn.proj.bias"); ep.gamma = P(b + "ls1.gamma"); ep.res1 = xres; ep.out = xres;
                 DAD_TRY(linear(mode, att, M, Dm, proj[i], ep, dry, st));
+                debug_label(("block " + std::to_string(i) + " ln2").c_str());
                 DAD_TRY(layernorm(xres, P(b + "norm2.weight"), P(b + "norm2.bias"), ln, bf, nullptr, M, Dm, 1, 1, 0, LN_EPS, st));
                 Epilogue e1; e1.bias = P(b + "mlp.fc1.bias"); e1.act = ACT_GELU; e1.out = hid; e1.out_bf16 = bf;
                 DAD_TRY(linear(mode, ln, M, Dm, fc1[i], e1, dry, st));
@@ -372,6 +389,7 @@ public:
                 if (i == L - 1) DAD_TRY(capture("block_last", xres, false, M * Dm, st));
                 if (tj < 4 && i == desc.taps[tj]) {
                     // final LayerNorm on the tapped residual, cls row dropped (dinov2.py:310-312)
+                    debug_label("tap layernorm");
                     DAD_TRY(layernorm(xres, P(p + "norm.weight"), P(p + "norm.bias"), tapbuf[tj], bf,
                                       (tj == 3) ? feat_out : nullptr, Mp, Dm, np, T, 1, LN_EPS, st));
                     ++tj;
@@ -403,6 +421,7 @@ public:
                 const long long rows = static_cast<long long>(B) * hs[3] * wsz[3];
                 void* col = ar.take(rows * 9 * Cp * es);
                 rj = ar.take(rows * oc[3] * es);
+                debug_label("im2col_s2");
                 if (!dry) DAD_TRY(im2col_s2(pj, col, bf, B, ph, pw, oc[3], Cp, st));
                 Epilogue e3; e3.bias = P(h + "resize_layers.3.bias"); e3.out = rj; e3.out_bf16 = bf;
                 DAD_TRY(linear(mode, col, rows, 9 * Cp, resize3, e3, dry, st));
@@ -410,15 +429,16 @@ public:
             const size_t n = static_cast<size_t>(B) * hs[j] * wsz[j] * F;
             lrn[j] = ar.take(n * es);
             lrn_relu[j] = ar.take(n * es);
+            DAD_REQUIRE(!ar.overflow, "forward: workspace arena overflow (reassemble %d)", j);
             Epilogue er; er.out = lrn[j]; er.out_bf16 = bf; er.out_relu = lrn_relu[j];
             DAD_TRY(conv(mode, rj, B, hs[j], wsz[j], oc[j], layer_rn[j], 9, er, dry, st));
             if (!dry) DAD_TRY(capture(("layer_rn" + std::to_string(j + 1)).c_str(), lrn[j], bf, n, st));
         }
         void *p4, *p3, *p2, *p1;
-        DAD_TRY(fusion(mode, 3, nullptr, lrn[3], lrn_relu[3], B, hs[3], wsz[3], hs[2], wsz[2], &p4, ar, dry, st));
-        DAD_TRY(fusion(mode, 2, p4, lrn[2], lrn_relu[2], B, hs[2], wsz[2], hs[1], wsz[1], &p3, ar, dry, st));
-        DAD_TRY(fusion(mode, 1, p3, lrn[1], lrn_relu[1], B, hs[1], wsz[1], hs[0], wsz[0], &p2, ar, dry, st));
-        DAD_TRY(fusion(mode, 0, p2, lrn[0], lrn_relu[0], B, hs[0], wsz[0], 2 * hs[0], 2 * wsz[0], &p1, ar, dry, st));
+        DAD_TRY(fusion(mode, 3, false, nullptr, lrn[3], lrn_relu[3], B, hs[3], wsz[3], hs[2], wsz[2], &p4, ar, dry, st));
+        DAD_TRY(fusion(mode, 2, true, p4, lrn[2], lrn_relu[2], B, hs[2], wsz[2], hs[1], wsz[1], &p3, ar, dry, st));
+        DAD_TRY(fusion(mode, 1, true, p3, lrn[1], lrn_relu[1], B, hs[1], wsz[1], hs[0], wsz[0], &p2, ar, dry, st));
+        DAD_TRY(fusion(mode, 0, true, p2, lrn[0], lrn_relu[0], B, hs[0], wsz[0], 2 * hs[0], 2 * wsz[0], &p1, ar, dry, st));
         const int H1 = 2 * hs[0], W1 = 2 * wsz[0];
         if (!dry) {
             DAD_TRY(capture("path_4", p4, bf, static_cast<long long>(B) * hs[2] * wsz[2] * F, st));
@@ -429,6 +449,12 @@ public:
         Epilogue eo1; eo1.bias = P(s + "output_conv1.bias"); eo1.out = o1; eo1.out_bf16 = bf;
         DAD_TRY(conv(mode, p1, B, H1, W1, F, output_conv1, 9, eo1, dry, st));
         void* up = ar.take(static_cast<size_t>(B) * H * W * F2 * es);
+        if (!dry && getenv("DAD_DEBUG_SYNC"))
+            fprintf(stderr, "dad[debug]: ws=%p bytes=%zu used=%zu o1=%p up=%p (H1=%d W1=%d H=%d W=%d F2=%d es=%zu)\n", ws,
+                    ws_bytes, ar.used, o1, up, H1, W1, H, W, F2, es);
+        float* t32 = mode == 1 ? reinterpret_cast<float*>(ar.take(static_cast<size_t>(B) * H * W * 32 * 4)) : nullptr;
+        DAD_REQUIRE(!ar.overflow, "forward: workspace arena overflow (head)");
+        debug_label("head bilinear");
         if (!dry) DAD_TRY(bilinear_nhwc(o1, up, bf, B, H1, W1, H, W, F2, st));
         if (mode == 0) {
             // conv3x3 -> ReLU -> conv1x1 -> ReLU (-> F.relu) fused in the GEMM epilogue
@@ -436,7 +462,6 @@ public:
             eh.head_b = head_bias_host; eh.head_out = depth_out;
             DAD_TRY(conv(mode, up, B, H, W, F2, output_conv2_0, 9, eh, dry, st));
         } else {
-            float* t32 = reinterpret_cast<float*>(ar.take(static_cast<size_t>(B) * H * W * 32 * 4));
             Epilogue eh; eh.bias = P(s + "output_conv2.0.bias"); eh.act = ACT_RELU; eh.out = t32;
             DAD_TRY(conv(mode, up, B, H, W, F2, output_conv2_0, 9, eh, dry, st));
             if (!dry) DAD_TRY(head1x1(t32, P(s + "output_conv2.2.weight"), head_bias_host, depth_out,

@@ -10,6 +10,7 @@ Forward-only: outputs are detached (training backward is out of scope, SURVEY.md
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -213,6 +214,7 @@ class _NativeDepthModel(nn.Module):
                 _lib.check(lib.dad_model_prepare(self._handle, mode, H, W, st), "dad_model_prepare")
                 self._prepared.add((mode, H, W))
             need = int(lib.dad_forward_workspace_bytes(self._handle, B, H, W, mode))
+            need += int(os.environ.get("DAD_WS_EXTRA_MB", "0")) << 20  # debugging aid
             if need == 0:
                 _lib.check(-1, "dad_forward_workspace_bytes")
             if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
