@@ -64,6 +64,15 @@ int dad_gemm(const void* A, const void* W, const float* bias, float* out, int M,
     return mode == 0 ? dad::gemm_tc(p, ST(stream)) : dad::gemm_simt(p, ST(stream));
 }
 
+int dad_gemm_ex(const void* A, const void* W, const float* bias, const float* gamma, const void* res, int res_bf16,
+                void* out, int out_bf16, int act, int M, int N, int K, int mode, void* stream) {
+    dad::GemmProblem p;
+    p.A = A; p.M = M; p.K = K; p.lda = K; p.Wt = W; p.N = N; p.Kp = K;
+    p.epi.bias = bias; p.epi.gamma = gamma; p.epi.res1 = res; p.epi.res1_bf16 = res_bf16; p.epi.act = act;
+    p.epi.out = out; p.epi.out_bf16 = out_bf16; p.epi.ldc = N;
+    return mode == 0 ? dad::gemm_tc(p, ST(stream)) : dad::gemm_simt(p, ST(stream));
+}
+
 int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
                   int Co, int taps, int mode, void* stream) {
     dad::GemmProblem p;

@@ -33,15 +33,55 @@ __device__ __forceinline__ void store4_bf16(bf16* base, long long off, const flo
     *reinterpret_cast<uint2*>(base + off) = u;
 }
 
-// grow: logical A-row index (token / input pixel); orow: output row index.
-__device__ __forceinline__ void epilogue_store4(const Epilogue& e, int N, long long grow, long long orow,
-                                                int col, float (&v)[4]) {
-    int bcol = col;
+// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) with fast exp / reciprocal: used when the
+// result is rounded to bf16 anyway (bf16 ulp 4e-3 relative); fp32 outputs use erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+// The epilogue of one (row, 4 columns) group is split in two so that callers can issue the global
+// loads of several groups (residuals / row table) before any dependent math or store:
+//   epilogue_prefetch : output offset + residual / table loads
+//   epilogue_finish   : bias -> activation -> LayerScale -> + table -> + residuals -> stores
+// KIND specialises the hot encoder epilogues at compile time (small code, no dead branches);
+// EK_GENERIC evaluates every option at run time.
+enum { EK_GENERIC = 0, EK_BIAS_BF16 = 1, EK_GELU_BF16 = 2, EK_RES_F32 = 3,
+       EK_GENERIC_NOGELU = 4 /* run-time generic without the GELU code (tensor-core engine: fc1 is EK_GELU_BF16) */ };
+
+// which specialised kind (if any) computes exactly what `e` asks for
+inline int epilogue_kind(const Epilogue& e) {
+    if (e.scat_k || e.rowtab || e.res2 || e.out_relu || e.head_out || !e.out || !e.bias) return EK_GENERIC;
+    if (e.out_bf16 && !e.gamma && !e.res1 && e.act == ACT_NONE) return EK_BIAS_BF16;
+    if (e.out_bf16 && !e.gamma && !e.res1 && e.act == ACT_GELU) return EK_GELU_BF16;
+    if (!e.out_bf16 && e.gamma && e.res1 && !e.res1_bf16 && e.act == ACT_NONE) return EK_RES_F32;
+    return EK_GENERIC;
+}
+
+struct EpiPre {
     long long off;
-    if (e.scat_k) {
+    int bcol;
+    bool skip;
+    float r1[4], r2[4], tab[4];
+};
+
+// grow: logical A-row index (token / input pixel); orow: output row index.
+template <int KIND = EK_GENERIC>
+__device__ __forceinline__ void epilogue_prefetch(const Epilogue& e, int N, long long grow, long long orow, int col,
+                                                  EpiPre& p) {
+    constexpr bool G = KIND == EK_GENERIC || KIND == EK_GENERIC_NOGELU;
+    p.bcol = col;
+    p.skip = false;
+    if (G && e.scat_k) {
         const int kk = col / e.scat_CoP;
         const int co = col - kk * e.scat_CoP;
-        if (co >= e.scat_Co) return;
+        if (co >= e.scat_Co) { p.skip = true; return; }
         const int ky = kk / e.scat_k, kx = kk - ky * e.scat_k;
         const int hw = e.scat_H * e.scat_W;
         const int b = static_cast<int>(grow / hw);
@@ -50,54 +90,76 @@ __device__ __forceinline__ void epilogue_store4(const Epilogue& e, int N, long l
         const long long opix =
             (static_cast<long long>(b) * (e.scat_k * e.scat_H) + (e.scat_k * y + ky)) * (e.scat_k * e.scat_W) +
             (e.scat_k * x + kx);
-        off = opix * e.ldc + co;
-        bcol = co;
+        p.off = opix * e.ldc + co;
+        p.bcol = co;
     } else {
-        off = orow * e.ldc + col;
+        p.off = orow * e.ldc + col;
     }
-    if (e.bias) {
-        const float4 b4 = *reinterpret_cast<const float4*>(e.bias + bcol);
+    if (G && e.rowtab) {
+        const long long tr = grow % e.rowtab_period;
+        const float4 t4 = *reinterpret_cast<const float4*>(e.rowtab + tr * N + col);
+        p.tab[0] = t4.x; p.tab[1] = t4.y; p.tab[2] = t4.z; p.tab[3] = t4.w;
+    }
+    if (G ? (e.res1 != nullptr) : (KIND == EK_RES_F32)) load4(e.res1, p.off, G ? e.res1_bf16 : 0, p.r1);
+    if (G && e.res2) load4(e.res2, p.off, e.res2_bf16, p.r2);
+}
+
+template <int KIND = EK_GENERIC>
+__device__ __forceinline__ void epilogue_finish(const Epilogue& e, const EpiPre& p, float (&v)[4]) {
+    constexpr bool G = KIND == EK_GENERIC || KIND == EK_GENERIC_NOGELU;
+    if (G && p.skip) return;
+    if (G ? (e.bias != nullptr) : true) {
+        const float4 b4 = *reinterpret_cast<const float4*>(e.bias + p.bcol);
         v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
     }
-    if (e.act == ACT_GELU) {
+    const int act = G ? e.act : (KIND == EK_GELU_BF16 ? ACT_GELU : ACT_NONE);
+    const bool obf = G ? (e.out_bf16 != 0) : (KIND != EK_RES_F32);
+    if (KIND != EK_GENERIC_NOGELU && act == ACT_GELU) {
+        if (obf) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
-    } else if (e.act == ACT_RELU) {
+            for (int i = 0; i < 4; ++i) v[i] = gelu_fast(v[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
+        }
+    } else if (act == ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
     }
-    if (e.gamma) {
-        const float4 g4 = *reinterpret_cast<const float4*>(e.gamma + bcol);
+    if (G ? (e.gamma != nullptr) : (KIND == EK_RES_F32)) {
+        const float4 g4 = *reinterpret_cast<const float4*>(e.gamma + p.bcol);
         v[0] *= g4.x; v[1] *= g4.y; v[2] *= g4.z; v[3] *= g4.w;
     }
-    if (e.rowtab) {
-        const long long tr = grow % e.rowtab_period;
-        const float4 t4 = *reinterpret_cast<const float4*>(e.rowtab + tr * N + col);
-        v[0] += t4.x; v[1] += t4.y; v[2] += t4.z; v[3] += t4.w;
-    }
-    if (e.res1) {
-        float r[4];
-        load4(e.res1, off, e.res1_bf16, r);
+    if (G && e.rowtab) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] += r[i];
+        for (int i = 0; i < 4; ++i) v[i] += p.tab[i];
     }
-    if (e.res2) {
-        float r[4];
-        load4(e.res2, off, e.res2_bf16, r);
+    if (G ? (e.res1 != nullptr) : (KIND == EK_RES_F32)) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] += r[i];
+        for (int i = 0; i < 4; ++i) v[i] += p.r1[i];
     }
-    if (e.out) {
-        if (e.out_bf16) store4_bf16(reinterpret_cast<bf16*>(e.out), off, v);
-        else *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off) = make_float4(v[0], v[1], v[2], v[3]);
+    if (G && e.res2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] += p.r2[i];
     }
-    if (e.out_relu) {
+    if (G ? (e.out != nullptr) : true) {
+        if (obf) store4_bf16(reinterpret_cast<bf16*>(e.out), p.off, v);
+        else *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + p.off) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (G && e.out_relu) {
         float r[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) r[i] = fmaxf(v[i], 0.f);
-        if (e.out_bf16) store4_bf16(reinterpret_cast<bf16*>(e.out_relu), off, r);
-        else *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out_relu) + off) = make_float4(r[0], r[1], r[2], r[3]);
+        if (obf) store4_bf16(reinterpret_cast<bf16*>(e.out_relu), p.off, r);
+        else *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out_relu) + p.off) = make_float4(r[0], r[1], r[2], r[3]);
     }
+}
+
+__device__ __forceinline__ void epilogue_store4(const Epilogue& e, int N, long long grow, long long orow, int col,
+                                                float (&v)[4]) {
+    EpiPre p;
+    epilogue_prefetch<EK_GENERIC>(e, N, grow, orow, col, p);
+    epilogue_finish<EK_GENERIC>(e, p, v);
 }
 
 }  // namespace dad

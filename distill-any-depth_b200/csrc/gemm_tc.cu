@@ -5,7 +5,8 @@
 //                      SWIZZLE_128B, through a STAGES-deep mbarrier ring
 //   warp 1 (one lane)  tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16, fp32 accumulate in TMEM);
 //                      tcgen05.commit frees smem stages and publishes finished accumulators
-//   warps 2-5          epilogue: tcgen05.ld (32 lanes x 32 columns) -> fused epilogue -> global
+//   warps 2-9          epilogue: tcgen05.ld (32 lanes x 32 columns) -> smem transpose -> fused epilogue ->
+//                      global, two warps per TMEM lane quarter (one column half each)
 // TMEM holds two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.
 //
@@ -26,7 +27,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quarter (column halves)
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int STG_LD = 20;        // floats per staged 16-column row: 16-byte aligned, (near) conflict-free float4 access
 
 struct TcArgs {
     Epilogue epi;
@@ -46,10 +49,11 @@ struct Cfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                      NUM_EPI_WARPS * 32 * STG_LD * 4 /*epilogue staging*/;
 };
 
-template <int BN>
+template <int BN, int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcArgs g) {
@@ -81,7 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(&tfull[i], 1);
-                ptx::mbar_init(&tempty[i], 128);
+                ptx::mbar_init(&tempty[i], 32 * NUM_EPI_WARPS);
             }
             ptx::fence_barrier_init();
         }
@@ -164,64 +168,96 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ---------------------------------------------------- epilogue (warps 2..5)
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const int r = quarter * 32 + lane;
+        // ---------------------------------------------------- epilogue (warps 2..9)
+        // TMEM -> registers (thread = row, 32 columns) -> padded smem transpose -> (row, 4 columns)
+        // groups: each global access of a warp covers 4 rows x 128 contiguous bytes.  Two warps share a
+        // TMEM lane quarter and drain one half of the tile's columns each.
+        const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;      // column half
+        float* stg = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256) + (warp - 2) * (32 * STG_LD);
+        const int tw_mask = (1 << g.tw_log2) - 1;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mt = tile / g.num_n_tiles;
             const int n0 = (tile - mt * g.num_n_tiles) * BN;
-            long long grow;
-            bool valid;
+            int cb = 0, cy0 = 0, cx0 = 0;
             if (g.conv) {
                 const int per_img = g.tiles_x * g.tiles_y;
-                const int b = mt / per_img;
-                const int rr = mt - b * per_img;
+                cb = mt / per_img;
+                const int rr = mt - cb * per_img;
                 const int ty = rr / g.tiles_x;
-                const int y = ty * g.th + (r >> g.tw_log2);
-                const int x = ((rr - ty * g.tiles_x) << g.tw_log2) + (r & ((1 << g.tw_log2) - 1));
-                valid = (y < g.H) && (x < g.W);
-                grow = (static_cast<long long>(b) * g.H + y) * g.W + x;
-            } else {
-                grow = static_cast<long long>(mt) * BM + r;
-                valid = grow < g.M;
+                cy0 = ty * g.th;
+                cx0 = (rr - ty * g.tiles_x) << g.tw_log2;
             }
+            // logical output row of tile row r (and whether it exists)
+            auto row_of = [&](int r, long long& grow) -> bool {
+                if (g.conv) {
+                    const int y = cy0 + (r >> g.tw_log2), x = cx0 + (r & tw_mask);
+                    grow = (static_cast<long long>(cb) * g.H + y) * g.W + x;
+                    return (y < g.H) && (x < g.W);
+                }
+                grow = static_cast<long long>(mt) * BM + r;
+                return grow < g.M;
+            };
             ptx::mbar_wait(&tfull[as], aphase);
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-            if (g.epi.head_out != nullptr) {
-                if constexpr (BN == 32) {
+            if (KIND == EK_GENERIC_NOGELU && g.epi.head_out != nullptr) {
+                if constexpr (BN == 32 && KIND == EK_GENERIC_NOGELU) {  // fused output head: relu(dot(relu(acc + b1), w2) + b2), one row per thread
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(t_row, v);
                     ptx::tmem_ld_wait();
-                    float s = 0.f;
+                    float sacc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float a = __uint_as_float(v[j]) + g.epi.bias[j];
-                        s = fmaf(fmaxf(a, 0.f), g.epi.head_w[j], s);
+                        sacc = fmaf(fmaxf(a, 0.f), g.epi.head_w[j], sacc);
                     }
-                    if (valid) g.epi.head_out[grow] = fmaxf(s + g.epi.head_b, 0.f);
+                    long long grow;
+                    if (half == 0 && row_of(quarter * 32 + lane, grow)) g.epi.head_out[grow] = fmaxf(sacc + g.epi.head_b, 0.f);
                 }
             } else {
+                // 16-column pieces: lane -> (row = pass * 8 + lane / 4, 4 columns = (lane % 4) * 4)
+                const int cg = (lane & 3) * 4;
+                constexpr int NPC = BN / 16;
+                const int c_lo = half * (NPC / 2), c_hi = c_lo + NPC / 2;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(t_row + c * 32, v);
+                for (int c = c_lo; c < c_hi; ++c) {
+                    uint32_t v[16];
+                    ptx::tmem_ld_32x16(t_row + c * 16, v);
                     ptx::tmem_ld_wait();
-                    if (valid) {
+                    float4* mine = reinterpret_cast<float4*>(stg + lane * STG_LD);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const int col = n0 + c * 32 + j;
-                            if (col < g.N) {
-                                float f[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])};
-                                epilogue_store4(g.epi, g.N, grow, grow, col, f);
+                    for (int j = 0; j < 4; ++j)
+                        mine[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    __syncwarp();
+                    const int col = n0 + c * 16 + cg;
+                    if (col < g.N) {
+                        EpiPre pre[4];
+                        bool ok[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {  // issue the residual / table loads of the 4 passes first
+                            const int rr = i * 8 + (lane >> 2);
+                            long long grow;
+                            ok[i] = row_of(quarter * 32 + rr, grow);
+                            if (ok[i]) epilogue_prefetch<KIND>(g.epi, g.N, grow, grow, col, pre[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (ok[i]) {
+                                const int rr = i * 8 + (lane >> 2);
+                                const float4 q = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cg);
+                                float f[4] = {q.x, q.y, q.z, q.w};
+                                epilogue_finish<KIND>(g.epi, pre[i], f);
                             }
                         }
                     }
+                    __syncwarp();
                 }
             }
+            // this warp's share of the accumulator has left TMEM: hand the stage back to the MMA warp
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
             as ^= 1;
@@ -272,20 +308,33 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims
     return DAD_OK;
 }
 
-template <int BN>
+template <int BN, int KIND>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        DAD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg<BN>::SMEM_BYTES));
         configured = true;
     }
     const int tiles = a.num_m_tiles * a.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     ProfScope prof(PROF_GEMM_TC, a.flops, stream);
-    gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+    gemm_tc_kernel<BN, KIND><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
+}
+
+template <int BN>
+int launch_kind(int kind, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
+    if constexpr (BN >= 128) {  // the specialised encoder epilogues only occur with wide N
+        switch (kind) {
+            case EK_BIAS_BF16: return launch<BN, EK_BIAS_BF16>(tmA, tmB, a, stream);
+            case EK_GELU_BF16: return launch<BN, EK_GELU_BF16>(tmA, tmB, a, stream);
+            case EK_RES_F32: return launch<BN, EK_RES_F32>(tmA, tmB, a, stream);
+            default: break;
+        }
+    }
+    return launch<BN, EK_GENERIC_NOGELU>(tmA, tmB, a, stream);
 }
 
 int pick_bn(int N) {
@@ -362,11 +411,13 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
         DAD_TRY(make_tmap(&tmB, p.Wt, 2, dims, strides, box));
     }
+    const int kind = epilogue_kind(p.epi);
+    DAD_REQUIRE(!(kind == EK_GENERIC && p.epi.act == ACT_GELU), "gemm_tc: GELU is only fused as bias+GELU->bf16");
     switch (bn) {
-        case 256: return launch<256>(tmA, tmB, a, stream);
-        case 128: return launch<128>(tmA, tmB, a, stream);
-        case 64: return launch<64>(tmA, tmB, a, stream);
-        default: return launch<32>(tmA, tmB, a, stream);
+        case 256: return launch_kind<256>(kind, tmA, tmB, a, stream);
+        case 128: return launch_kind<128>(kind, tmA, tmB, a, stream);
+        case 64: return launch_kind<64>(kind, tmA, tmB, a, stream);
+        default: return launch_kind<32>(kind, tmA, tmB, a, stream);
     }
 }
 

@@ -114,6 +114,10 @@ int dad_distill_loss(const float* student, const float* teacher, int strategy, i
  * out[M,N] (fp32) = A[M,K] (bf16 bits / fp32) * W[N,K]^T through the tcgen05 (mode 0) or FFMA (mode 1)
  * engine with an optional bias[N]; used by the parity tests to bisect the GEMM engine alone. */
 int dad_gemm(const void* A, const void* W, const float* bias, float* out, int M, int N, int K, int mode, void* stream);
+/* Same with the fused epilogues of the encoder: out = [res +] [gamma *] act(A W^T + bias); out / res are fp32
+ * or bf16 (out_bf16 / res_bf16); act: 0 none, 1 GELU(erf), 2 ReLU.  res may alias out (in-place residual). */
+int dad_gemm_ex(const void* A, const void* W, const float* bias, const float* gamma, const void* res, int res_bf16,
+                void* out, int out_bf16, int act, int M, int N, int K, int mode, void* stream);
 /* conv3x3 / 1x1 (stride 1, zero padding) on NHWC input [B,H,W,C] with packed weights [Co, taps*Cp]. */
 int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
                   int Co, int taps, int mode, void* stream);

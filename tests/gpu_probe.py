@@ -98,7 +98,41 @@ def step_forward_perf():
     json.dump(res, open(os.path.join(OUT, "probe_forward_perf.json"), "w"), indent=1)
 
 
-STEPS = {"gemm": step_gemm, "gemm_perf": step_gemm_perf, "forward_perf": step_forward_perf}
+def step_gemm_kinds():
+    """Throughput of the fused encoder epilogues at ViT-L B=32 shapes."""
+    import torch
+    from distill_any_depth_b200 import _lib as L
+    lib = L.load()
+    M = 43840
+    cases = [("qkv bias->bf16", 3072, 1024, "bias"), ("fc1 bias+gelu->bf16", 4096, 1024, "gelu"),
+             ("proj res fp32", 1024, 1024, "res"), ("fc2 res fp32", 1024, 4096, "res")]
+    for name, N, K, kind in cases:
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        bias = torch.randn(N, device="cuda"); gamma = torch.ones(N, device="cuda")
+        outb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        outf = torch.zeros(M, N, device="cuda")
+        def run():
+            if kind == "bias":
+                L.check(lib.dad_gemm_ex(L.ptr(A), L.ptr(W), L.ptr(bias), None, None, 0, L.ptr(outb), 1, 0, M, N, K, 0, L.stream_ptr()))
+            elif kind == "gelu":
+                L.check(lib.dad_gemm_ex(L.ptr(A), L.ptr(W), L.ptr(bias), None, None, 0, L.ptr(outb), 1, 1, M, N, K, 0, L.stream_ptr()))
+            else:
+                L.check(lib.dad_gemm_ex(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gamma), L.ptr(outf), 0, L.ptr(outf), 0, 0, M, N, K, 0, L.stream_ptr()))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"{name:24s} M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
+STEPS = {"gemm_kinds": step_gemm_kinds, "gemm": step_gemm, "gemm_perf": step_gemm_perf, "forward_perf": step_forward_perf}
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)

@@ -55,6 +55,41 @@ def test_gemm_simt_matches_fp32_matmul(M, N, K):
     assert (out - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K", [(1370, 1024, 1024), (2740, 3072, 1024), (785, 384, 384), (1000, 768, 3072)])
+@pytest.mark.parametrize("kind", ["bias_bf16", "gelu_bf16", "res_f32", "res_bf16_relu"])
+def test_gemm_tc_fused_epilogues(M, N, K, kind):
+    """The encoder epilogues (compile-time specialised) and a generic run-time one."""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(N, device="cuda", generator=g)
+    acc = A.float() @ W.float().t() + bias
+    if kind == "bias_bf16":
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        L.check(lib.dad_gemm_ex(L.ptr(A), L.ptr(W), L.ptr(bias), None, None, 0, L.ptr(out), 1, 0, M, N, K, 0, L.stream_ptr()))
+        ref, tol = acc, 1e-2
+    elif kind == "gelu_bf16":
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        L.check(lib.dad_gemm_ex(L.ptr(A), L.ptr(W), L.ptr(bias), None, None, 0, L.ptr(out), 1, 1, M, N, K, 0, L.stream_ptr()))
+        ref, tol = F.gelu(acc), 1e-2
+    elif kind == "res_f32":
+        res = torch.randn(M, N, device="cuda", generator=g)
+        out = res.clone()  # in-place residual update, as the encoder does
+        L.check(lib.dad_gemm_ex(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gamma), L.ptr(out), 0, L.ptr(out), 0, 0, M, N, K, 0, L.stream_ptr()))
+        ref, tol = res + gamma * acc, 2e-3
+    else:
+        res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        L.check(lib.dad_gemm_ex(L.ptr(A), L.ptr(W), L.ptr(bias), None, L.ptr(res), 1, L.ptr(out), 1, 2, M, N, K, 0, L.stream_ptr()))
+        ref, tol = res.float() + torch.relu(acc), 1e-2
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), err
+
+
 def pack_conv_weight(w, dtype):
     """[Co, Ci, kh, kw] -> [Co, taps * Cp] (tap-major, channels zero-padded to a multiple of 64)."""
     Co, Ci, kh, kw = w.shape
