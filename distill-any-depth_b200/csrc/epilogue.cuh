@@ -37,7 +37,7 @@ __device__ __forceinline__ void store4_bf16(bf16* base, long long off, const flo
 // result is rounded to bf16 anyway (bf16 ulp 4e-3 relative); fp32 outputs use erff.
 __device__ __forceinline__ float gelu_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));  // 1 + pz >= 1: MUFU.RCP is within 1 ulp
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
@@ -104,13 +104,30 @@ __device__ __forceinline__ void epilogue_prefetch(const Epilogue& e, int N, long
     if (G && e.res2) load4(e.res2, p.off, e.res2_bf16, p.r2);
 }
 
+// per-column vectors of a 4-column group (bias, LayerScale gamma): loaded once per group of rows
+struct EpiCols {
+    float4 b4, g4;
+};
 template <int KIND = EK_GENERIC>
-__device__ __forceinline__ void epilogue_finish(const Epilogue& e, const EpiPre& p, float (&v)[4]) {
+__device__ __forceinline__ void epilogue_load_cols(const Epilogue& e, int col, EpiCols& c) {
+    constexpr bool G = KIND == EK_GENERIC || KIND == EK_GENERIC_NOGELU;
+    int bcol = col;
+    c.b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    c.g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (G && e.scat_k) {
+        bcol = col % e.scat_CoP;
+        if (bcol >= e.scat_Co) return;  // padded output channel: never stored
+    }
+    if (G ? (e.bias != nullptr) : true) c.b4 = *reinterpret_cast<const float4*>(e.bias + bcol);
+    if (G ? (e.gamma != nullptr) : (KIND == EK_RES_F32)) c.g4 = *reinterpret_cast<const float4*>(e.gamma + bcol);
+}
+
+template <int KIND = EK_GENERIC>
+__device__ __forceinline__ void epilogue_finish(const Epilogue& e, const EpiPre& p, const EpiCols& c, float (&v)[4]) {
     constexpr bool G = KIND == EK_GENERIC || KIND == EK_GENERIC_NOGELU;
     if (G && p.skip) return;
     if (G ? (e.bias != nullptr) : true) {
-        const float4 b4 = *reinterpret_cast<const float4*>(e.bias + p.bcol);
-        v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+        v[0] += c.b4.x; v[1] += c.b4.y; v[2] += c.b4.z; v[3] += c.b4.w;
     }
     const int act = G ? e.act : (KIND == EK_GELU_BF16 ? ACT_GELU : ACT_NONE);
     const bool obf = G ? (e.out_bf16 != 0) : (KIND != EK_RES_F32);
@@ -127,8 +144,7 @@ __device__ __forceinline__ void epilogue_finish(const Epilogue& e, const EpiPre&
         for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
     }
     if (G ? (e.gamma != nullptr) : (KIND == EK_RES_F32)) {
-        const float4 g4 = *reinterpret_cast<const float4*>(e.gamma + p.bcol);
-        v[0] *= g4.x; v[1] *= g4.y; v[2] *= g4.z; v[3] *= g4.w;
+        v[0] *= c.g4.x; v[1] *= c.g4.y; v[2] *= c.g4.z; v[3] *= c.g4.w;
     }
     if (G && e.rowtab) {
 #pragma unroll
@@ -158,8 +174,10 @@ __device__ __forceinline__ void epilogue_finish(const Epilogue& e, const EpiPre&
 __device__ __forceinline__ void epilogue_store4(const Epilogue& e, int N, long long grow, long long orow, int col,
                                                 float (&v)[4]) {
     EpiPre p;
+    EpiCols c;
+    epilogue_load_cols<EK_GENERIC>(e, col, c);
     epilogue_prefetch<EK_GENERIC>(e, N, grow, orow, col, p);
-    epilogue_finish<EK_GENERIC>(e, p, v);
+    epilogue_finish<EK_GENERIC>(e, p, c, v);
 }
 
 }  // namespace dad

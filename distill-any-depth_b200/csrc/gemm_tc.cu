@@ -224,6 +224,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int c_lo = half * (NPC / 2), c_hi = c_lo + NPC / 2;
 #pragma unroll 1
                 for (int c = c_lo; c < c_hi; ++c) {
+                    const int col = n0 + c * 16 + cg;
+                    EpiCols cols;
+                    if (col < g.N) epilogue_load_cols<KIND>(g.epi, col, cols);  // in flight while TMEM is read
                     uint32_t v[16];
                     ptx::tmem_ld_32x16(t_row + c * 16, v);
                     ptx::tmem_ld_wait();
@@ -233,7 +236,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         mine[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                     __syncwarp();
-                    const int col = n0 + c * 16 + cg;
                     if (col < g.N) {
                         EpiPre pre[4];
                         bool ok[4];
@@ -250,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const int rr = i * 8 + (lane >> 2);
                                 const float4 q = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cg);
                                 float f[4] = {q.x, q.y, q.z, q.w};
-                                epilogue_finish<KIND>(g.epi, pre[i], f);
+                                epilogue_finish<KIND>(g.epi, pre[i], cols, f);
                             }
                         }
                     }
