@@ -175,9 +175,6 @@ def run_b200(a):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    lib.dad_launch_count.restype = ctypes.c_longlong
-    lib.dad_profile_get.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
-                                    ctypes.POINTER(ctypes.c_longlong)]
 
     B, H = a.batch, a.size
     kw = synthetic.MODEL_PRESETS[a.encoder]

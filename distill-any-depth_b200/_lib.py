@@ -39,6 +39,9 @@ PROTOTYPES = {
     "dad_gemm_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dad_conv_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dad_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "dad_launch_count": (_c.c_longlong, []),
+    "dad_profile_enable": (None, [_i]),
+    "dad_profile_get": (_i, [_i, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double), _c.POINTER(_c.c_longlong)]),
 }
 
 DAD_ERR_INVALID, DAD_ERR_UNSUPPORTED, DAD_ERR_CUDA, DAD_ERR_WORKSPACE = -1, -2, -3, -4

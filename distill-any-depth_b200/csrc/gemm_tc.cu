@@ -19,6 +19,7 @@
 #include "epilogue.cuh"
 #include "gemm.h"
 #include "ptx.cuh"
+#include "tmap.h"
 
 namespace dad {
 
@@ -276,40 +277,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
-        return set_error(DAD_ERR_INVALID, "TMA base address %p not 16-byte aligned", base);
-    for (int i = 0; i < rank - 1; ++i)
-        if (strides_bytes[i] % 16 != 0)
-            return set_error(DAD_ERR_INVALID, "TMA stride %llu not a multiple of 16 bytes",
-                             (unsigned long long)strides_bytes[i]);
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return DAD_OK;
-}
-
 template <int BN, int KIND>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
     static bool configured = false;
@@ -394,7 +361,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         const cuuint64_t strides[3] = {(cuuint64_t)p.ldp * 2, (cuuint64_t)p.ldp * 2 * p.W,
                                        (cuuint64_t)p.ldp * 2 * p.W * p.H};
         const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)tw, (cuuint32_t)a.th, 1};
-        DAD_TRY(make_tmap(&tmA, p.A, 4, dims, strides, box));
+        DAD_TRY(make_tmap_bf16(&tmA, p.A, 4, dims, strides, box));
     } else {
         DAD_REQUIRE(p.M > 0 && p.K > 0 && p.lda >= p.K && p.lda % 8 == 0, "gemm_tc: bad linear dims M=%d K=%d lda=%lld",
                     p.M, p.K, p.lda);
@@ -405,13 +372,13 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
         const cuuint64_t strides[1] = {(cuuint64_t)p.lda * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
-        DAD_TRY(make_tmap(&tmA, p.A, 2, dims, strides, box));
+        DAD_TRY(make_tmap_bf16(&tmA, p.A, 2, dims, strides, box));
     }
     {
         const cuuint64_t dims[2] = {(cuuint64_t)p.Kp, (cuuint64_t)p.N};
         const cuuint64_t strides[1] = {(cuuint64_t)p.Kp * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
-        DAD_TRY(make_tmap(&tmB, p.Wt, 2, dims, strides, box));
+        DAD_TRY(make_tmap_bf16(&tmB, p.Wt, 2, dims, strides, box));
     }
     const int kind = epilogue_kind(p.epi);
     DAD_REQUIRE(!(kind == EK_GENERIC && p.epi.act == ACT_GELU), "gemm_tc: GELU is only fused as bias+GELU->bf16");

@@ -124,6 +124,14 @@ int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float*
 /* attention over qkv [B*N, 3*heads*64] (q pre-scaled) -> out [B*N, heads*64]; bf16 bits (mode 0) or fp32. */
 int dad_attention(const void* qkv, void* out, int B, int N, int heads, int mode, void* stream);
 
+/* ------------------------------------------------------------------ measurement hooks (bench.py)
+ * Launch counter of this library's kernels, and optional per-kernel-class CUDA-event timing
+ * (class: 0 gemm_tc, 1 gemm_simt, 2 attention, 3 layernorm, 4 elementwise, 5 loss; `work` = algorithmic FLOPs
+ * for classes 0-2, algorithmic bytes for 3-5).  Enabling clears previous records. */
+long long dad_launch_count(void);
+void dad_profile_enable(int on);
+int dad_profile_get(int cls, double* ms, double* work, long long* launches);
+
 #ifdef __cplusplus
 }
 #endif

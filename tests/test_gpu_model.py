@@ -18,10 +18,10 @@ pytestmark = pytest.mark.gpu
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 
 
-def build(preset, seed, teacher=False):
+def build(preset, seed, teacher=False, head_bias=0.25):
     import distill_any_depth_b200 as d
     kw = synthetic.MODEL_PRESETS[preset]
-    sd = synthetic.make_state_dict(seed=seed, **kw)
+    sd = synthetic.make_state_dict(seed=seed, head_bias=head_bias, **kw)
     if teacher:
         from oracle.make_golden import student_to_teacher_keys
         m = d.DepthAnything(**kw)
@@ -41,8 +41,8 @@ def report(name, payload):
 @pytest.mark.parametrize("case", MODEL_CASES, ids=lambda c: c[0])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_forward_matches_reference_fixture(case, precision, golden_model):
-    name, preset, B, H, W, ws, xs, teacher = case
-    m, sd, kw = build(preset, ws, teacher)
+    name, preset, B, H, W, ws, xs, teacher, hb = case
+    m, sd, kw = build(preset, ws, teacher, hb)
     m.precision = precision
     x = synthetic.make_images(B, H, W, seed=xs)
     with torch.no_grad():

@@ -1,0 +1,161 @@
+"""CPU: host-side mirror of the reference interface (parameter layout, option handling, errors) and the
+data-parallel loss finishing (world_size-2 gloo) - no GPU."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from distill_any_depth_b200 import synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_student_state_dict_layout_matches_reference_shapes():
+    import distill_any_depth_b200 as d
+    for preset in ("vits", "vitb"):
+        kw = synthetic.MODEL_PRESETS[preset]
+        m = d.DepthAnythingV2(**kw)
+        want = synthetic.param_shapes(**kw)
+        got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert got == {k: tuple(s) for k, s in want.items()}
+        assert m.load_state_dict(synthetic.make_state_dict(seed=0, **kw), strict=True)
+    assert len(d.DepthAnythingV2(**synthetic.MODEL_PRESETS["vitb"]).state_dict()) == 239
+    m = d.DepthAnythingV2(**synthetic.MODEL_PRESETS["vits"])
+    assert m.encoder == "vits" and m.pretrained.embed_dim == 384 and m.pretrained.n_blocks == 12
+    assert m.pretrained.num_heads == 6 and m.pretrained.patch_size == 14
+    assert m.intermediate_layer_idx["vitl"] == [4, 11, 17, 23]
+
+
+def test_teacher_key_layout_and_mapping():
+    import distill_any_depth_b200 as d
+    from oracle.make_golden import student_to_teacher_keys
+    kw = synthetic.MODEL_PRESETS["vitl"]
+    t = d.DepthAnything(**kw)
+    keys = list(t.state_dict())
+    assert len(keys) == 407 and "backbone.blocks.0.23.mlp.fc2.weight" in keys and "backbone.mask_token" in keys
+    want = student_to_teacher_keys({k: None for k in synthetic.param_shapes(**kw)})
+    assert set(keys) == set(want)
+    assert all(t._student_key(k) in synthetic.param_shapes(**kw) for k in keys)
+    assert float(t.backbone.blocks[0][0].ls1.gamma[0]) == pytest.approx(1e-5)  # ViT_DINO.py:587
+
+
+def test_options_outside_the_hot_path_raise():
+    import distill_any_depth_b200 as d
+    kw = synthetic.MODEL_PRESETS["vits"]
+    with pytest.raises(KeyError):
+        d.DepthAnythingV2(encoder="vitx")
+    with pytest.raises(NotImplementedError):
+        d.DepthAnythingV2(encoder="vitg")
+    with pytest.raises(NotImplementedError):
+        d.DepthAnythingV2(use_bn=True, **kw)
+    with pytest.raises(NotImplementedError):
+        d.DepthAnythingV2(use_clstoken=True, **kw)
+    with pytest.raises(NotImplementedError):
+        d.DepthAnything(encoder="vitb")
+    with pytest.raises(NotImplementedError):
+        d.DepthAnything(use_registers=True)
+    with pytest.raises(NotImplementedError):
+        d.get_contexts_ds(3, torch.ones(1, 1, 4, 4, dtype=torch.bool))
+
+
+def test_product_path_refuses_cpu_tensors():
+    """No CPU fallback: the product functions fail loudly instead of silently computing on the host."""
+    import distill_any_depth_b200 as d
+    m = d.DepthAnythingV2(**synthetic.MODEL_PRESETS["vits"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 28, 28))
+    x = torch.rand(1, 1, 8, 8)
+    for fn in (lambda: d.SSILoss()(x, x, x > 0.5), lambda: d.gradient_preservation_loss(x),
+               lambda: d.distillation_loss(x, x, "hybrid"), lambda: d.get_contexts_dr(3, x, None),
+               lambda: d.masked_shift_and_scale(x, x, x > 0.5),
+               lambda: d.feature_distillation_loss(torch.rand(1, 4, 8), torch.rand(1, 4, 8))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fn()
+
+
+def test_product_package_does_not_import_the_oracle():
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); import distill_any_depth_b200; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'") % ROOT
+    subprocess.run([sys.executable, "-c", code], check=True)
+    for root, _, files in os.walk(os.path.join(ROOT, "distill-any-depth_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                assert "import oracle" not in open(os.path.join(root, f)).read(), f
+
+
+def test_shard_range_partitions_the_batch():
+    from distill_any_depth_b200.dist import shard_range
+    for n in (1, 7, 8, 128, 130):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _partials_cpu(pred, gt, fs, ft):
+    """(numerator, denominator) of each loss for one shard, computed with the oracle's formulas."""
+    ssi = oracle.SSILoss()
+    full = torch.ones_like(gt, dtype=torch.bool)
+    dense = ssi(pred, gt, full, dense=True)
+    ctx = oracle.get_contexts_dr(3, gt, None)
+    K = ctx.shape[0]
+    rep = lambda x: x.unsqueeze(0).expand(K, *x.shape).reshape(-1, *x.shape[-3:])
+    per = ssi(rep(pred), rep(gt), ctx.reshape(-1, *ctx.shape[-3:]), dense=True).reshape(*ctx.shape).sum(0)
+    times = ctx.sum(0)
+    valid = times != 0
+    per = torch.where(valid, per / times.clamp(min=1), per)
+    kx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]]).view(1, 1, 3, 3)
+    gx = torch.nn.functional.conv2d(pred, kx, padding=1)
+    gy = torch.nn.functional.conv2d(pred, kx.transpose(2, 3), padding=1)
+    g = torch.exp(-torch.sqrt(gx ** 2 + gy ** 2 + 1e-6))
+    sn = torch.nn.functional.normalize(fs, dim=1)
+    tn = torch.nn.functional.normalize(ft, dim=1)
+    cos = torch.nn.functional.cosine_similarity(sn, tn, dim=1)
+    t64 = lambda a, b: torch.tensor([float(a), float(b)], dtype=torch.float64)
+    return {"ssi": ("ssi", t64(dense.double().sum(), full.sum())),
+            "hdn": ("hdn", t64(per.double().sum(), valid.sum())),
+            "grad": ("grad", t64(g.double().sum(), g.numel())),
+            "feat": ("feat", t64(cos.double().sum(), cos.numel()))}
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from distill_any_depth_b200.dist import finish_losses, shard_batch
+    pred, gt, _ = synthetic.make_depth_pair(6, 40, 56, seed=3)
+    fs, ft = synthetic.make_features(6, 20, 32, seed=4), synthetic.make_features(6, 20, 32, seed=5)
+    sl = lambda x: shard_batch(x, rank, world)
+    out = finish_losses(_partials_cpu(sl(pred), sl(gt), sl(fs), sl(ft)))
+    if rank == 0:
+        q.put({k: float(v) for k, v in out.items()})
+    dist.destroy_process_group()
+
+
+def test_two_rank_losses_equal_single_process_full_batch():
+    """8e: sharded partials + ONE all-reduce == the reference computed on the concatenated batch."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pred, gt, _ = synthetic.make_depth_pair(6, 40, 56, seed=3)
+    fs, ft = synthetic.make_features(6, 20, 32, seed=4), synthetic.make_features(6, 20, 32, seed=5)
+    ssi = oracle.SSILoss()
+    ref = {"ssi": ssi(pred, gt, torch.ones_like(gt, dtype=torch.bool)),
+           "hdn": oracle.compute_hdn_loss(ssi, pred, gt, oracle.get_contexts_dr(3, gt, None)),
+           "grad": oracle.gradient_preservation_loss(pred),
+           "feat": oracle.feature_distillation_loss(fs, ft)}
+    for k, v in ref.items():
+        assert abs(got[k] - float(v)) <= 1e-5 * max(abs(float(v)), 1e-6), (k, got[k], float(v))

@@ -12,9 +12,9 @@ from helpers import sub
 
 @pytest.mark.parametrize("case", [c for c in MODEL_CASES if c[0] != "vits_518"], ids=lambda c: c[0])
 def test_model_matches_reference_fixture(case, golden_model):
-    name, preset, B, H, W, ws, xs, _teacher = case
+    name, preset, B, H, W, ws, xs, _teacher, hb = case
     kw = synthetic.MODEL_PRESETS[preset]
-    sd = synthetic.make_state_dict(seed=ws, **kw)
+    sd = synthetic.make_state_dict(seed=ws, head_bias=hb, **kw)
     x = synthetic.make_images(B, H, W, seed=xs)
     with torch.no_grad():
         d, f = oracle.depth_anything_forward(x, sd, kw["encoder"])
