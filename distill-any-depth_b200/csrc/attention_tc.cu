@@ -1,15 +1,17 @@
 // Fused multi-head attention on the 5th-gen tensor cores (sm_100a), head_dim 64, non-causal, no mask
 // (reference dinov2_layers/attention.py:49-62; 64^-0.5 is folded into the packed qkv weights).
 //
-// One CTA = one (image, head, 128-query tile); two CTAs are co-resident per SM so one CTA's MMAs overlap the
-// other's softmax.  Roles (192 threads):
-//   warps 0-3  softmax: thread = query row.  S row is read from TMEM twice (max, then exp2), P is written
-//              back to TMEM as packed bf16 (tcgen05.st) and consumed by the second MMA straight from TMEM.
-//   warp 4     TMA producer: Q tile once, then K / V tiles (128 keys x 64) through a 2-stage mbarrier ring,
+// One CTA = one (image, head, 128-query tile); two CTAs are co-resident per SM.  Roles (192 threads):
+//   warps 0-3  softmax: thread = query row; the 64 scores of a key tile are read from TMEM once, exponentiated
+//              in registers, and P is written back to TMEM as packed bf16 (tcgen05.st) where the second MMA
+//              consumes it directly (A operand from TMEM).
+//   warp 4     TMA producer: Q tile once, then K / V tiles (64 keys x 64) through a 4-stage mbarrier ring,
 //              3-D tensor maps over qkv [B, N, 3*D] so rows past N are zero-filled per image.
-//   warp 5     tcgen05.mma issuer:  S[128x128] = Q K^T  (A, B from smem, K-major)
+//   warp 5     tcgen05.mma issuer:  S[128x64] = Q K^T  (A, B from smem, K-major)
 //                                   O[128x64] += P V     (A = P from TMEM, B = V from smem, MN-major)
-// TMEM (256 columns per CTA): S fp32 [0,128), P bf16x2 [128,192), O fp32 [192,256).
+// S and P are double-buffered in TMEM (256 columns per CTA: S0 S1 | P0 P1 | O), so Q K^T of tile j+2 is issued
+// as soon as the softmax has drained S of tile j, and the softmax of tile j+1 never waits for the tensor pipe:
+// the kernel is bounded by the exp2 throughput of the MUFU (16 / clk / SM), not by MMA latency.
 // Online softmax keeps a per-row reference maximum; O / l are rescaled (TMEM round trip) only when the running
 // maximum exceeds the reference by more than 2^8 ("lazy rescale": exact, P <= 2^8 stays well inside bf16 /
 // fp32 range), so in the common case O is never touched until the final normalisation.
@@ -21,13 +23,14 @@ namespace dad {
 
 namespace {
 
-constexpr int BQ = 128, BKV = 128, HD = 64;
-constexpr int TILE_BYTES = BKV * HD * 2;  // 16 KB
-constexpr int KV_STAGES = 2;
+constexpr int BQ = 128, BKV = 64, HD = 64;
+constexpr int Q_BYTES = BQ * HD * 2;      // 16 KB
+constexpr int KV_BYTES = BKV * HD * 2;    // 8 KB
+constexpr int KV_STAGES = 4;
 constexpr int ATT_THREADS = 192;
 constexpr int TMEM_COLS = 256;
-constexpr int S_COL = 0, P_COL = 128, O_COL = 192;
-constexpr int ATT_SMEM = (1 + 2 * KV_STAGES) * TILE_BYTES + 1024 + 256;
+constexpr int S_COL = 0, P_COL = 128, O_COL = 192;  // S0 [0,64) S1 [64,128) | P0 [128,160) P1 [160,192) | O [192,256)
+constexpr int ATT_SMEM = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 1024 + 256;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
@@ -37,17 +40,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
-    uint8_t* sK = smem + TILE_BYTES;
-    uint8_t* sV = smem + (1 + KV_STAGES) * TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + 2 * KV_STAGES) * TILE_BYTES);
+    uint8_t* sK = smem + Q_BYTES;
+    uint8_t* sV = smem + Q_BYTES + KV_STAGES * KV_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_BYTES + 2 * KV_STAGES * KV_BYTES);
     uint64_t* q_full = bars;
-    uint64_t* k_full = bars + 1;                  // [KV_STAGES]
-    uint64_t* v_full = bars + 1 + KV_STAGES;      // [KV_STAGES]
-    uint64_t* kv_empty = bars + 1 + 2 * KV_STAGES;  // [KV_STAGES]
-    uint64_t* s_full = bars + 1 + 3 * KV_STAGES;
-    uint64_t* p_full = s_full + 1;
-    uint64_t* o_full = s_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+    uint64_t* k_full = bars + 1;                      // [KV_STAGES]
+    uint64_t* v_full = bars + 1 + KV_STAGES;          // [KV_STAGES]
+    uint64_t* kv_empty = bars + 1 + 2 * KV_STAGES;    // [KV_STAGES]
+    uint64_t* s_full = bars + 1 + 3 * KV_STAGES;      // [2]
+    uint64_t* p_full = s_full + 2;                    // [2]
+    uint64_t* o_full = s_full + 4;                    // one completion per P V
+    uint64_t* done = s_full + 5;                      // last P V retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -66,9 +70,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 ptx::mbar_init(&v_full[i], 1);
                 ptx::mbar_init(&kv_empty[i], 1);
             }
-            ptx::mbar_init(s_full, 1);
-            ptx::mbar_init(p_full, 128);
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(&s_full[i], 1);
+                ptx::mbar_init(&p_full[i], 128);
+            }
             ptx::mbar_init(o_full, 1);
+            ptx::mbar_init(done, 1);
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -83,16 +90,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp == 4) {
         if (lane == 0) {
             // ---------------------------------------------------------------- TMA producer
-            ptx::mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            ptx::mbar_arrive_expect_tx(q_full, Q_BYTES);
             ptx::tma_load_3d(sQ, &tmQ, q_full, h * HD, q0, b);
             for (int j = 0; j < T; ++j) {
                 const int s = j % KV_STAGES;
                 const uint32_t ph = (j / KV_STAGES) & 1;
                 ptx::mbar_wait(&kv_empty[s], ph ^ 1);
-                ptx::mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
-                ptx::tma_load_3d(sK + s * TILE_BYTES, &tmK, &k_full[s], h * HD, j * BKV, b);
-                ptx::mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
-                ptx::tma_load_3d(sV + s * TILE_BYTES, &tmV, &v_full[s], h * HD, j * BKV, b);
+                ptx::mbar_arrive_expect_tx(&k_full[s], KV_BYTES);
+                ptx::tma_load_3d(sK + s * KV_BYTES, &tmK, &k_full[s], h * HD, j * BKV, b);
+                ptx::mbar_arrive_expect_tx(&v_full[s], KV_BYTES);
+                ptx::tma_load_3d(sV + s * KV_BYTES, &tmV, &v_full[s], h * HD, j * BKV, b);
             }
         }
     } else if (warp == 5) {
@@ -101,33 +108,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV);
             constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_bmn(BQ, HD);
             const uint32_t q_addr = ptx::smem_u32(sQ);
-            auto issue_qk = [&](int j) {
+            auto issue_qk = [&](int j) {  // S[j & 1] = Q K_j^T
                 const int s = j % KV_STAGES;
                 ptx::mbar_wait(&k_full[s], (j / KV_STAGES) & 1);
                 ptx::tc_fence_after();
-                const uint32_t k_addr = ptx::smem_u32(sK + s * TILE_BYTES);
+                const uint32_t k_addr = ptx::smem_u32(sK + s * KV_BYTES);
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)
-                    ptx::umma_bf16(tmem + S_COL, ptx::make_smem_desc_sw128(q_addr + k * 32),
+                    ptx::umma_bf16(tmem + S_COL + (j & 1) * BKV, ptx::make_smem_desc_sw128(q_addr + k * 32),
                                    ptx::make_smem_desc_sw128(k_addr + k * 32), idesc_qk, k != 0 ? 1u : 0u);
-                ptx::umma_commit(s_full);
+                ptx::umma_commit(&s_full[j & 1]);
             };
             ptx::mbar_wait(q_full, 0);
             issue_qk(0);
+            if (T > 1) issue_qk(1);
             for (int j = 0; j < T; ++j) {
                 const int s = j % KV_STAGES;
-                ptx::mbar_wait(p_full, j & 1);                       // P_j written, S_j fully read
+                ptx::mbar_wait(&p_full[j & 1], (j >> 1) & 1);       // P_j written, S[j & 1] drained
                 ptx::mbar_wait(&v_full[s], (j / KV_STAGES) & 1);
                 ptx::tc_fence_after();
-                const uint32_t v_addr = ptx::smem_u32(sV + s * TILE_BYTES);
+                const uint32_t v_addr = ptx::smem_u32(sV + s * KV_BYTES);
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k)
-                    ptx::umma_bf16_ts(tmem + O_COL, tmem + P_COL + k * 8,
+                    ptx::umma_bf16_ts(tmem + O_COL, tmem + P_COL + (j & 1) * (BKV / 2) + k * 8,
                                       ptx::make_smem_desc_mn_sw128(v_addr + k * 16 * 128), idesc_pv,
                                       (j | k) != 0 ? 1u : 0u);
-                ptx::umma_commit(&kv_empty[s]);                      // K_j / V_j stage free once PV_j retires
+                ptx::umma_commit(&kv_empty[s]);                      // K_j / V_j stage free once P V_j retires
                 ptx::umma_commit(o_full);
-                if (j + 1 < T) issue_qk(j + 1);
+                if (j == T - 1) ptx::umma_commit(done);
+                if (j + 2 < T) issue_qk(j + 2);
             }
         }
     } else {
@@ -137,24 +146,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float m_ref = -INFINITY;  // reference maximum (log2 domain) the stored P / O / l are relative to
         float l = 0.f;
         for (int j = 0; j < T; ++j) {
-            ptx::mbar_wait(s_full, j & 1);
+            const int buf = j & 1;
+            ptx::mbar_wait(&s_full[buf], (j >> 1) & 1);
             ptx::tc_fence_after();
             const int nvalid = min(BKV, N - j * BKV);
-            // pass 1: row maximum of this tile
-            float tmax = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < BKV / 32; ++c) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(tS + c * 32, v);
+            uint32_t v[64];
+            {
+                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+                uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+                ptx::tmem_ld_32x32(tS + buf * BKV, lo);
+                ptx::tmem_ld_32x32(tS + buf * BKV + 32, hi);
                 ptx::tmem_ld_wait();
-                if (c * 32 + 32 <= nvalid) {
+            }
+            float tmax = -INFINITY;
+            if (nvalid == BKV) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
-                } else {
+                for (int i = 0; i < BKV; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < nvalid) tmax = fmaxf(tmax, __uint_as_float(v[i]));
-                }
+                for (int i = 0; i < BKV; ++i)
+                    if (i < nvalid) tmax = fmaxf(tmax, __uint_as_float(v[i]));
             }
             tmax *= LOG2E;
             if (j == 0) {
@@ -162,8 +173,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             } else {
                 const bool need = tmax > m_ref + RESCALE_THRESHOLD;
                 if (__any_sync(0xffffffffu, need)) {
-                    // rare: rescale O (TMEM) and l to the new reference; PV_{j-1} has retired (s_full(j) is
-                    // committed after it) and PV_j cannot start before this thread arrives on p_full
+                    // rare: rescale O (TMEM) and l to the new reference.  P V_{j-1} must have retired: o_full is in
+                    // phase j-1 or j here (P V_{j-2} retired before s_full of tile j, P V_j needs this thread's arrive)
+                    ptx::mbar_wait(o_full, (j - 1) & 1);
+                    ptx::tc_fence_after();
                     const float alpha = need ? ptx::ex2_approx(m_ref - tmax) : 1.0f;
                     if (need) m_ref = tmax;
                     l *= alpha;
@@ -178,31 +191,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     }
                 }
             }
-            // pass 2: P = exp2(s * log2e - m_ref) -> bf16 pairs in TMEM; row sum in fp32
-#pragma unroll 1
+            // P = exp2(s * log2e - m_ref) -> bf16 pairs in TMEM (P[buf]: P V_{j-2} has retired); row sum in fp32
+            float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
             for (int c = 0; c < BKV / 32; ++c) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(tS + c * 32, v);
-                ptx::tmem_ld_wait();
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), LOG2E, -m_ref));
-                    float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), LOG2E, -m_ref));
-                    if (c * 32 + i >= nvalid) p0 = 0.f;
-                    if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
-                    l += p0 + p1;
+                    float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[c * 32 + i]), LOG2E, -m_ref));
+                    float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[c * 32 + i + 1]), LOG2E, -m_ref));
+                    if (nvalid != BKV) {
+                        if (c * 32 + i >= nvalid) p0 = 0.f;
+                        if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
+                    }
+                    ls0 += p0;
+                    ls1 += p1;
                     __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
                     pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
                 }
-                ptx::tmem_st_32x16(tP + c * 16, pk);
+                ptx::tmem_st_32x16(tP + buf * (BKV / 2) + c * 16, pk);
             }
+            l += ls0 + ls1;
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
-            ptx::mbar_arrive(p_full);
+            ptx::mbar_arrive(&p_full[buf]);
         }
         // final: O / l -> bf16 -> global (each thread owns one 128-byte row segment)
-        ptx::mbar_wait(o_full, (T - 1) & 1);
+        ptx::mbar_wait(done, 0);
         ptx::tc_fence_after();
         const int row = q0 + warp * 32 + lane;
         const float inv = 1.0f / l;
@@ -249,7 +264,7 @@ int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream
     for (int i = 0; i < 3; ++i) {
         const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
         const cuuint64_t strides[2] = {(cuuint64_t)3 * D * 2, (cuuint64_t)3 * D * 2 * N};
-        const cuuint32_t box[3] = {(cuuint32_t)HD, (cuuint32_t)BKV, 1};
+        const cuuint32_t box[3] = {(cuuint32_t)HD, (cuuint32_t)(i == 0 ? BQ : BKV), 1};
         DAD_TRY(make_tmap_bf16(&tm[i], qkv + static_cast<long long>(i) * D, 3, dims, strides, box));
     }
     const dim3 grid(cdiv(N, BQ), heads, B);

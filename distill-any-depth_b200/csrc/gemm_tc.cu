@@ -175,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // TMEM lane quarter and drain one half of the tile's columns each.
         const int quarter = warp & 3;          // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;      // column half
-        float* stg = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256) + (warp - 2) * (32 * STG_LD);
+        const uint32_t stg = ptx::smem_u32(smem + STAGES * C::STAGE_BYTES + 256) + (warp - 2) * (32 * STG_LD * 4);
         const int tw_mask = (1 << g.tw_log2) - 1;
         int as = 0;
         uint32_t aphase = 0;
@@ -231,11 +231,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t v[16];
                     ptx::tmem_ld_32x16(t_row + c * 16, v);
                     ptx::tmem_ld_wait();
-                    float4* mine = reinterpret_cast<float4*>(stg + lane * STG_LD);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        mine[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        ptx::sts128(stg + (lane * STG_LD + 4 * j) * 4, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                     __syncwarp();
                     if (col < g.N) {
                         EpiPre pre[4];
@@ -251,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int i = 0; i < 4; ++i) {
                             if (ok[i]) {
                                 const int rr = i * 8 + (lane >> 2);
-                                const float4 q = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cg);
+                                const float4 q = ptx::lds128(stg + (rr * STG_LD + cg) * 4);
                                 float f[4] = {q.x, q.y, q.z, q.w};
                                 epilogue_finish<KIND>(g.epi, pre[i], cols, f);
                             }
