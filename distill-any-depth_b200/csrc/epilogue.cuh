@@ -60,7 +60,7 @@ inline int epilogue_kind(const Epilogue& e) {
     if (e.scat_k || e.rowtab || e.res2 || e.out_relu || e.head_out || !e.out || !e.bias) return EK_GENERIC;
     if (e.out_bf16 && !e.gamma && !e.res1 && e.act == ACT_NONE) return EK_BIAS_BF16;
     if (e.out_bf16 && !e.gamma && !e.res1 && e.act == ACT_GELU) return EK_GELU_BF16;
-    if (!e.out_bf16 && e.gamma && e.res1 && !e.res1_bf16 && e.act == ACT_NONE) return EK_RES_F32;
+    if (!e.out_bf16 && e.gamma && e.res1 && !e.res1_bf16 && e.act == ACT_NONE && e.res1 == e.out) return EK_RES_F32;  // x += g*(acc+b)
     return EK_GENERIC;
 }
 

@@ -50,14 +50,16 @@ struct Cfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                      NUM_EPI_WARPS * 32 * STG_LD * 4 /*epilogue staging*/;
+    static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + 1024;  // barriers live in the 1 KB before it
+    static constexpr int STAGING_BYTES = 2 * BM * 128;               // TMA-store path: one 128-row x 128-byte tile per column half
+    static constexpr int SMEM_BYTES = STAGING_OFF + STAGING_BYTES + 1024 /*align slack*/;
+    static_assert(NUM_EPI_WARPS * 32 * STG_LD * 4 <= STAGING_BYTES, "generic staging must fit");
 };
 
 template <int BN, int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ TcArgs g) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcArgs g) {
     using C = Cfg<BN>;
     constexpr int STAGES = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -175,7 +177,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // TMEM lane quarter and drain one half of the tile's columns each.
         const int quarter = warp & 3;          // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;      // column half
-        const uint32_t stg = ptx::smem_u32(smem + STAGES * C::STAGE_BYTES + 256) + (warp - 2) * (32 * STG_LD * 4);
+        const uint32_t stg = ptx::smem_u32(smem + C::STAGING_OFF) + (warp - 2) * (32 * STG_LD * 4);
+        const uint32_t tile_stg = ptx::smem_u32(smem + C::STAGING_OFF) + half * (BM * 128);  // TMA-store staging tile
         const int tw_mask = (1 << g.tw_log2) - 1;
         int as = 0;
         uint32_t aphase = 0;
@@ -204,6 +207,78 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(&tfull[as], aphase);
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+            if constexpr (KIND == EK_BIAS_BF16 || KIND == EK_GELU_BF16 || KIND == EK_RES_F32) {
+                // ---- TMA-store epilogue: thread = row; each column half stages 128 rows x 128 bytes (SWIZZLE_128B)
+                // and one thread hands the tile to the TMA unit (plain store, or fp32 reduce-add into the residual
+                // stream: x += gamma * (acc + bias) without ever reading x into the SM).
+                constexpr bool F32 = KIND == EK_RES_F32;
+                constexpr int CW = F32 ? 32 : 64;              // columns per staged tile (128 bytes per row)
+                constexpr int NCHUNK = BN / CW;
+                const int c_lo = half * (NCHUNK / 2), c_hi = c_lo + NCHUNK / 2;
+                const int r_tile = quarter * 32 + lane;
+                const bool issuer = (quarter == 0) && (lane == 0);
+                const uint32_t row_addr = tile_stg + r_tile * 128;
+#pragma unroll 1
+                for (int c = c_lo; c < c_hi; ++c) {
+                    const int col0 = n0 + c * CW;
+                    uint32_t v[CW];
+                    {
+                        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+                        ptx::tmem_ld_32x32(t_row + c * CW, lo);
+                        if constexpr (!F32) {
+                            uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+                            ptx::tmem_ld_32x32(t_row + c * CW + 32, hi);
+                        }
+                        ptx::tmem_ld_wait();
+                    }
+                    if (c == c_hi - 1) {  // this warp's share of the accumulator is in registers: release the TMEM stage
+                        ptx::tc_fence_before();
+                        ptx::mbar_arrive(&tempty[as]);
+                    }
+                    uint32_t w[32];  // 128 bytes of output per row
+#pragma unroll
+                    for (int i = 0; i < CW; i += 4) {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (col0 + i < g.N) {
+                            b4 = *reinterpret_cast<const float4*>(g.epi.bias + col0 + i);   // warp-uniform address
+                            if constexpr (F32) g4 = *reinterpret_cast<const float4*>(g.epi.gamma + col0 + i);
+                        }
+                        float f0 = __uint_as_float(v[i]) + b4.x, f1 = __uint_as_float(v[i + 1]) + b4.y;
+                        float f2 = __uint_as_float(v[i + 2]) + b4.z, f3 = __uint_as_float(v[i + 3]) + b4.w;
+                        if constexpr (KIND == EK_GELU_BF16) {
+                            f0 = gelu_fast(f0); f1 = gelu_fast(f1); f2 = gelu_fast(f2); f3 = gelu_fast(f3);
+                        }
+                        if constexpr (F32) {
+                            w[i] = __float_as_uint(f0 * g4.x); w[i + 1] = __float_as_uint(f1 * g4.y);
+                            w[i + 2] = __float_as_uint(f2 * g4.z); w[i + 3] = __float_as_uint(f3 * g4.w);
+                        } else {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(f0, f1), p1 = __floats2bfloat162_rn(f2, f3);
+                            w[i >> 1] = *reinterpret_cast<uint32_t*>(&p0);
+                            w[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
+                        }
+                    }
+                    if (issuer) ptx::bulk_wait_read0();      // previous tile of this half has been read by the TMA unit
+                    ptx::named_bar_sync(1 + half, 128);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)              // 16-byte chunk j of the row lands at chunk (j ^ (row & 7))
+                        ptx::sts128u(row_addr + ((j ^ (r_tile & 7)) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                    ptx::fence_proxy_async_smem();
+                    ptx::named_bar_sync(1 + half, 128);
+                    if (issuer) {
+                        if (g.conv) {
+                            ptx::tma_store_4d(&tmC, tile_stg, col0, cx0, cy0, cb);
+                        } else if constexpr (F32) {
+                            ptx::tma_reduce_add_2d(&tmC, tile_stg, col0, mt * BM);
+                        } else {
+                            ptx::tma_store_2d(&tmC, tile_stg, col0, mt * BM);
+                        }
+                        ptx::bulk_commit();
+                    }
+                }
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+                continue;
+            }
             if (KIND == EK_GENERIC_NOGELU && g.epi.head_out != nullptr) {
                 if constexpr (BN == 32 && KIND == EK_GENERIC_NOGELU) {  // fused output head: relu(dot(relu(acc + b1), w2) + b2), one row per thread
                     uint32_t v[32];
@@ -267,6 +342,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     }
 
+    if constexpr (KIND == EK_BIAS_BF16 || KIND == EK_GELU_BF16 || KIND == EK_RES_F32) {
+        if (warp >= 2 && (warp & 3) == 0 && lane == 0) ptx::bulk_wait0();  // the issuers drain their TMA stores
+    }
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -277,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ------------------------------------------------------------------ host side
 template <int BN, int KIND>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcArgs& a, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         DAD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -287,22 +365,23 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cuda
     const int tiles = a.num_m_tiles * a.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     ProfScope prof(PROF_GEMM_TC, a.flops, stream);
-    gemm_tc_kernel<BN, KIND><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+    gemm_tc_kernel<BN, KIND><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, a);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 
 template <int BN>
-int launch_kind(int kind, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
+int launch_kind(int kind, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcArgs& a,
+                cudaStream_t stream) {
     if constexpr (BN >= 128) {  // the specialised encoder epilogues only occur with wide N
         switch (kind) {
-            case EK_BIAS_BF16: return launch<BN, EK_BIAS_BF16>(tmA, tmB, a, stream);
-            case EK_GELU_BF16: return launch<BN, EK_GELU_BF16>(tmA, tmB, a, stream);
-            case EK_RES_F32: return launch<BN, EK_RES_F32>(tmA, tmB, a, stream);
+            case EK_BIAS_BF16: return launch<BN, EK_BIAS_BF16>(tmA, tmB, tmC, a, stream);
+            case EK_GELU_BF16: return launch<BN, EK_GELU_BF16>(tmA, tmB, tmC, a, stream);
+            case EK_RES_F32: return launch<BN, EK_RES_F32>(tmA, tmB, tmC, a, stream);
             default: break;
         }
     }
-    return launch<BN, EK_GENERIC_NOGELU>(tmA, tmB, a, stream);
+    return launch<BN, EK_GENERIC_NOGELU>(tmA, tmB, tmC, a, stream);
 }
 
 int pick_bn(int N) {
@@ -379,13 +458,33 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
         DAD_TRY(make_tmap_bf16(&tmB, p.Wt, 2, dims, strides, box));
     }
-    const int kind = epilogue_kind(p.epi);
+    int kind = epilogue_kind(p.epi);
+    if (bn < 128) kind = EK_GENERIC;  // the specialised (TMA-store) epilogues exist for the wide tiles only
     DAD_REQUIRE(!(kind == EK_GENERIC && p.epi.act == ACT_GELU), "gemm_tc: GELU is only fused as bias+GELU->bf16");
+    CUtensorMap tmC = tmA;  // placeholder for the generic epilogue (never dereferenced)
+    if (kind != EK_GENERIC) {
+        const bool f32 = kind == EK_RES_F32;
+        const int es = f32 ? 4 : 2, cw = f32 ? 32 : 64;
+        DAD_REQUIRE((p.epi.ldc * es) % 16 == 0, "gemm_tc: output row pitch must be a multiple of 16 bytes");
+        if (p.conv) {
+            const int tw = 1 << a.tw_log2;
+            const cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+            const cuuint64_t strides[3] = {(cuuint64_t)p.epi.ldc * es, (cuuint64_t)p.epi.ldc * es * p.W,
+                                           (cuuint64_t)p.epi.ldc * es * p.W * p.H};
+            const cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)tw, (cuuint32_t)a.th, 1};
+            DAD_TRY(make_tmap(&tmC, f32 ? 1 : 0, p.epi.out, 4, dims, strides, box));
+        } else {
+            const cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.M};
+            const cuuint64_t strides[1] = {(cuuint64_t)p.epi.ldc * es};
+            const cuuint32_t box[2] = {(cuuint32_t)cw, (cuuint32_t)BM};
+            DAD_TRY(make_tmap(&tmC, f32 ? 1 : 0, p.epi.out, 2, dims, strides, box));
+        }
+    }
     switch (bn) {
-        case 256: return launch_kind<256>(kind, tmA, tmB, a, stream);
-        case 128: return launch_kind<128>(kind, tmA, tmB, a, stream);
-        case 64: return launch_kind<64>(kind, tmA, tmB, a, stream);
-        default: return launch_kind<32>(kind, tmA, tmB, a, stream);
+        case 256: return launch_kind<256>(kind, tmA, tmB, tmC, a, stream);
+        case 128: return launch_kind<128>(kind, tmA, tmB, tmC, a, stream);
+        case 64: return launch_kind<64>(kind, tmA, tmB, tmC, a, stream);
+        default: return launch_kind<32>(kind, tmA, tmB, tmC, a, stream);
     }
 }
 

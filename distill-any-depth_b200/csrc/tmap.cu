@@ -20,8 +20,8 @@ EncodeTiledFn get_encode_fn() {
 }
 }  // namespace
 
-int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box) {
+int make_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims,
+              const cuuint64_t* strides_bytes, const cuuint32_t* box) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -31,7 +31,7 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t*
         if (strides_bytes[i] % 16 != 0)
             return set_error(DAD_ERR_INVALID, "TMA stride %llu not a multiple of 16 bytes",
                              (unsigned long long)strides_bytes[i]);
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+    CUresult r = fn(m, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);

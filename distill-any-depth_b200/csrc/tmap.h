@@ -7,7 +7,12 @@
 
 namespace dad {
 
-int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box);
+// dtype: 0 = bf16, 1 = fp32
+int make_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims,
+              const cuuint64_t* strides_bytes, const cuuint32_t* box);
+inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                          const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    return make_tmap(m, 0, base, rank, dims, strides_bytes, box);
+}
 
 }  // namespace dad

@@ -132,7 +132,38 @@ def step_gemm_kinds():
         print(f"{name:24s} M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
 
 
-STEPS = {"gemm_kinds": step_gemm_kinds, "gemm": step_gemm, "gemm_perf": step_gemm_perf, "forward_perf": step_forward_perf}
+def step_conv_perf():
+    """Implicit-GEMM conv throughput at the decoder shapes of ViT-L 518x518 (B=32); fp32 out + bias (generic kind)."""
+    import torch
+    from distill_any_depth_b200 import _lib as L
+    from test_gpu_kernels import pack_conv_weight
+    lib = L.load()
+    cases = [("refinenet1 rcu 148^2 256->256", 32, 148, 148, 256, 256, 9), ("refinenet2 rcu 74^2", 32, 74, 74, 256, 256, 9),
+             ("output_conv1 296^2 256->128", 32, 296, 296, 256, 128, 9), ("head 518^2 128->32", 32, 518, 518, 128, 32, 9),
+             ("layer3_rn 37^2 1024->256", 32, 37, 37, 1024, 256, 9), ("out_conv 1x1 148^2", 32, 148, 148, 256, 256, 1),
+             ("layer1_rn 148^2 256->256", 32, 148, 148, 256, 256, 9)]
+    for name, B, H, W, C, Co, taps in cases:
+        k = 3 if taps == 9 else 1
+        x = torch.randn(B, H, W, C, device="cuda").bfloat16()
+        w = pack_conv_weight(torch.randn(Co, C, k, k, device="cuda") * 0.05, torch.bfloat16)
+        bias = torch.randn(Co, device="cuda")
+        out = torch.empty(B, H, W, Co, device="cuda")
+        run = lambda: L.check(lib.dad_conv_nhwc(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(out), B, H, W, C, Co, taps, 0, L.stream_ptr()))
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        fl = 2.0 * B * H * W * Co * C * taps
+        print(f"{name:32s} {ms:7.3f} ms  {fl / ms / 1e9:6.0f} TFLOP/s", flush=True)
+
+
+STEPS = {"conv_perf": step_conv_perf, "gemm_kinds": step_gemm_kinds, "gemm": step_gemm, "gemm_perf": step_gemm_perf, "forward_perf": step_forward_perf}
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
