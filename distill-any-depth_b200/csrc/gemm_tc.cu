@@ -16,6 +16,8 @@
 // zero-filled by the TMA unit (that is the padding).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "epilogue.cuh"
 #include "gemm.h"
 #include "ptx.cuh"
@@ -397,6 +399,10 @@ int pick_bn(int N) {
 
 int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     DAD_REQUIRE(p.A && p.Wt && p.N > 0, "gemm_tc: null operand or N<=0");
+    {
+        static const bool no_2cta = getenv("DAD_NO_2CTA") != nullptr;  // A/B switch while the 2-CTA kernel is validated
+        if (!no_2cta && gemm_tc2_eligible(p)) return gemm_tc2(p, stream);
+    }
     DAD_REQUIRE(p.N % 8 == 0, "gemm_tc: N=%d must be a multiple of 8", p.N);
     DAD_REQUIRE(p.Kp % 8 == 0, "gemm_tc: Kp=%d must be a multiple of 8", p.Kp);
     TcArgs a{};
