@@ -33,17 +33,23 @@ __device__ __forceinline__ void store4_bf16(bf16* base, long long off, const flo
     *reinterpret_cast<uint2*>(base + off) = u;
 }
 
-// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) with fast exp / reciprocal: used when the
-// result is rounded to bf16 anyway (bf16 ulp 4e-3 relative); fp32 outputs use erff.
+// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) with MUFU reciprocal / exp2 in flush-to-zero mode (no range
+// fix-up code): used when the result is rounded to bf16 anyway (bf16 ulp 4e-3 relative); fp32 outputs use erff.
+// 15 instructions per element: 5 FMUL, 7 FFMA, 2 MUFU, 1 LOP3.
 __device__ __forceinline__ float gelu_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));  // 1 + pz >= 1: MUFU.RCP is within 1 ulp
+    const float ax = fabsf(x);
+    const float z = ax * 0.70710678118654752440f;                 // |x| / sqrt(2)
+    const float zl = ax * 0.84932180028801904272f;                // |x| * sqrt(log2(e) / 2): zl^2 = z^2 * log2(e)
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-(zl * zl)));
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
-    const float erf_abs = 1.0f - poly * t * __expf(-z * z);
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+    const float erf_abs = fmaf(-(poly * t), e, 1.0f);
+    const float hx = 0.5f * x;
+    return fmaf(hx, copysignf(erf_abs, x), hx);
 }
 
 // The epilogue of one (row, 4 columns) group is split in two so that callers can issue the global
