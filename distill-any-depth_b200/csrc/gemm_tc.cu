@@ -43,37 +43,55 @@ struct TcArgs {
     int tw_log2, th;        // spatial tile (conv): TW = 1 << tw_log2, TH = 128 / TW
     int tiles_x, tiles_y;
     int num_m_tiles, num_n_tiles;
+    int halo_bo;            // halo mode: 1 = put the x shift into the descriptor base_offset (bring-up switch)
     double flops;           // algorithmic 2*M*N*K of this launch (host-side bookkeeping only)
 };
 
-template <int BN>
+// HALO = true: small-N 3x3 convolution with shared-memory resident weights and input patch.  The M tile is 16 x 8
+// output pixels; per 64-channel chunk ONE 18 x 16-pixel halo box is fetched (36 KB) and all nine taps read it
+// through row-shifted UMMA descriptors (row pitch 16 pixels = 2048 B; the 128B swizzle is a function of the
+// absolute smem address for both TMA and UMMA, so shifted views need no fix-up), so the activations cross
+// L2 -> smem once instead of nine times and one mbarrier round trip feeds 36 MMAs instead of 4.  The persistent
+// CTA loads the whole weight set once.
+constexpr int HALO_W = 16, HALO_H = 18, HALO_BYTES = HALO_W * HALO_H * 128;  // 36 KB
+constexpr int WRES_BYTES = 73728;  // resident weights: 9 taps x Cp x N x 2 B (e.g. 128 -> 32 channels, or 64 -> 64)
+
+template <int BN, bool HALO = false>
 struct Cfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+    // halo mode: a ring of SA halo stages; the whole weight set (<= WRES_BYTES) stays resident in shared memory
+    static constexpr int SA = 3;
+    static constexpr int SB = WRES_BYTES / B_STAGE_BYTES;  // resident (tap, chunk) weight tiles
+    static constexpr int RING_BYTES = HALO ? SA * HALO_BYTES + WRES_BYTES : STAGES * STAGE_BYTES;
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-    static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + 1024;  // barriers live in the 1 KB before it
+    static constexpr int STAGING_OFF = RING_BYTES + 1024;            // barriers live in the 1 KB before it
     static constexpr int STAGING_BYTES = 2 * BM * 128;               // TMA-store path: one 128-row x 128-byte tile per column half
     static constexpr int SMEM_BYTES = STAGING_OFF + STAGING_BYTES + 1024 /*align slack*/;
     static_assert(NUM_EPI_WARPS * 32 * STG_LD * 4 <= STAGING_BYTES, "generic staging must fit");
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int BN, int KIND>
+template <int BN, int KIND, bool HALO = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcArgs g) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, HALO>;
     constexpr int STAGES = C::STAGES;
+    constexpr int NA = HALO ? C::SA : STAGES, NB = HALO ? C::SB : STAGES;  // ring depths (A / B share one ring unless HALO)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + STAGES;
-    uint64_t* tfull = bars + 2 * STAGES;
-    uint64_t* tempty = bars + 2 * STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint8_t* sB = smem + NA * (HALO ? HALO_BYTES : A_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES);
+    uint64_t* full = bars;                  // [NB]  (B ring; carries A too unless HALO)
+    uint64_t* empty = bars + NB;            // [NB]
+    uint64_t* tfull = bars + 2 * NB;
+    uint64_t* tempty = bars + 2 * NB + 2;
+    uint64_t* afull = bars + 2 * NB + 4;    // [NA]  halo ring (HALO only)
+    uint64_t* aempty = afull + NA;          // [NA]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + NA);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -84,9 +102,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int i = 0; i < STAGES; ++i) {
+            for (int i = 0; i < NB; ++i) {
                 ptx::mbar_init(&full[i], 1);
                 ptx::mbar_init(&empty[i], 1);
+            }
+            if constexpr (HALO) {
+                for (int i = 0; i < NA; ++i) {
+                    ptx::mbar_init(&afull[i], 1);
+                    ptx::mbar_init(&aempty[i], 1);
+                }
             }
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(&tfull[i], 1);
@@ -109,8 +133,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------ TMA producer
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, sa = 0;
+            uint32_t phase = 0, pa = 0;
+            bool weights_loaded = false;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int mt = tile / g.num_n_tiles;
                 const int n0 = (tile - mt * g.num_n_tiles) * BN;
@@ -123,6 +148,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     y0 = ty * g.th;
                     x0 = (r - ty * g.tiles_x) << g.tw_log2;
                 }
+                if constexpr (HALO) {
+                    if (!weights_loaded) {  // once per CTA: all (chunk, tap) weight tiles, one barrier
+                        weights_loaded = true;
+                        ptx::mbar_arrive_expect_tx(&full[0], static_cast<uint32_t>(g.cchunks * 9 * C::B_STAGE_BYTES));
+                        for (int cc = 0; cc < g.cchunks; ++cc)
+                            for (int tap = 0; tap < 9; ++tap)
+                                ptx::tma_load_2d(sB + (cc * 9 + tap) * C::B_STAGE_BYTES, &tmB, &full[0],
+                                                 (tap * g.cchunks + cc) * BK, n0);
+                    }
+                    for (int cc = 0; cc < g.cchunks; ++cc) {
+                        ptx::mbar_wait(&aempty[sa], pa ^ 1);
+                        ptx::mbar_arrive_expect_tx(&afull[sa], HALO_BYTES);
+                        ptx::tma_load_4d(sA + sa * HALO_BYTES, &tmA, &afull[sa], cc * BK, x0 - 1, y0 - 1, b);
+                        if (++sa == NA) { sa = 0; pa ^= 1; }
+                    }
+                } else {
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
@@ -139,20 +180,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ptx::tma_load_2d(sB + stage * C::B_STAGE_BYTES, &tmB, &full[stage], kb * BK, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ------------------------------------------------ MMA issuer
             constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, sa = 0;
+            uint32_t phase = 0, pa = 0;
+            bool weights_ready = false;
             int as = 0;
             uint32_t aphase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
+                if constexpr (HALO) {
+                    if (!weights_ready) {
+                        weights_ready = true;
+                        ptx::mbar_wait(&full[0], 0);
+                    }
+                    for (int cc = 0; cc < g.cchunks; ++cc) {
+                        ptx::mbar_wait(&afull[sa], pa);
+                        ptx::tc_fence_after();
+                        const uint32_t halo = ptx::smem_u32(sA + sa * HALO_BYTES);
+#pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int dy = tap / 3, dx = tap - dy * 3;
+                            const uint32_t a_addr = halo + (dy * HALO_W + dx) * 128;
+                            const uint32_t b_addr = ptx::smem_u32(sB + (cc * 9 + tap) * C::B_STAGE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                ptx::umma_bf16(d_tmem, ptx::make_smem_desc_sw128_halo(a_addr + k * 32, HALO_W * 128, dx, g.halo_bo),
+                                               ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, (cc | tap | k) != 0 ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&aempty[sa]);  // the nine taps of this chunk have read the halo
+                        if (++sa == NA) { sa = 0; pa ^= 1; }
+                    }
+                } else {
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&full[stage], phase);
                     ptx::tc_fence_after();
@@ -166,6 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     ptx::umma_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
                 }
                 ptx::umma_commit(&tfull[as]);
                 as ^= 1;
@@ -356,20 +423,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ host side
-template <int BN, int KIND>
+template <int BN, int KIND, bool HALO = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcArgs& a, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        DAD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            Cfg<BN>::SMEM_BYTES));
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg<BN, HALO>::SMEM_BYTES));
         configured = true;
     }
     const int tiles = a.num_m_tiles * a.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     ProfScope prof(PROF_GEMM_TC, a.flops, stream);
-    gemm_tc_kernel<BN, KIND><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, a);
+    gemm_tc_kernel<BN, KIND, HALO><<<grid, NUM_THREADS, Cfg<BN, HALO>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, a);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
+}
+
+template <int BN>
+int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcArgs& a,
+                cudaStream_t stream) {
+    return launch<BN, EK_GENERIC_NOGELU, true>(tmA, tmB, tmC, a, stream);
 }
 
 template <int BN>
@@ -418,6 +491,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     a.num_n_tiles = cdiv(p.N, bn);
 
     CUtensorMap tmA, tmB;
+    bool halo = false;
     if (p.conv) {
         DAD_REQUIRE(p.taps == 1 || p.taps == 9, "gemm_tc: taps must be 1 or 9");
         DAD_REQUIRE(p.C % 8 == 0 && p.ldp % 8 == 0, "gemm_tc: conv C/ldp must be multiples of 8");
@@ -430,12 +504,24 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         a.B = p.B; a.H = p.H; a.W = p.W;
         a.M = p.B * p.H * p.W;
         a.flops = 2.0 * a.M * p.N * (static_cast<double>(p.taps) * p.C);
-        // choose the spatial tile (TH x TW = 128) with the least padded area
-        long long best = -1;
-        for (int l2 = 3; l2 <= 7; ++l2) {
-            const int tw = 1 << l2, th = BM / tw;
-            const long long area = static_cast<long long>(cdiv(p.W, tw)) * tw * cdiv(p.H, th) * th;
-            if (best < 0 || area < best) { best = area; a.tw_log2 = l2; a.th = th; }
+        static const bool halo_off = getenv("DAD_NO_HALO") != nullptr;      // bring-up A/B switches
+        // measured on B200: UMMA applies the 128B swizzle to absolute shared-memory address bits, exactly like TMA,
+        // so a row-shifted view needs base_offset = 0 (DAD_HALO_BO=1 re-enables it for experiments)
+        static const bool halo_bo_off = getenv("DAD_HALO_BO") == nullptr;
+        halo = !halo_off && p.taps == 9 && bn <= 64 && cdiv(p.N, bn) == 1 &&
+               static_cast<long long>(9) * cdiv(p.C, BK) * bn * BK * 2 <= WRES_BYTES;  // weights fit in smem
+        a.halo_bo = halo_bo_off ? 0 : 1;
+        if (halo) {  // 16 x 8 output pixels per tile, one 18 x 16 halo box per channel chunk
+            a.tw_log2 = 3;
+            a.th = 16;
+        } else {
+            // choose the spatial tile (TH x TW = 128) with the least padded area
+            long long best = -1;
+            for (int l2 = 3; l2 <= 7; ++l2) {
+                const int tw = 1 << l2, th = BM / tw;
+                const long long area = static_cast<long long>(cdiv(p.W, tw)) * tw * cdiv(p.H, th) * th;
+                if (best < 0 || area < best) { best = area; a.tw_log2 = l2; a.th = th; }
+            }
         }
         const int tw = 1 << a.tw_log2;
         a.tiles_x = cdiv(p.W, tw);
@@ -444,7 +530,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         const cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
         const cuuint64_t strides[3] = {(cuuint64_t)p.ldp * 2, (cuuint64_t)p.ldp * 2 * p.W,
                                        (cuuint64_t)p.ldp * 2 * p.W * p.H};
-        const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)tw, (cuuint32_t)a.th, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(halo ? HALO_W : tw), (cuuint32_t)(halo ? HALO_H : a.th), 1};
         DAD_TRY(make_tmap_bf16(&tmA, p.A, 4, dims, strides, box));
     } else {
         DAD_REQUIRE(p.M > 0 && p.K > 0 && p.lda >= p.K && p.lda % 8 == 0, "gemm_tc: bad linear dims M=%d K=%d lda=%lld",
@@ -486,6 +572,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
             DAD_TRY(make_tmap(&tmC, f32 ? 1 : 0, p.epi.out, 2, dims, strides, box));
         }
     }
+    if (halo) return bn == 64 ? launch_halo<64>(tmA, tmB, tmC, a, stream) : launch_halo<32>(tmA, tmB, tmC, a, stream);
     switch (bn) {
         case 256: return launch_kind<256>(kind, tmA, tmB, tmC, a, stream);
         case 128: return launch_kind<128>(kind, tmA, tmB, tmC, a, stream);

@@ -215,6 +215,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
     return d;
 }
+// K-major SWIZZLE_128B view into a larger swizzled buffer: 8-row groups `sbo_bytes` apart, start address shifted by
+// `row_shift` rows (128 B each) from a 1024-byte aligned pattern origin -> base_offset = row_shift & 7.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_halo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t row_shift,
+                                                              int use_base_offset) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    if (use_base_offset) d |= static_cast<uint64_t>(row_shift & 7) << 49;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 // MN-major B operand tile: rows = K index (128-byte rows of 64 bf16 along N), SWIZZLE_128B; groups of 8 K-rows
 // are 1024 B apart (SBO); one 64-element N block (LBO unused).  canonical ((8,n),(8,k)):((1,LBO),(8,SBO)).
 __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) {

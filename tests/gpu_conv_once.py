@@ -7,7 +7,7 @@ import torch
 from distill_any_depth_b200 import _lib as L
 from test_gpu_kernels import pack_conv_weight
 
-B, H, W, C, Co, taps = 8, 148, 148, 256, 256, 9
+B, H, W, C, Co, taps = (int(v) for v in sys.argv[1:7]) if len(sys.argv) >= 7 else (8, 148, 148, 256, 256, 9)
 lib = L.load()
 x = torch.randn(B, H, W, C, device="cuda").bfloat16()
 w = pack_conv_weight(torch.randn(Co, C, 3, 3, device="cuda") * 0.05, torch.bfloat16)
