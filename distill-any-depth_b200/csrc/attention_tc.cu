@@ -103,41 +103,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            // ---------------------------------------------------------------- MMA issuer
-            constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV);
-            constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_bmn(BQ, HD);
-            const uint32_t q_addr = ptx::smem_u32(sQ);
-            auto issue_qk = [&](int j) {  // S[j & 1] = Q K_j^T
-                const int s = j % KV_STAGES;
-                ptx::mbar_wait(&k_full[s], (j / KV_STAGES) & 1);
-                ptx::tc_fence_after();
-                const uint32_t k_addr = ptx::smem_u32(sK + s * KV_BYTES);
+        // -------------------------------------------------------------------- MMA issuer
+        // warp-uniform control flow, one elected lane issues; descriptors = constant high word + (address >> 4)
+        constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV);
+        constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_bmn(BQ, HD);
+        constexpr uint32_t kDescHiMn = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t q_lo = ptx::desc_lo_sw128(ptx::smem_u32(sQ));
+        const uint32_t k_lo0 = ptx::desc_lo_sw128(ptx::smem_u32(sK));
+        const uint32_t v_lo0 = ptx::desc_lo_mn_sw128(ptx::smem_u32(sV));
+        auto issue_qk = [&](int j) {  // S[j & 1] = Q K_j^T
+            const int s = j % KV_STAGES;
+            ptx::mbar_wait(&k_full[s], (j / KV_STAGES) & 1);
+            ptx::tc_fence_after();
+            const uint32_t k_lo = k_lo0 + s * (KV_BYTES >> 4);
+            if (ptx::elect_one()) {
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)
-                    ptx::umma_bf16(tmem + S_COL + (j & 1) * BKV, ptx::make_smem_desc_sw128(q_addr + k * 32),
-                                   ptx::make_smem_desc_sw128(k_addr + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+                    ptx::umma_bf16(tmem + S_COL + (j & 1) * BKV, ptx::make_desc(q_lo + 2 * k, ptx::kDescHiSw128),
+                                   ptx::make_desc(k_lo + 2 * k, ptx::kDescHiSw128), idesc_qk, k != 0 ? 1u : 0u);
                 ptx::umma_commit(&s_full[j & 1]);
-            };
-            ptx::mbar_wait(q_full, 0);
-            issue_qk(0);
-            if (T > 1) issue_qk(1);
-            for (int j = 0; j < T; ++j) {
-                const int s = j % KV_STAGES;
-                ptx::mbar_wait(&p_full[j & 1], (j >> 1) & 1);       // P_j written, S[j & 1] drained
-                ptx::mbar_wait(&v_full[s], (j / KV_STAGES) & 1);
-                ptx::tc_fence_after();
-                const uint32_t v_addr = ptx::smem_u32(sV + s * KV_BYTES);
+            }
+            __syncwarp();
+        };
+        ptx::mbar_wait(q_full, 0);
+        issue_qk(0);
+        if (T > 1) issue_qk(1);
+        for (int j = 0; j < T; ++j) {
+            const int s = j % KV_STAGES;
+            ptx::mbar_wait(&p_full[j & 1], (j >> 1) & 1);       // P_j written, S[j & 1] drained
+            ptx::mbar_wait(&v_full[s], (j / KV_STAGES) & 1);
+            ptx::tc_fence_after();
+            const uint32_t v_lo = v_lo0 + s * (KV_BYTES >> 4);
+            if (ptx::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < BKV / 16; ++k)
+                for (int k = 0; k < BKV / 16; ++k)   // 16 keys = 16 rows of 128 B per k-step
                     ptx::umma_bf16_ts(tmem + O_COL, tmem + P_COL + (j & 1) * (BKV / 2) + k * 8,
-                                      ptx::make_smem_desc_mn_sw128(v_addr + k * 16 * 128), idesc_pv,
-                                      (j | k) != 0 ? 1u : 0u);
-                ptx::umma_commit(&kv_empty[s]);                      // K_j / V_j stage free once P V_j retires
+                                      ptx::make_desc(v_lo + k * (16 * 128 >> 4), kDescHiMn), idesc_pv, (j | k) != 0 ? 1u : 0u);
+                ptx::umma_commit(&kv_empty[s]);                  // K_j / V_j stage free once P V_j retires
                 ptx::umma_commit(o_full);
                 if (j == T - 1) ptx::umma_commit(done);
-                if (j + 2 < T) issue_qk(j + 2);
             }
+            __syncwarp();
+            if (j + 2 < T) issue_qk(j + 2);
         }
     } else {
         // -------------------------------------------------------------------- softmax (warps 0-3)

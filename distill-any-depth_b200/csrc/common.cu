@@ -32,7 +32,7 @@ int num_sms() {
 // ------------------------------------------------------------------ profiling / launch counting
 static thread_local char g_label[128] = "";
 void debug_label(const char* s) {
-    static const bool dbg = getenv("DAD_DEBUG_SYNC") != nullptr;
+    static const bool dbg = getenv("DAD_DEBUG_SYNC") != nullptr || getenv("DAD_DEBUG_TIME") != nullptr;
     if (!dbg) return;
     snprintf(g_label, sizeof(g_label), "%s", s);
 }
@@ -44,8 +44,18 @@ bool g_prof = false;
 std::mutex g_mu;
 }  // namespace
 
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+static bool debug_time() {
+    static const bool on = getenv("DAD_DEBUG_TIME") != nullptr;
+    return on;
+}
+
 ProfScope::ProfScope(int cls, double work, cudaStream_t stream, int launches) : idx(-1), st(stream) {
     g_launches += launches;
+    if (debug_time()) {
+        if (!g_t0) { cudaEventCreate(&g_t0); cudaEventCreate(&g_t1); }
+        cudaEventRecord(g_t0, st);
+    }
     if (!g_prof) return;
     std::lock_guard<std::mutex> lk(g_mu);
     ProfRec r{cls, work, nullptr, nullptr};
@@ -55,6 +65,13 @@ ProfScope::ProfScope(int cls, double work, cudaStream_t stream, int launches) : 
     idx = static_cast<int>(g_recs.size()) - 1;
 }
 ProfScope::~ProfScope() {
+    if (debug_time()) {  // per-launch device time with the current label (serialises the stream)
+        cudaEventRecord(g_t1, st);
+        cudaEventSynchronize(g_t1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_t0, g_t1);
+        fprintf(stderr, "dad[time] %8.3f ms  %s\n", ms, g_label);
+    }
     static const bool dbg = getenv("DAD_DEBUG_SYNC") != nullptr;
     if (dbg) {  // bisecting aid: surface the first faulting launch with its label
         cudaError_t e = cudaStreamSynchronize(st);

@@ -43,7 +43,6 @@ struct TcArgs {
     int tw_log2, th;        // spatial tile (conv): TW = 1 << tw_log2, TH = 128 / TW
     int tiles_x, tiles_y;
     int num_m_tiles, num_n_tiles;
-    int halo_bo;            // halo mode: 1 = put the x shift into the descriptor base_offset (bring-up switch)
     double flops;           // algorithmic 2*M*N*K of this launch (host-side bookkeeping only)
 };
 
@@ -184,60 +183,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
-            int stage = 0, sa = 0;
-            uint32_t phase = 0, pa = 0;
-            bool weights_ready = false;
-            int as = 0;
-            uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                ptx::mbar_wait(&tempty[as], aphase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                if constexpr (HALO) {
-                    if (!weights_ready) {
-                        weights_ready = true;
-                        ptx::mbar_wait(&full[0], 0);
-                    }
-                    for (int cc = 0; cc < g.cchunks; ++cc) {
-                        ptx::mbar_wait(&afull[sa], pa);
-                        ptx::tc_fence_after();
-                        const uint32_t halo = ptx::smem_u32(sA + sa * HALO_BYTES);
-#pragma unroll 1
+        // ---------------------------------------------------- MMA issuer
+        // The whole warp walks the pipeline with uniform control flow and ONE elected lane issues: descriptors are
+        // (constant high word, low word = address >> 4), so each tcgen05.mma costs two integer adds to set up.
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+        const uint32_t sA_lo = ptx::desc_lo_sw128(ptx::smem_u32(sA)), sB_lo = ptx::desc_lo_sw128(ptx::smem_u32(sB));
+        int stage = 0, sa = 0;
+        uint32_t phase = 0, pa = 0;
+        bool weights_ready = false;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            ptx::mbar_wait(&tempty[as], aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            if constexpr (HALO) {
+                if (!weights_ready) {
+                    weights_ready = true;
+                    ptx::mbar_wait(&full[0], 0);
+                }
+                for (int cc = 0; cc < g.cchunks; ++cc) {
+                    ptx::mbar_wait(&afull[sa], pa);
+                    ptx::tc_fence_after();
+                    const uint32_t halo_lo = sA_lo + sa * (HALO_BYTES >> 4);
+                    const uint32_t w_lo = sB_lo + cc * 9 * (C::B_STAGE_BYTES >> 4);
+                    if (ptx::elect_one()) {
+#pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
-                            const int dy = tap / 3, dx = tap - dy * 3;
-                            const uint32_t a_addr = halo + (dy * HALO_W + dx) * 128;
-                            const uint32_t b_addr = ptx::smem_u32(sB + (cc * 9 + tap) * C::B_STAGE_BYTES);
+                            const uint32_t a_lo = halo_lo + ((tap / 3) * HALO_W + (tap % 3)) * (128 >> 4);
+                            const uint32_t b_lo = w_lo + tap * (C::B_STAGE_BYTES >> 4);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                ptx::umma_bf16(d_tmem, ptx::make_smem_desc_sw128_halo(a_addr + k * 32, HALO_W * 128, dx, g.halo_bo),
-                                               ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, (cc | tap | k) != 0 ? 1u : 0u);
+                                ptx::umma_bf16(d_tmem, ptx::make_desc(a_lo + 2 * k, ptx::kDescHiSw128Halo),
+                                               ptx::make_desc(b_lo + 2 * k, ptx::kDescHiSw128), idesc,
+                                               (cc | tap | k) != 0 ? 1u : 0u);
                         }
                         ptx::umma_commit(&aempty[sa]);  // the nine taps of this chunk have read the halo
-                        if (++sa == NA) { sa = 0; pa ^= 1; }
                     }
-                } else {
+                    __syncwarp();
+                    if (++sa == NA) { sa = 0; pa ^= 1; }
+                }
+            } else {
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&full[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(sA + stage * A_STAGE_BYTES);
-                    const uint32_t b_addr = ptx::smem_u32(sB + stage * C::B_STAGE_BYTES);
+                    const uint32_t a_lo = sA_lo + stage * (A_STAGE_BYTES >> 4);
+                    const uint32_t b_lo = sB_lo + stage * (C::B_STAGE_BYTES >> 4);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ad = ptx::make_smem_desc_sw128(a_addr + k * 32);
-                        const uint64_t bd = ptx::make_smem_desc_sw128(b_addr + k * 32);
-                        ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k)
+                            ptx::umma_bf16(d_tmem, ptx::make_desc(a_lo + 2 * k, ptx::kDescHiSw128),
+                                           ptx::make_desc(b_lo + 2 * k, ptx::kDescHiSw128), idesc, (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_commit(&empty[stage]);
                     }
-                    ptx::umma_commit(&empty[stage]);
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                }
-                ptx::umma_commit(&tfull[as]);
-                as ^= 1;
-                if (as == 0) aphase ^= 1;
             }
+            if (ptx::elect_one()) ptx::umma_commit(&tfull[as]);
+            __syncwarp();
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
         }
     } else {
         // ---------------------------------------------------- epilogue (warps 2..9)
@@ -505,12 +511,10 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         a.M = p.B * p.H * p.W;
         a.flops = 2.0 * a.M * p.N * (static_cast<double>(p.taps) * p.C);
         static const bool halo_off = getenv("DAD_NO_HALO") != nullptr;      // bring-up A/B switches
-        // measured on B200: UMMA applies the 128B swizzle to absolute shared-memory address bits, exactly like TMA,
-        // so a row-shifted view needs base_offset = 0 (DAD_HALO_BO=1 re-enables it for experiments)
-        static const bool halo_bo_off = getenv("DAD_HALO_BO") == nullptr;
+        // (measured on B200: UMMA applies the 128B swizzle to absolute shared-memory address bits, exactly like TMA,
+        // so the row-shifted halo views need base_offset = 0 in their descriptors)
         halo = !halo_off && p.taps == 9 && bn <= 64 && cdiv(p.N, bn) == 1 &&
                static_cast<long long>(9) * cdiv(p.C, BK) * bn * BK * 2 <= WRES_BYTES;  // weights fit in smem
-        a.halo_bo = halo_bo_off ? 0 : 1;
         if (halo) {  // 16 x 8 output pixels per tile, one 18 x 16 halo box per channel chunk
             a.tw_log2 = 3;
             a.th = 16;

@@ -141,9 +141,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         __syncwarp();  // reconverge before the (warp-aligned) cluster barrier below
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
-            // ------------------------------------------------ MMA issuer (leader CTA, one thread, both SMs)
+        if (leader) {
+            // ------------------------------------------------ MMA issuer (leader CTA; warp-uniform loop, one elected lane
+            // issues for both SMs; descriptors = constant high word + (address >> 4))
             constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * BM, BN);
+            const uint32_t sA_lo = ptx::desc_lo_sw128(ptx::smem_u32(sA)), sB_lo = ptx::desc_lo_sw128(ptx::smem_u32(sB));
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -155,16 +157,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&full[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(sA + stage * A_STAGE);
-                    const uint32_t b_addr = ptx::smem_u32(sB + stage * B_STAGE);
+                    const uint32_t a_lo = sA_lo + stage * (A_STAGE >> 4), b_lo = sB_lo + stage * (B_STAGE >> 4);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16_cg2(d_tmem, ptx::make_smem_desc_sw128(a_addr + k * 32),
-                                      ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_mc(&empty[stage], 3);
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_cg2(d_tmem, ptx::make_desc(a_lo + 2 * k, ptx::kDescHiSw128),
+                                          ptx::make_desc(b_lo + 2 * k, ptx::kDescHiSw128), idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_mc(&empty[stage], 3);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_mc(&tfull[as], 3);
+                if (ptx::elect_one()) umma_commit_mc(&tfull[as], 3);
+                __syncwarp();
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
             }

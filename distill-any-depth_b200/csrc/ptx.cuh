@@ -215,6 +215,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
     return d;
 }
+// Split form of the same descriptors for the MMA issue loop: the high word is a constant, the low word is
+// (address >> 4) | LBO, so stepping along K / stages / taps is ONE integer add per operand.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, version 1, SWIZZLE_128B
+constexpr uint32_t kDescHiSw128Halo = (2048u >> 4) | (1u << 14) | (2u << 29);  // 8-row groups 2048 B apart (halo views)
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_mn_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | ((1024u >> 4) << 16); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
 // K-major SWIZZLE_128B view into a larger swizzled buffer: 8-row groups `sbo_bytes` apart, start address shifted by
 // `row_shift` rows (128 B each) from a 1024-byte aligned pattern origin -> base_offset = row_shift & 7.
 __device__ __forceinline__ uint64_t make_smem_desc_sw128_halo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t row_shift,
