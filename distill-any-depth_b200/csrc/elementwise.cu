@@ -103,36 +103,29 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* in, const f
 // ---------------------------------------------------------------- bilinear, align_corners=True (K14/K16)
 // NHWC, VEC channels per thread.  Index maths as ATen's area_pixel_compute_source_index.
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) bilinear_kernel(const T* in, T* out, int B, int Hi, int Wi, int Ho, int Wo, int C,
-                                                       float sh, float sw) {
+__global__ void __launch_bounds__(256) bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int Hi, int Wi, int Ho,
+                                                       int Wo, int C, float sh, float sw) {
+    // grid: (x-chunks, output row, image); thread -> (output column, VEC-channel group); 32-bit index maths only
     const int cv = C / VEC;
-    const long long total = static_cast<long long>(B) * Ho * Wo * cv;
-    for (long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * 256) {
-        const int c = static_cast<int>(idx % cv);
-        long long p = idx / cv;
-        const int ox = static_cast<int>(p % Wo);
-        p /= Wo;
-        const int oy = static_cast<int>(p % Ho);
-        const int b = static_cast<int>(p / Ho);
-        const float fy = sh * oy, fx = sw * ox;
-        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-        const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
-        const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-        const T* base = in + static_cast<long long>(b) * Hi * Wi * C + c * VEC;
-        const T* p00 = base + (static_cast<long long>(y0) * Wi + x0) * C;
-        const T* p01 = base + (static_cast<long long>(y0) * Wi + x1) * C;
-        const T* p10 = base + (static_cast<long long>(y1) * Wi + x0) * C;
-        const T* p11 = base + (static_cast<long long>(y1) * Wi + x1) * C;
-        struct alignas(16) Pack { T v[VEC]; };
-        const Pack a = *reinterpret_cast<const Pack*>(p00), bq = *reinterpret_cast<const Pack*>(p01);
-        const Pack cq = *reinterpret_cast<const Pack*>(p10), d = *reinterpret_cast<const Pack*>(p11);
-        Pack o;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= Wo * cv) return;
+    const int ox = i / cv, c = i - ox * cv;
+    const int oy = blockIdx.y, b = blockIdx.z;
+    const float fy = sh * oy, fx = sw * ox;
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const T* base = in + static_cast<long long>(b) * Hi * Wi * C + c * VEC;
+    const T* r0 = base + static_cast<long long>(y0) * Wi * C;
+    const T* r1 = base + static_cast<long long>(y1) * Wi * C;
+    struct alignas(16) Pack { T v[VEC]; };
+    const Pack a = *reinterpret_cast<const Pack*>(r0 + x0 * C), bq = *reinterpret_cast<const Pack*>(r0 + x1 * C);
+    const Pack cq = *reinterpret_cast<const Pack*>(r1 + x0 * C), d = *reinterpret_cast<const Pack*>(r1 + x1 * C);
+    Pack o;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j)
-            o.v[j] = from_f<T>(hy * (hx * to_f(a.v[j]) + lx * to_f(bq.v[j])) + ly * (hx * to_f(cq.v[j]) + lx * to_f(d.v[j])));
-        *reinterpret_cast<Pack*>(out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C + c * VEC) = o;
-    }
+    for (int j = 0; j < VEC; ++j)
+        o.v[j] = from_f<T>(hy * (hx * to_f(a.v[j]) + lx * to_f(bq.v[j])) + ly * (hx * to_f(cq.v[j]) + lx * to_f(d.v[j])));
+    *reinterpret_cast<Pack*>(out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C + c * VEC) = o;
 }
 
 // ---------------------------------------------------------------- 3x3 stride-2 pad-1 im2col (K12)
@@ -303,14 +296,15 @@ int bilinear_nhwc(const void* in, void* out, int is_bf16, int B, int Hi, int Wi,
     const float sh = Ho > 1 ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.f;
     const float sw = Wo > 1 ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.f;
     ProfScope prof(PROF_ELEM, static_cast<double>(B) * C * (is_bf16 ? 2 : 4) * (static_cast<double>(Hi) * Wi + static_cast<double>(Ho) * Wo), st);
+    DAD_REQUIRE(Ho <= 65535 && B <= 65535, "bilinear: output height / batch too large for the launch grid");
     if (is_bf16) {
-        const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
-        bilinear_kernel<bf16, 8><<<grid_for(total), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out),
-                                                                  B, Hi, Wi, Ho, Wo, C, sh, sw);
+        const dim3 grid(cdiv(Wo * (C / 8), 256), Ho, B);
+        bilinear_kernel<bf16, 8><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), Hi, Wi, Ho,
+                                                       Wo, C, sh, sw);
     } else {
-        const long long total = static_cast<long long>(B) * Ho * Wo * (C / 4);
-        bilinear_kernel<float, 4><<<grid_for(total), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out),
-                                                                   B, Hi, Wi, Ho, Wo, C, sh, sw);
+        const dim3 grid(cdiv(Wo * (C / 4), 256), Ho, B);
+        bilinear_kernel<float, 4><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), Hi, Wi,
+                                                        Ho, Wo, C, sh, sw);
     }
     DAD_CHECK_LAUNCH();
     return DAD_OK;

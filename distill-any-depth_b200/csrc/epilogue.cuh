@@ -78,9 +78,19 @@ struct EpiPre {
 };
 
 // grow: logical A-row index (token / input pixel); orow: output row index.
+// ConvTranspose scatter: output pixel index of input row `grow` for the (ky, kx) = (0, 0) sub-pixel
+__device__ __forceinline__ long long epilogue_scatter_base(const Epilogue& e, long long grow) {
+    const int hw = e.scat_H * e.scat_W;
+    const int b = static_cast<int>(grow / hw);
+    const int rem = static_cast<int>(grow - static_cast<long long>(b) * hw);
+    const int y = rem / e.scat_W, x = rem - y * e.scat_W;
+    return (static_cast<long long>(b) * (e.scat_k * e.scat_H) + e.scat_k * y) * (e.scat_k * e.scat_W) + e.scat_k * x;
+}
+
+// `sbase`: epilogue_scatter_base(grow) when e.scat_k != 0 (callers hoist it: it only depends on the row)
 template <int KIND = EK_GENERIC>
 __device__ __forceinline__ void epilogue_prefetch(const Epilogue& e, int N, long long grow, long long orow, int col,
-                                                  EpiPre& p) {
+                                                  EpiPre& p, long long sbase = 0) {
     constexpr bool G = KIND == EK_GENERIC || KIND == EK_GENERIC_NOGELU;
     p.bcol = col;
     p.skip = false;
@@ -89,14 +99,7 @@ __device__ __forceinline__ void epilogue_prefetch(const Epilogue& e, int N, long
         const int co = col - kk * e.scat_CoP;
         if (co >= e.scat_Co) { p.skip = true; return; }
         const int ky = kk / e.scat_k, kx = kk - ky * e.scat_k;
-        const int hw = e.scat_H * e.scat_W;
-        const int b = static_cast<int>(grow / hw);
-        const int rem = static_cast<int>(grow - static_cast<long long>(b) * hw);
-        const int y = rem / e.scat_W, x = rem - y * e.scat_W;
-        const long long opix =
-            (static_cast<long long>(b) * (e.scat_k * e.scat_H) + (e.scat_k * y + ky)) * (e.scat_k * e.scat_W) +
-            (e.scat_k * x + kx);
-        p.off = opix * e.ldc + co;
+        p.off = (sbase + static_cast<long long>(ky) * (e.scat_k * e.scat_W) + kx) * e.ldc + co;
         p.bcol = co;
     } else {
         p.off = orow * e.ldc + col;
@@ -182,7 +185,7 @@ __device__ __forceinline__ void epilogue_store4(const Epilogue& e, int N, long l
     EpiPre p;
     EpiCols c;
     epilogue_load_cols<EK_GENERIC>(e, col, c);
-    epilogue_prefetch<EK_GENERIC>(e, N, grow, orow, col, p);
+    epilogue_prefetch<EK_GENERIC>(e, N, grow, orow, col, p, e.scat_k ? epilogue_scatter_base(e, grow) : 0);
     epilogue_finish<EK_GENERIC>(e, p, c, v);
 }
 

@@ -373,6 +373,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int cg = (lane & 3) * 4;
                 constexpr int NPC = BN / 16;
                 const int c_lo = half * (NPC / 2), c_hi = c_lo + NPC / 2;
+                // the four rows this lane finishes are the same for every piece of the tile: resolve them once
+                bool ok[4];
+                long long grow4[4], sbase4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ok[i] = row_of(quarter * 32 + i * 8 + (lane >> 2), grow4[i]);
+                    sbase4[i] = (g.epi.scat_k && ok[i]) ? epilogue_scatter_base(g.epi, grow4[i]) : 0;
+                }
+                // residual rows of the NEXT tile -> L2 (they stream from HBM; without this every piece eats a DRAM latency)
+                if (g.epi.res1 != nullptr && tile + static_cast<int>(gridDim.x) < num_tiles) {
+                    const int nt = tile + gridDim.x;
+                    const int nmt = nt / g.num_n_tiles;
+                    const int nn0 = (nt - nmt * g.num_n_tiles) * BN;
+                    int nb = 0, ny0 = 0, nx0 = 0;
+                    if (g.conv) {
+                        const int per_img = g.tiles_x * g.tiles_y;
+                        nb = nmt / per_img;
+                        const int rr = nmt - nb * per_img;
+                        const int ty = rr / g.tiles_x;
+                        ny0 = ty * g.th;
+                        nx0 = (rr - ty * g.tiles_x) << g.tw_log2;
+                    }
+                    const int es1 = g.epi.res1_bf16 ? 2 : 4;
+                    const int lines = (BN * es1) >> 7;  // 128-byte lines per tile row
+                    for (int l = (warp - 2) * 32 + lane; l < BM * lines; l += 32 * NUM_EPI_WARPS) {
+                        const int r = l / lines, ln = l - r * lines;
+                        long long nrow;
+                        bool rok;
+                        if (g.conv) {
+                            const int y = ny0 + (r >> g.tw_log2), x = nx0 + (r & tw_mask);
+                            nrow = (static_cast<long long>(nb) * g.H + y) * g.W + x;
+                            rok = (y < g.H) && (x < g.W);
+                        } else {
+                            nrow = static_cast<long long>(nmt) * BM + r;
+                            rok = nrow < g.M;
+                        }
+                        if (rok && nn0 + ln * (128 / es1) < g.N) {
+                            const long long boff = (nrow * g.epi.ldc + nn0) * es1 + ln * 128;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(g.epi.res1) + boff));
+                            if (g.epi.res2 != nullptr)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(g.epi.res2) + boff));
+                        }
+                    }
+                }
 #pragma unroll 1
                 for (int c = c_lo; c < c_hi; ++c) {
                     const int col = n0 + c * 16 + cg;
@@ -388,14 +432,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                     if (col < g.N) {
                         EpiPre pre[4];
-                        bool ok[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {  // issue the residual / table loads of the 4 passes first
-                            const int rr = i * 8 + (lane >> 2);
-                            long long grow;
-                            ok[i] = row_of(quarter * 32 + rr, grow);
-                            if (ok[i]) epilogue_prefetch<KIND>(g.epi, g.N, grow, grow, col, pre[i]);
-                        }
+                        for (int i = 0; i < 4; ++i)  // issue the residual / table loads of the 4 passes first
+                            if (ok[i]) epilogue_prefetch<KIND>(g.epi, g.N, grow4[i], grow4[i], col, pre[i], sbase4[i]);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             if (ok[i]) {
