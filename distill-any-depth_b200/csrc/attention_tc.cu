@@ -13,7 +13,7 @@
 // as soon as the softmax has drained S of tile j, and the softmax of tile j+1 never waits for the tensor pipe:
 // the kernel is bounded by the exp2 throughput of the MUFU (16 / clk / SM), not by MMA latency.
 // Online softmax keeps a per-row reference maximum; O / l are rescaled (TMEM round trip) only when the running
-// maximum exceeds the reference by more than 2^8 ("lazy rescale": exact, P <= 2^8 stays well inside bf16 /
+// maximum exceeds the reference by more than 2^16 ("lazy rescale": exact, P <= 2^16 stays well inside bf16 /
 // fp32 range), so in the common case O is never touched until the final normalisation.
 #include "elementwise.h"
 #include "ptx.cuh"
@@ -32,7 +32,7 @@ constexpr int TMEM_COLS = 256;
 constexpr int S_COL = 0, P_COL = 128, O_COL = 192;  // S0 [0,64) S1 [64,128) | P0 [128,160) P1 [160,192) | O [192,256)
 constexpr int ATT_SMEM = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 1024 + 256;
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
+constexpr float RESCALE_THRESHOLD = 16.0f;  // log2 units: P <= 2^16 relative to the reference maximum
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -152,73 +152,92 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t tS = tmem + lane_base + S_COL, tP = tmem + lane_base + P_COL, tO = tmem + lane_base + O_COL;
         float m_ref = -INFINITY;  // reference maximum (log2 domain) the stored P / O / l are relative to
         float l = 0.f;
+        uint32_t v[BKV];          // the 64 scores of this row in the current key tile
+        uint32_t (&v_lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+        uint32_t (&v_hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+
+        // exp2 of one 32-column half against m_ref -> packed bf16 pairs; returns the partial row sum
+        auto exp_half = [&](const uint32_t (&x)[32], int col0, int nvalid, uint32_t (&pk)[16]) -> float {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                float p0 = ptx::ex2_approx(fmaf(__uint_as_float(x[i]), LOG2E, -m_ref));
+                float p1 = ptx::ex2_approx(fmaf(__uint_as_float(x[i + 1]), LOG2E, -m_ref));
+                if (nvalid != BKV) {
+                    if (col0 + i >= nvalid) p0 = 0.f;
+                    if (col0 + i + 1 >= nvalid) p1 = 0.f;
+                }
+                s0 += p0;
+                s1 += p1;
+                __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+                pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            return s0 + s1;
+        };
+        auto half_max = [&](const uint32_t (&x)[32], int col0, int nvalid) -> float {
+            float a = -INFINITY, b2 = -INFINITY, c2 = -INFINITY, d2 = -INFINITY;  // four independent chains
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float x0 = (col0 + i < nvalid) ? __uint_as_float(x[i]) : -INFINITY;
+                const float x1 = (col0 + i + 1 < nvalid) ? __uint_as_float(x[i + 1]) : -INFINITY;
+                const float x2 = (col0 + i + 2 < nvalid) ? __uint_as_float(x[i + 2]) : -INFINITY;
+                const float x3 = (col0 + i + 3 < nvalid) ? __uint_as_float(x[i + 3]) : -INFINITY;
+                a = fmaxf(a, x0); b2 = fmaxf(b2, x1); c2 = fmaxf(c2, x2); d2 = fmaxf(d2, x3);
+            }
+            return fmaxf(fmaxf(a, b2), fmaxf(c2, d2));
+        };
+
+        // software pipeline: the first half of tile j+1 is requested from TMEM while P_j's stores drain
+        ptx::mbar_wait(&s_full[0], 0);
+        ptx::tc_fence_after();
+        ptx::tmem_ld_32x32(tS, v_lo);
         for (int j = 0; j < T; ++j) {
             const int buf = j & 1;
-            ptx::mbar_wait(&s_full[buf], (j >> 1) & 1);
-            ptx::tc_fence_after();
             const int nvalid = min(BKV, N - j * BKV);
-            uint32_t v[64];
-            {
-                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-                uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-                ptx::tmem_ld_32x32(tS + buf * BKV, lo);
-                ptx::tmem_ld_32x32(tS + buf * BKV + 32, hi);
+            ptx::tmem_ld_wait();                                   // first half of tile j is in registers
+            ptx::tmem_ld_32x32(tS + buf * BKV + 32, v_hi);          // second half: in flight during the first exps
+            if (j == 0) {                                          // the very first tile defines the reference maximum
                 ptx::tmem_ld_wait();
+                m_ref = fmaxf(half_max(v_lo, 0, nvalid), half_max(v_hi, 32, nvalid)) * LOG2E;
             }
-            float tmax = -INFINITY;
-            if (nvalid == BKV) {
-#pragma unroll
-                for (int i = 0; i < BKV; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
-            } else {
-#pragma unroll
-                for (int i = 0; i < BKV; ++i)
-                    if (i < nvalid) tmax = fmaxf(tmax, __uint_as_float(v[i]));
-            }
-            tmax *= LOG2E;
-            if (j == 0) {
-                m_ref = tmax;
-            } else {
-                const bool need = tmax > m_ref + RESCALE_THRESHOLD;
-                if (__any_sync(0xffffffffu, need)) {
-                    // rare: rescale O (TMEM) and l to the new reference.  P V_{j-1} must have retired: o_full is in
-                    // phase j-1 or j here (P V_{j-2} retired before s_full of tile j, P V_j needs this thread's arrive)
-                    ptx::mbar_wait(o_full, (j - 1) & 1);
-                    ptx::tc_fence_after();
-                    const float alpha = need ? ptx::ex2_approx(m_ref - tmax) : 1.0f;
-                    if (need) m_ref = tmax;
-                    l *= alpha;
+            uint32_t pk[16];
+            float lt = exp_half(v_lo, 0, nvalid, pk);
+            ptx::tmem_st_32x16(tP + buf * (BKV / 2), pk);
+            const float mx_lo = half_max(v_lo, 0, nvalid);
+            ptx::tmem_ld_wait();                                   // second half arrived
+            lt += exp_half(v_hi, 32, nvalid, pk);
+            ptx::tmem_st_32x16(tP + buf * (BKV / 2) + 16, pk);
+            const float tmax = fmaxf(mx_lo, half_max(v_hi, 32, nvalid)) * LOG2E;
+            const bool need = tmax > m_ref + RESCALE_THRESHOLD;
+            if (__any_sync(0xffffffffu, need)) {
+                // rare: the running maximum left the comfort zone of the reference.  Rescale O (TMEM) and l to the new
+                // reference and redo this tile's P against it.  P V_{j-1} must have retired: o_full is in phase j-1
+                // or j here (P V_{j-2} retired before s_full of tile j, P V_j needs this thread's arrive below).
+                ptx::mbar_wait(o_full, (j - 1) & 1);
+                ptx::tc_fence_after();
+                const float alpha = need ? ptx::ex2_approx(m_ref - tmax) : 1.0f;
+                if (need) m_ref = tmax;
+                l *= alpha;
 #pragma unroll 1
-                    for (int c = 0; c < HD / 16; ++c) {
-                        uint32_t o[16];
-                        ptx::tmem_ld_32x16(tO + c * 16, o);
-                        ptx::tmem_ld_wait();
+                for (int c = 0; c < HD / 16; ++c) {
+                    uint32_t o[16];
+                    ptx::tmem_ld_32x16(tO + c * 16, o);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        ptx::tmem_st_32x16(tO + c * 16, o);
-                    }
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    ptx::tmem_st_32x16(tO + c * 16, o);
                 }
+                lt = exp_half(v_lo, 0, nvalid, pk);
+                ptx::tmem_st_32x16(tP + buf * (BKV / 2), pk);
+                lt += exp_half(v_hi, 32, nvalid, pk);
+                ptx::tmem_st_32x16(tP + buf * (BKV / 2) + 16, pk);
             }
-            // P = exp2(s * log2e - m_ref) -> bf16 pairs in TMEM (P[buf]: P V_{j-2} has retired); row sum in fp32
-            float ls0 = 0.f, ls1 = 0.f;
-#pragma unroll
-            for (int c = 0; c < BKV / 32; ++c) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[c * 32 + i]), LOG2E, -m_ref));
-                    float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[c * 32 + i + 1]), LOG2E, -m_ref));
-                    if (nvalid != BKV) {
-                        if (c * 32 + i >= nvalid) p0 = 0.f;
-                        if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
-                    }
-                    ls0 += p0;
-                    ls1 += p1;
-                    __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
-                }
-                ptx::tmem_st_32x16(tP + buf * (BKV / 2) + c * 16, pk);
+            l += lt;
+            if (j + 1 < T) {                                       // request the next tile's first half before draining
+                ptx::mbar_wait(&s_full[buf ^ 1], ((j + 1) >> 1) & 1);
+                ptx::tc_fence_after();
+                ptx::tmem_ld_32x32(tS + (buf ^ 1) * BKV, v_lo);
             }
-            l += ls0 + ls1;
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             ptx::mbar_arrive(&p_full[buf]);

@@ -102,30 +102,43 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* in, const f
 
 // ---------------------------------------------------------------- bilinear, align_corners=True (K14/K16)
 // NHWC, VEC channels per thread.  Index maths as ATen's area_pixel_compute_source_index.
+constexpr int BIL_ROWS = 8;  // output rows per thread (amortises index maths, keeps 8 independent row pairs in flight)
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int Hi, int Wi, int Ho,
                                                        int Wo, int C, float sh, float sw) {
-    // grid: (x-chunks, output row, image); thread -> (output column, VEC-channel group); 32-bit index maths only
+    // grid: (x-chunks, output row groups, image); thread -> (output column, VEC-channel group) x BIL_ROWS rows
     const int cv = C / VEC;
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= Wo * cv) return;
     const int ox = i / cv, c = i - ox * cv;
-    const int oy = blockIdx.y, b = blockIdx.z;
-    const float fy = sh * oy, fx = sw * ox;
-    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
-    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const int b = blockIdx.z;
+    const float fx = sw * ox;
+    const int x0 = static_cast<int>(fx);
+    const int x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float lx = fx - x0, hx = 1.f - lx;
     const T* base = in + static_cast<long long>(b) * Hi * Wi * C + c * VEC;
-    const T* r0 = base + static_cast<long long>(y0) * Wi * C;
-    const T* r1 = base + static_cast<long long>(y1) * Wi * C;
+    T* obase = out + static_cast<long long>(b) * Ho * Wo * C + static_cast<long long>(ox) * C + c * VEC;
     struct alignas(16) Pack { T v[VEC]; };
-    const Pack a = *reinterpret_cast<const Pack*>(r0 + x0 * C), bq = *reinterpret_cast<const Pack*>(r0 + x1 * C);
-    const Pack cq = *reinterpret_cast<const Pack*>(r1 + x0 * C), d = *reinterpret_cast<const Pack*>(r1 + x1 * C);
-    Pack o;
+    const int oy0 = blockIdx.y * BIL_ROWS;
+#pragma unroll 4
+    for (int r = 0; r < BIL_ROWS; ++r) {
+        const int oy = oy0 + r;
+        if (oy >= Ho) break;
+        const float fy = sh * oy;
+        const int y0 = static_cast<int>(fy);
+        const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0);
+        const float ly = fy - y0, hy = 1.f - ly;
+        const T* r0 = base + static_cast<long long>(y0) * Wi * C;
+        const T* r1 = base + static_cast<long long>(y1) * Wi * C;
+        const Pack a = *reinterpret_cast<const Pack*>(r0 + x0 * C), bq = *reinterpret_cast<const Pack*>(r0 + x1 * C);
+        const Pack cq = *reinterpret_cast<const Pack*>(r1 + x0 * C), d = *reinterpret_cast<const Pack*>(r1 + x1 * C);
+        Pack o;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j)
-        o.v[j] = from_f<T>(hy * (hx * to_f(a.v[j]) + lx * to_f(bq.v[j])) + ly * (hx * to_f(cq.v[j]) + lx * to_f(d.v[j])));
-    *reinterpret_cast<Pack*>(out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C + c * VEC) = o;
+        for (int j = 0; j < VEC; ++j)
+            o.v[j] = from_f<T>(hy * (hx * to_f(a.v[j]) + lx * to_f(bq.v[j])) + ly * (hx * to_f(cq.v[j]) + lx * to_f(d.v[j])));
+        *reinterpret_cast<Pack*>(obase + static_cast<long long>(oy) * Wo * C) = o;
+    }
 }
 
 // ---------------------------------------------------------------- 3x3 stride-2 pad-1 im2col (K12)
@@ -298,11 +311,11 @@ int bilinear_nhwc(const void* in, void* out, int is_bf16, int B, int Hi, int Wi,
     ProfScope prof(PROF_ELEM, static_cast<double>(B) * C * (is_bf16 ? 2 : 4) * (static_cast<double>(Hi) * Wi + static_cast<double>(Ho) * Wo), st);
     DAD_REQUIRE(Ho <= 65535 && B <= 65535, "bilinear: output height / batch too large for the launch grid");
     if (is_bf16) {
-        const dim3 grid(cdiv(Wo * (C / 8), 256), Ho, B);
+        const dim3 grid(cdiv(Wo * (C / 8), 256), cdiv(Ho, BIL_ROWS), B);
         bilinear_kernel<bf16, 8><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), Hi, Wi, Ho,
                                                        Wo, C, sh, sw);
     } else {
-        const dim3 grid(cdiv(Wo * (C / 4), 256), Ho, B);
+        const dim3 grid(cdiv(Wo * (C / 4), 256), cdiv(Ho, BIL_ROWS), B);
         bilinear_kernel<float, 4><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), Hi, Wi,
                                                         Ho, Wo, C, sh, sw);
     }
