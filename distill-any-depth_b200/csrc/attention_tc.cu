@@ -15,6 +15,8 @@
 // Online softmax keeps a per-row reference maximum; O / l are rescaled (TMEM round trip) only when the running
 // maximum exceeds the reference by more than 2^16 ("lazy rescale": exact, P <= 2^16 stays well inside bf16 /
 // fp32 range), so in the common case O is never touched until the final normalisation.
+#include <type_traits>
+
 #include "elementwise.h"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -156,14 +158,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t (&v_lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
         uint32_t (&v_hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
 
-        // exp2 of one 32-column half against m_ref -> packed bf16 pairs; returns the partial row sum
-        auto exp_half = [&](const uint32_t (&x)[32], int col0, int nvalid, uint32_t (&pk)[16]) -> float {
+        // exp2 of one 32-column half against m_ref -> packed bf16 pairs; returns the partial row sum.
+        // Full tiles (all but the last) take the unmasked instantiation: FFMA + MUFU + FADD per element.
+        auto exp_half = [&](auto masked, const uint32_t (&x)[32], int col0, int nvalid, uint32_t (&pk)[16]) -> float {
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
                 float p0 = ptx::ex2_approx(fmaf(__uint_as_float(x[i]), LOG2E, -m_ref));
                 float p1 = ptx::ex2_approx(fmaf(__uint_as_float(x[i + 1]), LOG2E, -m_ref));
-                if (nvalid != BKV) {
+                if (decltype(masked)::value) {
                     if (col0 + i >= nvalid) p0 = 0.f;
                     if (col0 + i + 1 >= nvalid) p1 = 0.f;
                 }
@@ -174,7 +177,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             return s0 + s1;
         };
-        auto half_max = [&](const uint32_t (&x)[32], int col0, int nvalid) -> float {
+        auto half_max = [&](const uint32_t (&x)[32], int col0, int nvalid) -> float {  // first tile / rare path only
             float a = -INFINITY, b2 = -INFINITY, c2 = -INFINITY, d2 = -INFINITY;  // four independent chains
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -186,6 +189,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             return fmaxf(fmaxf(a, b2), fmaxf(c2, d2));
         };
+        using TrueT = std::true_type;
+        using FalseT = std::false_type;
+        constexpr float P_LIMIT = 65536.0f;  // 2^RESCALE_THRESHOLD
 
         // software pipeline: the first half of tile j+1 is requested from TMEM while P_j's stores drain
         ptx::mbar_wait(&s_full[0], 0);
@@ -201,35 +207,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 m_ref = fmaxf(half_max(v_lo, 0, nvalid), half_max(v_hi, 32, nvalid)) * LOG2E;
             }
             uint32_t pk[16];
-            float lt = exp_half(v_lo, 0, nvalid, pk);
-            ptx::tmem_st_32x16(tP + buf * (BKV / 2), pk);
-            const float mx_lo = half_max(v_lo, 0, nvalid);
-            ptx::tmem_ld_wait();                                   // second half arrived
-            lt += exp_half(v_hi, 32, nvalid, pk);
+            float lt;
+            if (nvalid == BKV) {
+                lt = exp_half(FalseT{}, v_lo, 0, nvalid, pk);
+                ptx::tmem_st_32x16(tP + buf * (BKV / 2), pk);
+                ptx::tmem_ld_wait();                               // second half arrived
+                lt += exp_half(FalseT{}, v_hi, 32, nvalid, pk);
+            } else {
+                lt = exp_half(TrueT{}, v_lo, 0, nvalid, pk);
+                ptx::tmem_st_32x16(tP + buf * (BKV / 2), pk);
+                ptx::tmem_ld_wait();
+                lt += exp_half(TrueT{}, v_hi, 32, nvalid, pk);
+            }
             ptx::tmem_st_32x16(tP + buf * (BKV / 2) + 16, pk);
-            const float tmax = fmaxf(mx_lo, half_max(v_hi, 32, nvalid)) * LOG2E;
-            const bool need = tmax > m_ref + RESCALE_THRESHOLD;
+            // some P above 2^16 <=> some score more than 16 (log2 units) above the reference: seen in the row sum,
+            // so the common path carries no max tracking at all
+            const bool need = !(lt <= P_LIMIT);
             if (__any_sync(0xffffffffu, need)) {
-                // rare: the running maximum left the comfort zone of the reference.  Rescale O (TMEM) and l to the new
-                // reference and redo this tile's P against it.  P V_{j-1} must have retired: o_full is in phase j-1
-                // or j here (P V_{j-2} retired before s_full of tile j, P V_j needs this thread's arrive below).
-                ptx::mbar_wait(o_full, (j - 1) & 1);
-                ptx::tc_fence_after();
+                // rare: rescale O (TMEM) and l to the true running maximum and redo this tile's P against it.
+                // P V_{j-1} must have retired: o_full is in phase j-1 or j here (P V_{j-2} retired before s_full of
+                // tile j, P V_j needs this thread's arrive below).
+                if (j > 0) {
+                    ptx::mbar_wait(o_full, (j - 1) & 1);
+                    ptx::tc_fence_after();
+                }
+                const float tmax = fmaxf(half_max(v_lo, 0, nvalid), half_max(v_hi, 32, nvalid)) * LOG2E;
                 const float alpha = need ? ptx::ex2_approx(m_ref - tmax) : 1.0f;
                 if (need) m_ref = tmax;
                 l *= alpha;
+                if (j > 0) {
 #pragma unroll 1
-                for (int c = 0; c < HD / 16; ++c) {
-                    uint32_t o[16];
-                    ptx::tmem_ld_32x16(tO + c * 16, o);
-                    ptx::tmem_ld_wait();
+                    for (int c = 0; c < HD / 16; ++c) {
+                        uint32_t o[16];
+                        ptx::tmem_ld_32x16(tO + c * 16, o);
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    ptx::tmem_st_32x16(tO + c * 16, o);
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        ptx::tmem_st_32x16(tO + c * 16, o);
+                    }
                 }
-                lt = exp_half(v_lo, 0, nvalid, pk);
+                lt = exp_half(TrueT{}, v_lo, 0, nvalid, pk);
                 ptx::tmem_st_32x16(tP + buf * (BKV / 2), pk);
-                lt += exp_half(v_hi, 32, nvalid, pk);
+                lt += exp_half(TrueT{}, v_hi, 32, nvalid, pk);
                 ptx::tmem_st_32x16(tP + buf * (BKV / 2) + 16, pk);
             }
             l += lt;
