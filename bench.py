@@ -37,10 +37,32 @@ def parse():
     ap.add_argument("--size", type=int, default=518)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],
+                    help="c3 (default, the metric's config): ViT-L 518^2 B=32 bf16 fwd + SSI + HDN-DR; the others are "
+                         "BASELINE.json's remaining GPU configs, for DESIGN.md's table (not bench lines): c2 ViT-B 392^2 "
+                         "B=16 + SSI/grad; c4 distillation step teacher ViT-L + student ViT-B 392^2 B=16/GPU, 5 losses; "
+                         "c5 ViT-L 1036^2 forward, batch 8 split over the GPUs (strong scaling)")
+    a = ap.parse_args()
+    if a.workload == "c2":
+        a.encoder, a.size, a.batch = "vitb", 392, 16
+    elif a.workload == "c4":
+        a.encoder, a.size, a.batch = "vitb", 392, 16
+    elif a.workload == "c5":
+        a.encoder, a.size, a.batch = "vitl", 1036, max(1, 8 // max(a.gpus, 1))
+    return a
 
 
 def workload_name(a):
+    if a.workload == "c2":
+        return (f"DepthAnythingV2 vitb/128 392x392 batch {a.batch}/GPU {a.precision} forward + SSI + gradient loss "
+                f"(BASELINE configs[1])")
+    if a.workload == "c4":
+        return (f"distillation step: DepthAnything vitl teacher + DepthAnythingV2 vitb student (two student forwards as "
+                f"upstream) 392x392 batch {a.batch}/GPU {a.precision}, SC/LG(hybrid) + feature + gradient + HDN-DR losses "
+                f"(BASELINE configs[3], forward half)")
+    if a.workload == "c5":
+        return (f"DepthAnythingV2 vitl 1036x1036 (5476 tokens) batch {a.batch}/GPU {a.precision} forward "
+                f"(BASELINE configs[4]; batch 8 split over the GPUs)")
     return (f"DepthAnythingV2 {a.encoder} {a.size}x{a.size} batch {a.batch}/GPU {a.precision} forward + "
             f"SSI + HDN-DR(level 3) loss, synthetic images, random-init weights (BASELINE configs[2] + loss)")
 
@@ -190,7 +212,29 @@ def run_b200(a):
     copy_stream = torch.cuda.Stream(dev)
     x_stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
 
+    teacher = None
+    if a.workload == "c4":
+        from distill_any_depth_b200.dam import student_to_teacher_keys
+        tkw = synthetic.MODEL_PRESETS["vitl"]
+        teacher = d.DepthAnything(**tkw)
+        teacher.load_state_dict(student_to_teacher_keys(synthetic.make_state_dict(seed=2, head_bias=0.6, **tkw)), strict=True)
+        teacher = teacher.to(dev).eval()
+        teacher.precision = a.precision
+
+    def step_c4(x):
+        out = d.distillation_step_losses(model, teacher, x, x)
+        return torch.stack([out["batch_loss"], out["hdn_loss"]])
+
     def losses_of(depth):
+        if a.workload == "c5":   # forward only; the D2H read is one element of the depth map
+            return depth.view(-1)[:2].clone()
+        if a.workload == "c2":
+            ssi, p1 = losses._ssi(depth, gt, full, False, want_partials=True)
+            gr, p2 = losses._grad(depth, want_partials=True)
+            if world > 1:
+                out = finish_losses({"ssi": ("ssi", p1), "grad": ("grad", p2)})
+                return torch.stack([out["ssi"], out["grad"]])
+            return torch.stack([ssi, gr])
         ssi, p1 = losses._ssi(depth, gt, full, False, want_partials=True)
         hdn, p2 = losses.hdn_loss_dr(depth, gt, None, 3, want_partials=True)
         if world > 1:  # full-batch losses: ONE all-reduce of the (num, den) partials
@@ -199,6 +243,8 @@ def run_b200(a):
         return torch.stack([ssi, hdn])
 
     def step_device():
+        if a.workload == "c4":
+            return step_c4(x_dev)
         depth, _ = model(x_dev)
         return losses_of(depth)
 
@@ -209,6 +255,8 @@ def run_b200(a):
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         torch.cuda.current_stream().wait_event(ev)
+        if a.workload == "c4":
+            return step_c4(buf).cpu()
         depth, _ = model(buf)
         return losses_of(depth).cpu()  # D2H read of the step's result
 
@@ -260,6 +308,13 @@ def run_b200(a):
             prof[name] = dict(ms_per_step=ms_.value / psteps, launches_per_step=n.value / psteps,
                               work_per_step=work.value / psteps, avg_launch_ms=ms_.value / n.value)
     lib.dad_profile_enable(0)
+    pk_ = peaks()
+    for name, rec in prof.items():  # every class against ITS roofline (tensor for GEMM / attention, HBM for the rest)
+        per_s = rec["work_per_step"] / (rec["ms_per_step"] * 1e-3)
+        if name in ("gemm_tc", "gemm_simt", "attention"):
+            rec.update(bound="tensor", achieved_tflops=per_s / 1e12, frac=per_s / 1e12 / pk_["tf_sustained"])
+        else:
+            rec.update(bound="hbm", achieved_gbs=per_s / 1e9, frac=per_s / 1e9 / pk_["hbm"])
 
     if rank != 0:
         if world > 1:
@@ -281,7 +336,8 @@ def run_b200(a):
                         launches_per_step=gt_["launches_per_step"], avg_launch_ms=gt_["avg_launch_ms"],
                         share_of_step=gt_["ms_per_step"] / (ms_dev / a.steps))
     line = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
-                ms_per_step=ms_dev / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                ms_per_step=ms_dev / a.steps, higher_is_better=True, scaling="strong" if a.workload == "c5" else "weak",
+                vs_baseline=None,
                 dtype=a.precision, data="synthetic",
                 config=dict(workload=workload_name(a), global_batch=B * world, per_gpu_batch=B,
                             parallelism=f"dp{world} (images sharded by rank; one all-reduce of loss partials per step)",
@@ -290,7 +346,7 @@ def run_b200(a):
                 e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=int(x_host.numel() * 4),
                          d2h_bytes_per_step=8, ms_per_step=ms_e2e / a.steps),
                 gpu_launches=int(launches), clocks=sampler.result(), roofline=roofline, kernel_breakdown=prof)
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and a.workload == "c3":
         line["cpu_baseline"] = cpu_baseline(a)
     print(json.dumps(line), flush=True)
     if world > 1:

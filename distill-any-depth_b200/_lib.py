@@ -30,6 +30,8 @@ PROTOTYPES = {
     "dad_masked_shift_and_scale": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dad_ssi_loss": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dad_contexts_dr": (_i, [_i, _vp, _vp, _i, _i64, _vp, _vp, _sz, _vp]),
+    "dad_contexts_dp": (_i, [_i, _vp, _vp, _i, _i64, _vp, _vp, _sz, _vp]),
+    "dad_contexts_ds": (_i, [_i, _vp, _i, _i, _i, _vp, _vp]),
     "dad_hdn_loss_dr": (_i, [_i, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dad_hdn_loss": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dad_grad_loss": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -29,6 +29,15 @@ int dad_contexts_dr(int level, const float* gt, const uint8_t* mask, int B, int6
     return dad::contexts_dr(level, gt, mask, B, L, ctx_out, ws, wsb, ST(stream));
 }
 
+int dad_contexts_dp(int level, const float* gt, const uint8_t* mask, int B, int64_t L, uint8_t* ctx_out, void* ws,
+                    size_t wsb, void* stream) {
+    return dad::contexts_dp(level, gt, mask, B, L, ctx_out, ws, wsb, ST(stream));
+}
+
+int dad_contexts_ds(int level, const uint8_t* mask, int B, int H, int W, uint8_t* ctx_out, void* stream) {
+    return dad::contexts_ds(level, mask, B, H, W, ctx_out, ST(stream));
+}
+
 int dad_hdn_loss_dr(int level, const float* pred, const float* gt, const uint8_t* mask, int B, int64_t L,
                     float* out_scalar, double* partials, void* ws, size_t wsb, void* stream) {
     return dad::hdn_loss_dr(level, pred, gt, mask, B, L, out_scalar, partials, ws, wsb, ST(stream));

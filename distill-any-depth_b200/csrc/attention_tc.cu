@@ -15,6 +15,7 @@
 // Online softmax keeps a per-row reference maximum; O / l are rescaled (TMEM round trip) only when the running
 // maximum exceeds the reference by more than 2^16 ("lazy rescale": exact, P <= 2^16 stays well inside bf16 /
 // fp32 range), so in the common case O is never touched until the final normalisation.
+#include <cstdlib>
 #include <type_traits>
 
 #include "elementwise.h"
@@ -36,6 +37,9 @@ constexpr int ATT_SMEM = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 1024 + 256;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 16.0f;  // log2 units: P <= 2^16 relative to the reference maximum
 
+// POLY = how many of every 8 exponentials are evaluated by ptx::ex2_fma on the FMA pipe instead of the MUFU
+// (the softmax is bounded by the 16 exp2 / clk / SM of the MUFU, while the FMA pipe has slack).
+template <int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int N, int D) {
@@ -164,8 +168,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-                float p0 = ptx::ex2_approx(fmaf(__uint_as_float(x[i]), LOG2E, -m_ref));
-                float p1 = ptx::ex2_approx(fmaf(__uint_as_float(x[i + 1]), LOG2E, -m_ref));
+                // elements 1, 5 (POLY >= 2), 3 (POLY >= 3), 7 (POLY >= 4) of every 8 go to the FMA pipe
+                const int e1 = (i + 1) & 7;
+                const bool poly1 = (POLY >= 2 && (e1 == 1 || e1 == 5)) || (POLY >= 3 && e1 == 3) || (POLY >= 4 && e1 == 7);
+                const float a0 = fmaf(__uint_as_float(x[i]), LOG2E, -m_ref);
+                const float a1 = fmaf(__uint_as_float(x[i + 1]), LOG2E, -m_ref);
+                float p0 = ptx::ex2_approx(a0);
+                float p1 = poly1 ? ptx::ex2_fma(a1) : ptx::ex2_approx(a1);
                 if (decltype(masked)::value) {
                     if (col0 + i >= nvalid) p0 = 0.f;
                     if (col0 + i + 1 >= nvalid) p1 = 0.f;
@@ -300,10 +309,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // qkv [B*N, 3*D] bf16 (q pre-scaled) -> out [B*N, D] bf16
 int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st) {
     const int D = heads * HD;
-    static bool configured = false;
-    if (!configured) {
-        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        configured = true;
+    static int poly = -1;
+    if (poly < 0) {
+        const char* e = getenv("DAD_ATT_POLY");  // A/B switch: exponentials per 8 moved from the MUFU to the FMA pipe
+        poly = e ? atoi(e) : 2;
+        if (poly != 0 && poly != 2 && poly != 3 && poly != 4) poly = 2;
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     }
     CUtensorMap tm[3];
     for (int i = 0; i < 3; ++i) {
@@ -313,7 +327,12 @@ int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream
         DAD_TRY(make_tmap_bf16(&tm[i], qkv + static_cast<long long>(i) * D, 3, dims, strides, box));
     }
     const dim3 grid(cdiv(N, BQ), heads, B);
-    attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D);
+    switch (poly) {
+        case 0: attention_tc_kernel<0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
+        case 3: attention_tc_kernel<3><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
+        case 4: attention_tc_kernel<4><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
+        default: attention_tc_kernel<2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
+    }
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

@@ -20,6 +20,7 @@ namespace {
 constexpr int MODE_MASK = 0;  // K = 1: optional u8 mask [B, L]
 constexpr int MODE_DR = 1;    // K = 2^level - 1 depth-range contexts from gt + optional mask
 constexpr int MODE_CTX = 2;   // K explicit u8 contexts [K, B, L]
+constexpr int MODE_RANK = 3;  // K order statistics of ONE array over the optional mask (quantile bins, HDN-DP)
 constexpr int MAX_K = 21;
 constexpr int THREADS = 256;
 
@@ -38,6 +39,7 @@ struct SelArgs {
     const uint8_t* mask;   // [B, L] or null
     const uint8_t* ctx;    // [K, B, L] (MODE_CTX)
     int B, K, level, narr; // narr = 2 (pred, gt) or 1 (pred only)
+    int nq;                // MODE_RANK: quantile points q_j = j / (nq - 1); row 2j = floor rank, 2j + 1 = ceil rank
     long long L;
     int chunk;             // pixels per CTA
     // workspace
@@ -74,6 +76,9 @@ __device__ __forceinline__ uint32_t member_bits(const SelArgs& a, int b, long lo
                                                 const float* hi, bool has_valid) {
     if (MODE == MODE_MASK) {
         return a.mask ? (a.mask[static_cast<long long>(b) * a.L + i] != 0 ? 1u : 0u) : 1u;
+    } else if (MODE == MODE_RANK) {
+        const bool valid = a.mask ? a.mask[static_cast<long long>(b) * a.L + i] != 0 : true;
+        return valid ? ((1u << a.K) - 1u) : 0u;
     } else if (MODE == MODE_DR) {
         const bool valid = a.mask ? a.mask[static_cast<long long>(b) * a.L + i] != 0 : true;
         if (!valid || !has_valid) return 0u;
@@ -190,6 +195,13 @@ __global__ void __launch_bounds__(THREADS) sel_hist_kernel(const SelArgs a, int 
     }
 }
 
+// rank of quantile point j among n non-NaN values as ATen computes it (aten/native/Sorting.cpp quantile_compute):
+// fp32 q = j / (nq - 1) times fp32(n - 1), one rounding.
+__device__ __forceinline__ float quantile_rank(int j, int nq, uint32_t n) {
+    const float q = static_cast<float>(j) / static_cast<float>(nq - 1);  // powers of two: exact
+    return __fmul_rn(q, static_cast<float>(n - 1u));
+}
+
 // one warp per row: locate the bin that holds rank k, extend the prefix
 __global__ void __launch_bounds__(THREADS) sel_scan_kernel(const SelArgs a, int pass) {
     const int r = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
@@ -208,6 +220,11 @@ __global__ void __launch_bounds__(THREADS) sel_scan_kernel(const SelArgs a, int 
     uint32_t k;
     if (pass == 0) {
         k = total ? (total - 1) / 2 : 0;  // lower median rank
+        if (a.nq > 0 && total) {          // quantile order statistic (torch.nanquantile, 'linear' interpolation)
+            const int kk = r % a.K;
+            const float rk = quantile_rank(kk >> 1, a.nq, total);
+            k = static_cast<uint32_t>((kk & 1) ? ceilf(rk) : floorf(rk));
+        }
         if (lane == 0) a.count[r] = total;
     } else {
         k = a.krank[r];
@@ -513,6 +530,62 @@ __global__ void __launch_bounds__(THREADS) contexts_dr_kernel(const SelArgs a, u
     }
 }
 
+// ---------------------------------------------------------------- HDN-DP context export (bool [K,B,L])
+// get_contexts_dp (tools/train_distillation.py:578-644): bins between nanquantile(i * bin) and nanquantile((i + 1) * bin)
+// of the valid gt values; 'linear' interpolation = lerp(sorted[floor r], sorted[ceil r], r - floor r) with ATen's
+// fused form (fma(w, d, lo) for w < 0.5, fma(w - 1, d, hi) otherwise); an image without valid pixels has NaN
+// quantiles, i.e. empty contexts.
+__global__ void __launch_bounds__(THREADS) contexts_dp_kernel(const SelArgs a, uint8_t* out) {
+    __shared__ float Q[MAX_K];
+    const int b = blockIdx.y;
+    const uint32_t n = a.count[row_of(a, 0, b, 0)];
+    if (threadIdx.x < a.nq && n) {
+        const int j = threadIdx.x;
+        const float lo = a.t[row_of(a, 0, b, 2 * j)], hi = a.t[row_of(a, 0, b, 2 * j + 1)];
+        const float rk = quantile_rank(j, a.nq, n);
+        const float w = __fsub_rn(rk, floorf(rk));
+        const float d = __fsub_rn(hi, lo);
+        Q[j] = (w < 0.5f) ? __fmaf_rn(w, d, lo) : __fmaf_rn(__fsub_rn(w, 1.0f), d, hi);
+    }
+    __syncthreads();
+    const int nb = a.nq - 1;  // finest level: nb bins
+    const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
+    const long long end = min(start + a.chunk, a.L);
+    const int K = (nb << 1) - 1;
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        const float g = a.gt[b * a.L + i];
+        const bool valid = n && (a.mask ? a.mask[b * a.L + i] != 0 : true);
+        int k = 0;
+        for (int step = 1; step <= nb; step <<= 1)        // bins of `step` finest bins each, finest level first
+            for (int j = 0; j < nb; j += step, ++k)
+                out[(static_cast<long long>(k) * a.B + b) * a.L + i] = valid && g >= Q[j] && g < Q[j + step];
+        (void)K;
+    }
+}
+
+// ---------------------------------------------------------------- HDN-DS context export (bool [K,B,H,W])
+// get_contexts_ds / init_temp_masks_ds (:646-673): an n x n grid of [int(h*size/n), int((h+1)*size/n)) squares per
+// level (size = W; the reference needs square maps), AND-ed with the valid mask.
+__global__ void __launch_bounds__(THREADS) contexts_ds_kernel(const uint8_t* mask, int B, int H, int W, int level,
+                                                              uint8_t* out) {
+    const int b = blockIdx.y;
+    const long long L = static_cast<long long>(H) * W;
+    const int nb = 1 << (level - 1);
+    for (long long i = static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x; i < L;
+         i += static_cast<long long>(gridDim.x) * THREADS) {
+        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<long long>(y) * W);
+        const bool valid = mask ? mask[b * L + i] != 0 : true;
+        int k = 0;
+        for (int n = nb; n >= 1; n >>= 1)
+            for (int h = 0; h < n; ++h) {
+                const bool iny = y >= (h * W) / n && y < ((h + 1) * W) / n;
+                for (int w = 0; w < n; ++w, ++k)
+                    out[(static_cast<long long>(k) * B + b) * L + i] =
+                        valid && iny && x >= (w * W) / n && x < ((w + 1) * W) / n;
+            }
+    }
+}
+
 // ---------------------------------------------------------------- Sobel gradient loss
 __global__ void __launch_bounds__(THREADS) sobel_kernel(const float* d, int H, int W, double* acc) {
     const int b = blockIdx.z;
@@ -762,6 +835,41 @@ int contexts_dr(int level, const float* gt, const uint8_t* mask, int B, long lon
     init_minmax_kernel<<<cdiv(B, 128), 128, 0, st>>>(a.minmax, B);
     minmax_kernel<<<grid, THREADS, 0, st>>>(gt, mask, L, a.chunk, a.minmax);
     contexts_dr_kernel<<<grid, THREADS, 0, st>>>(a, ctx_out);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int contexts_dp(int level, const float* gt, const uint8_t* mask, int B, long long L, uint8_t* ctx_out, void* ws,
+                size_t ws_bytes, cudaStream_t st) {
+    DAD_REQUIRE(level >= 1 && level <= 4, "contexts_dp: level=%d unsupported (1..4)", level);
+    DAD_REQUIRE(gt && ctx_out && B > 0 && L > 0, "contexts_dp: bad arguments");
+    SelArgs a{};
+    a.nq = (1 << (level - 1)) + 1;
+    a.gt = gt; a.pred = gt; a.mask = mask; a.B = B; a.K = 2 * a.nq; a.level = level; a.narr = 1; a.L = L;
+    a.chunk = pick_chunk(L, B);
+    size_t zero_bytes = 0;
+    DAD_TRY(carve(a, ws, ws_bytes, &zero_bytes));
+    DAD_CHECK_CUDA(cudaMemsetAsync(ws, 0, zero_bytes, st));
+    const dim3 grid(static_cast<unsigned>(cdivl(L, a.chunk)), B);
+    const size_t sm_hist = static_cast<size_t>(a.K) * 256 * 4 + a.K * 4 + 2 * a.K * 4;
+    DAD_REQUIRE(sm_hist <= 48 * 1024, "contexts_dp: histogram does not fit");
+    for (int pass = 0; pass < 4; ++pass) {
+        sel_hist_kernel<MODE_RANK><<<grid, THREADS, sm_hist, st>>>(a, pass);
+        sel_scan_kernel<<<cdiv(a.R, THREADS / 32), THREADS, 0, st>>>(a, pass);
+    }
+    contexts_dp_kernel<<<grid, THREADS, 0, st>>>(a, ctx_out);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int contexts_ds(int level, const uint8_t* mask, int B, int H, int W, uint8_t* ctx_out, cudaStream_t st) {
+    DAD_REQUIRE(level >= 1 && level <= 3, "contexts_ds: level=%d unsupported (1..3: at most 21 contexts)", level);
+    DAD_REQUIRE(ctx_out && B > 0 && H > 0 && W > 0, "contexts_ds: bad arguments");
+    DAD_REQUIRE(H == W, "contexts_ds: the reference's template masks are size x size with size = W; H=%d != W=%d", H, W);
+    const long long L = static_cast<long long>(H) * W;
+    const long long want = cdivl(L, THREADS);
+    const dim3 grid(static_cast<unsigned>(want < 148 * 4 ? want : 148 * 4), B);
+    contexts_ds_kernel<<<grid, THREADS, 0, st>>>(mask, B, H, W, level, ctx_out);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

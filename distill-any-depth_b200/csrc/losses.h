@@ -17,6 +17,10 @@ int hdn_loss_ctx(const float* pred, const float* gt, const uint8_t* ctx, int K, 
                  double* partials, void* ws, size_t ws_bytes, cudaStream_t st);
 int contexts_dr(int level, const float* gt, const uint8_t* mask, int B, long long L, uint8_t* ctx_out, void* ws,
                 size_t ws_bytes, cudaStream_t st);
+// quantile-bin (DP) and spatial-grid (DS) HDN contexts; the HDN loss over them goes through hdn_loss_ctx
+int contexts_dp(int level, const float* gt, const uint8_t* mask, int B, long long L, uint8_t* ctx_out, void* ws,
+                size_t ws_bytes, cudaStream_t st);
+int contexts_ds(int level, const uint8_t* mask, int B, int H, int W, uint8_t* ctx_out, cudaStream_t st);
 int grad_loss(const float* depth, int B, int H, int W, float* out_scalar, double* partials, void* ws, size_t ws_bytes,
               cudaStream_t st);
 int feat_cos_loss(const float* s, const float* t, int B, int N, int Ds, int Dt, float* out_scalar, double* partials,

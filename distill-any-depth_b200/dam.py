@@ -5,6 +5,31 @@
 from .dpt import DinoV2Params, DPTHead, INTERMEDIATE_LAYER_IDX, _NativeDepthModel
 
 
+def teacher_to_student_keys(sd):
+    """``backbone.blocks.0.N.*`` / ``backbone.*`` (teacher, ViT_DINO.py:592) -> ``pretrained.blocks.N.*`` /
+    ``pretrained.*`` (student, dpt.py:196) for every key of a state dict; other keys pass through."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("backbone.blocks.0."):
+            k = "pretrained.blocks." + k[len("backbone.blocks.0."):]
+        elif k.startswith("backbone."):
+            k = "pretrained." + k[len("backbone."):]
+        out[k] = v
+    return out
+
+
+def student_to_teacher_keys(sd):
+    """Inverse of :func:`teacher_to_student_keys` (what ``tools/convert_checkpoint.py:7-28`` does to a DAv2 file)."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("pretrained.blocks."):
+            k = "backbone.blocks.0." + k[len("pretrained.blocks."):]
+        elif k.startswith("pretrained."):
+            k = "backbone." + k[len("pretrained."):]
+        out[k] = v
+    return out
+
+
 class DepthAnything(_NativeDepthModel):
     _encoder_attr = "backbone"
 
@@ -33,11 +58,7 @@ class DepthAnything(_NativeDepthModel):
         self._init_native(encoder, features, out_channels)
 
     def _student_key(self, k):
-        if k.startswith("backbone.blocks.0."):
-            return "pretrained.blocks." + k[len("backbone.blocks.0."):]
-        if k.startswith("backbone."):
-            return "pretrained." + k[len("backbone."):]
-        return k
+        return next(iter(teacher_to_student_keys({k: None})))
 
     def forward(self, x):
         """-> (depth [B,1,H,W], features[3][0])  (dam.py:396-419; the identity-size interpolate at :412 is exact)."""

@@ -177,14 +177,40 @@ def hdn_loss_dr(depth_preds, depth_gt, mask_valid=None, level=3, want_partials=F
 
 
 def get_contexts_dp(level, depth_gt, mask_valid):
-    raise NotImplementedError("HDN-DP contexts (tools/train_distillation.py:578-644) are outside the hot path "
-                              "(train() only wires 'dr', :1547); build them with the reference and pass the bool "
-                              "tensor to compute_hdn_loss")
+    """``:578-644`` -> bool ``[2**level - 1, B, 1, H, W]``: depth-percentile bins between the
+    ``nanquantile`` values of the valid pixels (exact order statistics by radix select + ATen's lerp)."""
+    g = _f32(depth_gt, "depth_gt")
+    if g.dim() != 4 or g.shape[1] != 1:
+        raise ValueError("get_contexts_dp expects depth_gt of shape [B, 1, H, W]")
+    if mask_valid is None:  # the reference indexes with ~mask_valid (:590): None is a TypeError upstream
+        raise TypeError("get_contexts_dp: mask_valid must be a bool tensor")
+    B, L = g.shape[0], g.shape[2] * g.shape[3]
+    m = _mask_u8(mask_valid, g)
+    K = 2 ** level - 1
+    out = torch.empty((K,) + tuple(g.shape), dtype=torch.uint8, device=g.device)
+    ws = _workspace(g.device, B, 2 ** level + 2)
+    _lib.check(_lib.load().dad_contexts_dp(level, _lib.ptr(g), _lib.ptr(m), B, L, _lib.ptr(out), _lib.ptr(ws),
+                                           ws.numel(), _lib.stream_ptr()), "get_contexts_dp")
+    return out.view(torch.bool)
 
 
 def get_contexts_ds(level, mask_valid):
-    raise NotImplementedError("HDN-DS contexts (tools/train_distillation.py:646-673) are outside the hot path; "
-                              "pass an explicit [K,B,1,H,W] bool tensor to compute_hdn_loss")
+    """``:646-673`` -> bool ``[1 + 4 + ... + 4**(level-1), B, 1, H, W]``: valid mask AND an n x n spatial
+    grid per level (template side = ``mask_valid.shape[-1]``; square maps, as upstream)."""
+    if not isinstance(mask_valid, torch.Tensor) or not mask_valid.is_cuda:
+        raise RuntimeError("mask_valid must be a CUDA tensor: the B200 loss path has no CPU fallback")
+    if mask_valid.dim() != 4 or mask_valid.shape[1] != 1:
+        raise ValueError("get_contexts_ds expects mask_valid of shape [B, 1, H, W]")
+    B, _, H, W = mask_valid.shape
+    if H != W:
+        raise RuntimeError(f"get_contexts_ds: template masks are {W}x{W} but the map is {H}x{W} "
+                           "(the reference's broadcast fails the same way)")
+    m = _mask_u8(mask_valid, mask_valid)
+    K = sum(4 ** i for i in range(level))
+    out = torch.empty((K, B, 1, H, W), dtype=torch.uint8, device=mask_valid.device)
+    _lib.check(_lib.load().dad_contexts_ds(level, _lib.ptr(m), B, H, W, _lib.ptr(out), _lib.stream_ptr()),
+               "get_contexts_ds")
+    return out.view(torch.bool)
 
 
 # ------------------------------------------------------------------------------------------ Sobel

@@ -90,6 +90,15 @@ int dad_ssi_loss(const float* pred, const float* gt, const uint8_t* mask, int ro
 /* get_contexts_dr(level, depth_gt, mask_valid) -> bool [2^level - 1, B, L]               :544-576 */
 int dad_contexts_dr(int level, const float* gt, const uint8_t* mask, int B, int64_t L, uint8_t* ctx_out,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* get_contexts_dp(level, depth_gt, mask_valid) -> bool [2^level - 1, B, L]: bins between the
+ * torch.nanquantile (linear interpolation) values of the valid pixels                     :578-644
+ * workspace: dad_loss_workspace_bytes(B, 2^level + 2) */
+int dad_contexts_dp(int level, const float* gt, const uint8_t* mask, int B, int64_t L, uint8_t* ctx_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* get_contexts_ds(level, mask_valid) -> bool [1 + 4 + .. + 4^(level-1), B, H, W]: mask AND the
+ * n x n grid templates of init_temp_masks_ds (square maps, as upstream); level <= 3     :646-673 */
+int dad_contexts_ds(int level, const uint8_t* mask /*NULL = all valid*/, int B, int H, int W, uint8_t* ctx_out,
+                    void* stream);
 /* compute_hdn_loss(SSILoss(), pred, gt, get_contexts_dr(level, gt, mask)) fused: contexts are never
  * materialised.                                                                          :544-576, :686-707 */
 int dad_hdn_loss_dr(int level, const float* pred, const float* gt, const uint8_t* mask, int B, int64_t L,

@@ -47,9 +47,13 @@ def test_losses_match_golden_reference(case, golden_losses):
         got[f"ctx_dr_count_{tag}"] = sub(ctx.sum(0).float().cpu())
         got[f"hdn_dr_{tag}"] = d.compute_hdn_loss(ssi, P, G, ctx)                 # fused path
         got[f"hdn_dr_{tag}#generic"] = d.compute_hdn_loss(ssi, P, G, ctx.clone())  # explicit-context path
-        got[f"hdn_dp_{tag}"] = d.compute_hdn_loss(ssi, P, G, oracle.get_contexts_dp(3, gt, mk).cuda())
+        cdp = d.get_contexts_dp(3, G, M)
+        assert torch.equal(cdp.cpu(), oracle.get_contexts_dp(3, gt, mk)), "get_contexts_dp differs from the oracle"
+        got[f"hdn_dp_{tag}"] = d.compute_hdn_loss(ssi, P, G, cdp)
         if H == W:
-            got[f"hdn_ds_{tag}"] = d.compute_hdn_loss(ssi, P, G, oracle.get_contexts_ds(3, mk).cuda())
+            cds = d.get_contexts_ds(3, M)
+            assert torch.equal(cds.cpu(), oracle.get_contexts_ds(3, mk)), "get_contexts_ds differs from the oracle"
+            got[f"hdn_ds_{tag}"] = d.compute_hdn_loss(ssi, P, G, cds)
     got["ctx_dr_none"] = sub(d.get_contexts_dr(3, G, None).sum(0).float().cpu())
     got["grad"] = d.gradient_preservation_loss(P)
     got["feat"] = d.feature_distillation_loss(fs.cuda(), ft.cuda())
@@ -155,11 +159,38 @@ def test_median_properties_and_edge_cases():
 
 def test_unsupported_options_raise():
     d = dad()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):
         d.get_contexts_dp(3, torch.zeros(1, 1, 4, 4, device="cuda"), None)
+    with pytest.raises(RuntimeError):  # non-square map: the reference's template broadcast fails too
+        d.get_contexts_ds(3, torch.ones(1, 1, 4, 6, dtype=torch.bool, device="cuda"))
     with pytest.raises(NotImplementedError):
         d.feature_distillation_loss(torch.zeros(1, 4, 8, device="cuda"), torch.zeros(1, 5, 8, device="cuda"))
     with pytest.raises(ValueError):
         d.distillation_loss(torch.zeros(1, 1, 4, 4, device="cuda"), torch.zeros(1, 1, 4, 4, device="cuda"), "bogus")
     with pytest.raises(RuntimeError):
         d.gradient_preservation_loss(torch.zeros(1, 1, 4, 4))
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4])
+@pytest.mark.parametrize("B,H,W", [(3, 37, 53), (2, 64, 64)])
+def test_contexts_dp_ds_bit_exact(level, B, H, W):
+    """HDN-DP / HDN-DS context builders (tools/train_distillation.py:578-673): bit-exact against the oracle,
+    including ties at quantile boundaries, images with 0 / 1 / 2 valid pixels and 1-ulp-adjacent values."""
+    d = dad()
+    g = torch.Generator().manual_seed(100 * level + B)
+    gt = torch.rand(B, 1, H, W, generator=g)
+    gt[0, 0, :4] = gt[0, 0, 4:8]                       # ties
+    gt[0, 0, 9, :16] = torch.nextafter(gt[0, 0, 8, :16], torch.tensor(2.0))  # adjacent floats
+    mask = torch.rand(B, 1, H, W, generator=g) > 0.3
+    if B > 2:
+        mask[2] = False
+        mask[2, 0, 3, 5] = True                         # single valid pixel
+    mask[1, 0, ::2] = False
+    for mk in (mask, torch.ones_like(mask), torch.zeros_like(mask)):
+        got = d.get_contexts_dp(level, gt.cuda(), mk.cuda())
+        exp = oracle.get_contexts_dp(level, gt, mk)
+        assert got.shape == exp.shape and got.dtype == torch.bool
+        assert torch.equal(got.cpu(), exp), (level, int((got.cpu() != exp).sum()))
+        if H == W and level <= 3:
+            gs = d.get_contexts_ds(level, mk.cuda())
+            assert torch.equal(gs.cpu(), oracle.get_contexts_ds(level, mk))

@@ -58,7 +58,7 @@ def test_options_outside_the_hot_path_raise():
         d.DepthAnything(encoder="vitb")
     with pytest.raises(NotImplementedError):
         d.DepthAnything(use_registers=True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):  # CPU tensor: no fallback
         d.get_contexts_ds(3, torch.ones(1, 1, 4, 4, dtype=torch.bool))
 
 
