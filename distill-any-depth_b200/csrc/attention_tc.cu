@@ -312,8 +312,10 @@ int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream
     static int poly = -1;
     if (poly < 0) {
         const char* e = getenv("DAD_ATT_POLY");  // A/B switch: exponentials per 8 moved from the MUFU to the FMA pipe
-        poly = e ? atoi(e) : 2;
-        if (poly != 0 && poly != 2 && poly != 3 && poly != 4) poly = 2;
+        // measured on B200 (ViT-L 518^2 B=32, no-rescale regime): POLY 0 / 2 / 3 = 0.358 / 0.371 / 0.392 ms per launch -
+        // the softmax warps are issue-bound as much as MUFU-bound, so the extra FMA-pipe instructions do not pay: default 0
+        poly = e ? atoi(e) : 0;
+        if (poly != 0 && poly != 2 && poly != 3 && poly != 4) poly = 0;
         DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
@@ -328,10 +330,10 @@ int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream
     }
     const dim3 grid(cdiv(N, BQ), heads, B);
     switch (poly) {
-        case 0: attention_tc_kernel<0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
         case 3: attention_tc_kernel<3><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
         case 4: attention_tc_kernel<4><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
-        default: attention_tc_kernel<2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
+        case 2: attention_tc_kernel<2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
+        default: attention_tc_kernel<0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
     }
     DAD_CHECK_LAUNCH();
     return DAD_OK;

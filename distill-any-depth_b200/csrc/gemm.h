@@ -61,6 +61,9 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream);
 // 2-CTA (cta_group::2) kernel for wide linear GEMMs with the encoder epilogues; gemm_tc() dispatches to it.
 bool gemm_tc2_eligible(const GemmProblem& p);
 int gemm_tc2(const GemmProblem& p, cudaStream_t stream);
+// 2-CTA halo-mode 3x3 convolution for wide N (conv_tc2.cu); gemm_tc() dispatches to it.
+bool conv_tc2_eligible(const GemmProblem& p);
+int conv_tc2(const GemmProblem& p, cudaStream_t stream);
 int gemm_simt(const GemmProblem& p, cudaStream_t stream);
 
 }  // namespace dad

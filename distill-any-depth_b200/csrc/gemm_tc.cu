@@ -296,6 +296,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
                 for (int c = c_lo; c < c_hi; ++c) {
                     const int col0 = n0 + c * CW;
+                    // ConvTranspose scatter: column = (ky * k + kx) * Co + co, a 64-column chunk lies in one (ky, kx)
+                    const int skk = g.epi.scat_k ? col0 / g.epi.scat_Co : 0;
+                    const int bcol0 = col0 - skk * g.epi.scat_Co;
                     uint32_t v[CW];
                     {
                         uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
@@ -315,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int i = 0; i < CW; i += 4) {
                         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
                         if (col0 + i < g.N) {
-                            b4 = *reinterpret_cast<const float4*>(g.epi.bias + col0 + i);   // warp-uniform address
+                            b4 = *reinterpret_cast<const float4*>(g.epi.bias + bcol0 + i);  // warp-uniform address
                             if constexpr (F32) g4 = *reinterpret_cast<const float4*>(g.epi.gamma + col0 + i);
                         }
                         float f0 = __uint_as_float(v[i]) + b4.x, f1 = __uint_as_float(v[i + 1]) + b4.y;
@@ -341,7 +344,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ptx::named_bar_sync(1 + half, 128);
                     if (issuer) {
                         if (g.conv) {
-                            ptx::tma_store_4d(&tmC, tile_stg, col0, cx0, cy0, cb);
+                            if (g.epi.scat_k) {  // out[b, k*y + ky, k*x + kx, co] as a 5-D box {64 co, TW x, 1 ky, TH y, 1 b}
+                                const int ky = skk / g.epi.scat_k, kx = skk - ky * g.epi.scat_k;
+                                ptx::tma_store_5d(&tmC, tile_stg, kx * g.epi.scat_Co + bcol0, cx0, ky, cy0, cb);
+                            } else {
+                                ptx::tma_store_4d(&tmC, tile_stg, col0, cx0, cy0, cb);
+                            }
                         } else if constexpr (F32) {
                             ptx::tma_reduce_add_2d(&tmC, tile_stg, col0, mt * BM);
                         } else {
@@ -520,6 +528,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     {
         static const bool no_2cta = getenv("DAD_NO_2CTA") != nullptr;  // A/B switch while the 2-CTA kernel is validated
         if (!no_2cta && gemm_tc2_eligible(p)) return gemm_tc2(p, stream);
+        if (!no_2cta && conv_tc2_eligible(p)) return conv_tc2(p, stream);
     }
     DAD_REQUIRE(p.N % 8 == 0, "gemm_tc: N=%d must be a multiple of 8", p.N);
     DAD_REQUIRE(p.Kp % 8 == 0, "gemm_tc: Kp=%d must be a multiple of 8", p.Kp);
@@ -594,6 +603,15 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         DAD_TRY(make_tmap_bf16(&tmB, p.Wt, 2, dims, strides, box));
     }
     int kind = epilogue_kind(p.epi);
+    // ConvTranspose (k = s) as a 1x1 "conv" whose bf16 output tile is scattered by ONE 5-D TMA store per 64-channel
+    // chunk instead of 8-byte scattered stores: needs whole 64-channel chunks per (ky, kx) and no padded channels
+    const Epilogue& e = p.epi;
+    const bool scat_tma = e.scat_k && p.conv && p.taps == 1 && e.scat_CoP == e.scat_Co && e.scat_Co % 64 == 0 &&
+                          e.scat_H == p.H && e.scat_W == p.W && e.bias && e.out && e.out_bf16 && !e.gamma && !e.res1 &&
+                          !e.res2 && !e.out_relu && !e.rowtab && !e.head_out && e.act == ACT_NONE && e.ldc == e.scat_Co &&
+                          bn >= 128;
+    if (scat_tma) kind = EK_BIAS_BF16;
+    DAD_REQUIRE(!(e.scat_k && p.conv && !scat_tma), "gemm_tc: conv-mode ConvTranspose scatter needs Co %% 64 == 0, bf16 out");
     if (bn < 128) kind = EK_GENERIC;  // the specialised (TMA-store) epilogues exist for the wide tiles only
     DAD_REQUIRE(!(kind == EK_GENERIC && p.epi.act == ACT_GELU), "gemm_tc: GELU is only fused as bias+GELU->bf16");
     CUtensorMap tmC = tmA;  // placeholder for the generic epilogue (never dereferenced)
@@ -601,7 +619,14 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         const bool f32 = kind == EK_RES_F32;
         const int es = f32 ? 4 : 2, cw = f32 ? 32 : 64;
         DAD_REQUIRE((p.epi.ldc * es) % 16 == 0, "gemm_tc: output row pitch must be a multiple of 16 bytes");
-        if (p.conv) {
+        if (scat_tma) {
+            const int tw = 1 << a.tw_log2, k = e.scat_k, Co = e.scat_Co;
+            const cuuint64_t dims[5] = {(cuuint64_t)k * Co, (cuuint64_t)p.W, (cuuint64_t)k, (cuuint64_t)p.H, (cuuint64_t)p.B};
+            const cuuint64_t sx = (cuuint64_t)k * Co * 2, sky = sx * p.W, sy = sky * k, sb = sy * p.H;
+            const cuuint64_t strides[4] = {sx, sky, sy, sb};
+            const cuuint32_t box[5] = {64u, (cuuint32_t)tw, 1u, (cuuint32_t)a.th, 1u};
+            DAD_TRY(make_tmap(&tmC, 0, p.epi.out, 5, dims, strides, box));
+        } else if (p.conv) {
             const int tw = 1 << a.tw_log2;
             const cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
             const cuuint64_t strides[3] = {(cuuint64_t)p.epi.ldc * es, (cuuint64_t)p.epi.ldc * es * p.W,

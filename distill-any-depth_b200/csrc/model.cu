@@ -415,7 +415,10 @@ public:
                 Epilogue es_; es_.bias = P(h + "resize_layers." + std::to_string(j) + ".bias"); es_.out = rj; es_.out_bf16 = bf;
                 es_.ldc = oc[j]; es_.scat_k = k; es_.scat_CoP = j == 0 ? CoP0 : CoP1; es_.scat_Co = oc[j];
                 es_.scat_H = ph; es_.scat_W = pw;
-                DAD_TRY(linear(mode, pj, Mp, oc[j], j == 0 ? resize0 : resize1, es_, dry, st));
+                if (mode == 0 && oc[j] % 64 == 0)  // 1x1 "conv" + 5-D TMA scatter store (gemm_tc.cu)
+                    DAD_TRY(conv(mode, pj, B, ph, pw, oc[j], j == 0 ? resize0 : resize1, 1, es_, dry, st));
+                else
+                    DAD_TRY(linear(mode, pj, Mp, oc[j], j == 0 ? resize0 : resize1, es_, dry, st));
             } else if (j == 3) {
                 const int Cp = cdiv(oc[3], 64) * 64;
                 const long long rows = static_cast<long long>(B) * hs[3] * wsz[3];

@@ -100,7 +100,10 @@ def pack_conv_weight(w, dtype):
 
 
 CONV_SHAPES = [(2, 19, 37, 64, 64, 9), (1, 37, 37, 256, 256, 9), (2, 24, 40, 96, 48, 9), (1, 74, 74, 128, 32, 9),
-               (3, 10, 10, 192, 64, 1), (1, 148, 148, 64, 128, 9), (2, 8, 16, 48, 64, 9)]
+               (3, 10, 10, 192, 64, 1), (1, 148, 148, 64, 128, 9), (2, 8, 16, 48, 64, 9),
+               # 2-CTA halo kernel (conv_tc2.cu): odd tile counts, channel tails, several chunks, N = 128 / 256 / 512
+               (3, 19, 19, 256, 256, 9), (1, 8, 8, 72, 128, 9), (2, 33, 50, 136, 256, 9), (1, 74, 74, 512, 256, 9),
+               (5, 16, 8, 64, 512, 9)]
 
 
 @pytest.mark.parametrize("B,H,W,C,Co,taps", CONV_SHAPES)
