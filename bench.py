@@ -325,6 +325,14 @@ def run_b200(a):
     value = imgs / ms_dev * 1e3
     e2e_value = imgs / max(ms_e2e, wall_e2e if world == 1 else ms_e2e) * 1e3
     gt_ = prof.get("gemm_tc")
+    traffic = None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture (tools/summarize_ncu.py), not measured live
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            tr = json.load(f)
+        if a.workload == "c3" and a.batch == 32:
+            traffic = tr["classes"]["gemm_tc"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = None
     if gt_:
         # dominant kernel: gemm_tc (tcgen05 GEMM / implicit-GEMM conv).  achieved = algorithmic FLOPs of all its
@@ -332,7 +340,8 @@ def run_b200(a):
         # inside a long step), from MEASURED_PEAKS.json.
         ach = gt_["work_per_step"] / (gt_["ms_per_step"] * 1e-3) / 1e12
         roofline = dict(bound="tensor", achieved=ach, peak=pk["tf_sustained"], unit="TFLOP/s", frac=ach / pk["tf_sustained"],
-                        traffic=None, kernel="gemm_tc_kernel (all launches of a step)", peak_source=pk["src"] + " sustained bf16",
+                        traffic=traffic, flops_per_launch=gt_["work_per_step"] / gt_["launches_per_step"],
+                        kernel="tcgen05 GEMM / implicit-GEMM conv kernels (gemm_tc, gemm_tc2, conv_tc2: all launches of a step)", peak_source=pk["src"] + " sustained bf16",
                         launches_per_step=gt_["launches_per_step"], avg_launch_ms=gt_["avg_launch_ms"],
                         share_of_step=gt_["ms_per_step"] / (ms_dev / a.steps))
     line = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),

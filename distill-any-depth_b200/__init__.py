@@ -9,4 +9,5 @@ from .losses import (masked_shift_and_scale, masked_l1_loss, SSILoss, get_contex
                      feature_distillation_loss, distillation_loss, global_normalize, hybrid_normalize,
                      local_normalize, normalize_depth)
 from . import dist  # noqa: F401
+from . import checkpoint  # noqa: F401
 from .step import distillation_step_losses  # noqa: F401

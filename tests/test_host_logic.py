@@ -159,3 +159,42 @@ def test_two_rank_losses_equal_single_process_full_batch():
            "feat": oracle.feature_distillation_loss(fs, ft)}
     for k, v in ref.items():
         assert abs(got[k] - float(v)) <= 1e-5 * max(abs(float(v)), 1e-6), (k, got[k], float(v))
+
+
+def test_checkpoint_io_round_trips_both_key_layouts(tmp_path):
+    """8f N3: safetensors / torch checkpoints in either reference key layout load into either native class
+    (tools/train_distillation.py:743-793, ViT_DINO.py:1372-1388, tools/convert_checkpoint.py)."""
+    import distill_any_depth_b200 as d
+    from distill_any_depth_b200 import checkpoint as ck
+    kw = synthetic.MODEL_PRESETS["vitl"]
+    sd = synthetic.make_state_dict(seed=4, **kw)
+    from safetensors.torch import save_file, load_file
+    flat = str(tmp_path / "dav2_vitl.safetensors")           # DAv2 release layout: pretrained.blocks.N.*
+    save_file({k: v.contiguous() for k, v in sd.items()}, flat)
+    t = d.DepthAnything(**kw)
+    res = ck.load_checkpoint(t, flat, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(t.backbone.blocks[0][5].attn.qkv.weight, sd["pretrained.blocks.5.attn.qkv.weight"])
+    assert torch.equal(t.backbone.blocks[0][0].norm1.bias, sd["pretrained.blocks.0.norm1.bias"])  # block 0 is not "chunk 0"
+    # the reference's half-converted layout (backbone.* but flat blocks, what convert_checkpoint.py writes) also loads
+    half = {("backbone" + k[len("pretrained"):] if k.startswith("pretrained.") else k): v for k, v in sd.items()}
+    half_path = str(tmp_path / "half.pth")
+    torch.save({"state_dict": half}, half_path)
+    t2 = d.DepthAnything(**kw)
+    ck.load_checkpoint(t2, half_path, strict=True)
+    assert all(torch.equal(a, b) for a, b in zip(t.state_dict().values(), t2.state_dict().values()))
+    # teacher save -> student load (blocks.0.N -> blocks.N), bit-identical tensors
+    out = str(tmp_path / "teacher.safetensors")
+    ck.save_checkpoint(t, out)
+    assert "backbone.blocks.0.23.mlp.fc2.weight" in load_file(out)
+    s = d.DepthAnythingV2(**kw)
+    ck.load_checkpoint(s, out, strict=True)
+    for k, v in sd.items():
+        assert torch.equal(s.state_dict()[k], v), k
+    keys = ck.convert_checkpoint(flat, str(tmp_path / "conv.safetensors"), layout="teacher")
+    assert "backbone.blocks.0.0.ls1.gamma" in keys and not any(k.startswith("pretrained.") for k in keys)
+    with pytest.raises(RuntimeError):  # a foreign key is an error, not a silent strict=False fallback
+        bad = dict(sd)
+        bad["pretrained.blocks.0.attn.extra"] = torch.zeros(1)
+        save_file({k: v.contiguous() for k, v in bad.items()}, str(tmp_path / "bad.safetensors"))
+        ck.load_checkpoint(d.DepthAnythingV2(**kw), str(tmp_path / "bad.safetensors"), strict=True)

@@ -125,7 +125,52 @@ def full(tag):
               f"tensor {m.get('tensor_pct', 0):5.1f}% issue {m.get('issue_pct', 0):5.1f}% dram {m.get('dram_pct', 0):5.1f}%  {n}")
 
 
+CLASSES = [("gemm_tc", ("gemm_tc", "conv_tc2")), ("attention", ("attention",)), ("layernorm", ("layernorm",)),
+           ("elementwise", ("bilinear", "im2col", "patch_im2col", "head1x1")),
+           ("loss", ("sel_", "mad_", "final_", "minmax", "init_minmax", "scale_", "ratio_", "sobel", "featcos", "l1_", "hyb_",
+                     "set_den", "contexts_"))]
+
+
+def klass(name):
+    for c, prefixes in CLASSES:
+        if any(name.startswith(p) for p in prefixes):
+            return c
+    return None
+
+
+def traffic(tag):
+    """DRAM bytes per launch of each bench.py kernel class over one step = sum over the class's kernels of
+    (launches in a step, from the launch list) x (average dram bytes per launch, from the --set full capture)."""
+    lp = os.path.join(ROOT, "profiles", f"ncu_launches_{tag}.json")
+    fp = os.path.join(ROOT, "profiles", f"ncu_full_{tag}.json")
+    if not (os.path.exists(lp) and os.path.exists(fp)):
+        return
+    L, F = json.load(open(lp))["kernels"], json.load(open(fp))["kernels"]
+    out = {}
+    for c, _ in CLASSES:
+        n = b = 0
+        missing = []
+        for k, a in L.items():
+            if klass(k) != c:
+                continue
+            if k not in F:
+                missing.append(k)
+                continue
+            n += a["launches"]
+            b += a["launches"] * F[k]["dram_bytes_per_launch"]
+        if n:
+            out[c] = dict(launches_per_step=n, dram_bytes_per_step=b, dram_bytes_per_launch=b / n, not_captured=missing)
+    res = dict(tag=tag, source=f"profiles/ncu_full_{tag}.json x profiles/ncu_launches_{tag}.json",
+               note="dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the launches of one step",
+               classes=out)
+    with open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    for c, v in out.items():
+        print(f"  traffic {c:12s} {v['dram_bytes_per_launch'] / 1e6:9.1f} MB/launch x {v['launches_per_step']}")
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     launches(tag)
     full(tag)
+    traffic(tag)
