@@ -10,4 +10,6 @@ from .losses import (masked_shift_and_scale, masked_l1_loss, SSILoss, get_contex
                      local_normalize, normalize_depth)
 from . import dist  # noqa: F401
 from . import checkpoint  # noqa: F401
+from . import preprocess  # noqa: F401
+from .graph import capture  # noqa: F401
 from .step import distillation_step_losses  # noqa: F401

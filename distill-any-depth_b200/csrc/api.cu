@@ -91,6 +91,19 @@ int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float*
     return mode == 0 ? dad::gemm_tc(p, ST(stream)) : dad::gemm_simt(p, ST(stream));
 }
 
+int dad_preprocess_image(const uint8_t* image, int h, int w, int64_t pitch_bytes, int swap_rb, int nh, int nw,
+                         const double* mean3, const double* std3, float* out_chw, void* stream) {
+    return dad::preprocess_image(image, h, w, pitch_bytes, swap_rb, nh, nw, mean3, std3, out_chw, ST(stream));
+}
+
+int dad_resize_depth(const float* in, int B, int H, int W, int h, int w, float* out, void* stream) {
+    return dad::resize_depth(in, B, H, W, h, w, out, ST(stream));
+}
+
+int dad_minmax_normalize(const float* in, int B, int64_t L, float* out, void* ws, size_t wsb, void* stream) {
+    return dad::minmax_normalize(in, B, L, out, ws, wsb, ST(stream));
+}
+
 int dad_attention(const void* qkv, void* out, int B, int N, int heads, int mode, void* stream) {
     return dad::attention(qkv, out, mode == 0, B, N, heads, ST(stream));
 }

@@ -16,6 +16,11 @@ int pack_linear(const float* w, void* out, int is_bf16, int N, int K, int Kp, in
 int pack_conv(const float* w, void* out, int is_bf16, int Co, int Ci, int taps, int Cp, cudaStream_t st);
 int pack_convT(const float* w, void* out, int is_bf16, int Ci, int Co, int k, int CoP, int Kp, cudaStream_t st);
 int copy_scale(const float* in, float* out, long long n, long long scale_n, float scale, cudaStream_t st);
+// imageproc.cu: pre- / post-processing next to the forward
+int preprocess_image(const uint8_t* src, int h, int w, long long pitch, int swap_rb, int nh, int nw, const double* mean,
+                     const double* stdv, float* dst, cudaStream_t st);
+int resize_depth(const float* in, int B, int Hi, int Wi, int Ho, int Wo, float* out, cudaStream_t st);
+int minmax_normalize(const float* in, int B, long long L, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st);  // tcgen05 / TMEM
 int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, cudaStream_t st);
 

@@ -172,6 +172,31 @@ __global__ void __launch_bounds__(THREADS) sel_hist_kernel(const SelArgs a, int 
         const uint32_t bits = inb ? member_bits<MODE>(a, b, i, g, lo, hi, has_valid) : 0u;
         if (__ballot_sync(0xffffffffu, bits != 0u) == 0u) continue;
         const uint32_t kp = f2key(p), kg = f2key(g);
+        if (MODE == MODE_DR) {
+            // Depth-range contexts of one level are disjoint unless the image is degenerate (range 0 at depth 0,
+            // SURVEY A.4 iii): a pixel then has at most ONE context per level, and (context, digit) can share one
+            // warp-aggregated atomic per level and array - 2 * level aggregations per pixel instead of 2 * K.
+            bool fast = true;
+            int lvl_first = 0;
+            for (int nb = 1 << (a.level - 1); nb >= 1; lvl_first += nb, nb >>= 1)
+                fast = fast && __popc(bits & (((1u << nb) - 1u) << lvl_first)) <= 1;
+            if (__all_sync(0xffffffffu, fast)) {
+                lvl_first = 0;
+                for (int nb = 1 << (a.level - 1); nb >= 1; lvl_first += nb, nb >>= 1) {
+                    const uint32_t sel = bits & (((1u << nb) - 1u) << lvl_first);
+                    const int k = sel ? __ffs(sel) - 1 : 0;
+                    {
+                        const bool ok = sel != 0u && (pass == 0 || (kp >> (shift + 8)) == (pref[k] >> (shift + 8)));
+                        agg_inc(h, ok, (static_cast<uint32_t>(k) << 8) | ((kp >> shift) & 255u), lane);
+                    }
+                    {
+                        const bool ok = sel != 0u && (pass == 0 || (kg >> (shift + 8)) == (pref[a.K + k] >> (shift + 8)));
+                        agg_inc(h + a.K * 256, ok, (static_cast<uint32_t>(k) << 8) | ((kg >> shift) & 255u), lane);
+                    }
+                }
+                continue;
+            }
+        }
         for (int k = 0; k < a.K; ++k) {
             const bool in = (bits >> k) & 1u;
             {

@@ -257,27 +257,17 @@ class DepthAnythingV2(_NativeDepthModel):
     @torch.no_grad()
     def infer_image(self, raw_image, input_size=518):
         """dpt.py:227-235 with its evident intent (upstream indexes the tuple and raises):
-        BGR uint8 image -> relative depth ``np.ndarray [h, w]`` at the raw resolution."""
+        BGR uint8 image -> relative depth ``np.ndarray [h, w]`` at the raw resolution.  Pre- and post-processing
+        run on the GPU (preprocess.py): the only host<->device traffic is the uint8 image and the final map."""
+        from . import preprocess
         image, (h, w) = self.image2tensor(raw_image, input_size)
         depth, _ = self.forward(image)
-        depth = F.interpolate(depth, (h, w), mode="bilinear", align_corners=True)[0, 0]
+        depth = preprocess.resize_depth(depth, (h, w))[0, 0]
         return depth.cpu().numpy()
 
     def image2tensor(self, raw_image, input_size=518):
-        """dpt.py:237-262: keep-aspect lower-bound resize to a multiple of 14 (cv2 INTER_CUBIC),
-        ImageNet normalisation, HWC->CHW."""
-        import cv2
-        h, w = raw_image.shape[:2]
-        image = cv2.cvtColor(raw_image, cv2.COLOR_BGR2RGB) / 255.0
-        scale = max(input_size / h, input_size / w)  # 'lower_bound', keep_aspect_ratio (util/transform.py:60-95)
-        nh = max(int(np.round(scale * h / 14) * 14), 14)
-        nw = max(int(np.round(scale * w / 14) * 14), 14)
-        if nh < input_size:
-            nh = int(np.ceil(scale * h / 14) * 14)
-        if nw < input_size:
-            nw = int(np.ceil(scale * w / 14) * 14)
-        image = cv2.resize(image, (nw, nh), interpolation=cv2.INTER_CUBIC)
-        image = (image - np.array([0.485, 0.456, 0.406])) / np.array([0.229, 0.224, 0.225])
-        image = np.ascontiguousarray(np.transpose(image, (2, 0, 1)).astype(np.float32))
+        """dpt.py:237-262: keep-aspect lower-bound resize to a multiple of 14 (cv2 INTER_CUBIC on the float64
+        image / 255), ImageNet normalisation, HWC->CHW; computed by one CUDA kernel from the uint8 image."""
+        from . import preprocess
         device = next(self.parameters()).device
-        return torch.from_numpy(image).unsqueeze(0).to(device), (h, w)
+        return preprocess.image_to_tensor(raw_image, input_size, device=device, bgr=True)

@@ -119,6 +119,18 @@ int dad_distill_loss(const float* student, const float* teacher, int strategy, i
                      float* out_scalar, double* partials, float* norm_student, float* norm_teacher, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ pre- / post-processing
+ * DepthAnythingV2.image2tensor (depth_anything_v2/dpt.py:237-262; util/transform.py:109-148): uint8 HWC image
+ * (device pointer, `pitch_bytes` per row; swap_rb = 1 for a BGR source) -> /255 -> cv2.resize(INTER_CUBIC) to
+ * (nh, nw) -> (x - mean) / std -> CHW fp32 [3, nh, nw].  mean3 / std3 are HOST pointers to 3 doubles. */
+int dad_preprocess_image(const uint8_t* image, int h, int w, int64_t pitch_bytes, int swap_rb, int nh, int nw,
+                         const double* mean3, const double* std3, float* out_chw, void* stream);
+/* F.interpolate(depth, (h, w), mode="bilinear", align_corners=True) on [B,1,H,W] fp32 (dpt.py:233). */
+int dad_resize_depth(const float* in, int B, int H, int W, int h, int w, float* out, void* stream);
+/* per image (d - min) / (max - min) (tools/testers/infer.py:135); workspace: 8 bytes per image. */
+int dad_minmax_normalize(const float* in, int B, int64_t L, float* out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* ------------------------------------------------------------------ kernel-level test entry points
  * out[M,N] (fp32) = A[M,K] (bf16 bits / fp32) * W[N,K]^T through the tcgen05 (mode 0) or FFMA (mode 1)
  * engine with an optional bias[N]; used by the parity tests to bisect the GEMM engine alone. */

@@ -1,5 +1,7 @@
 """CPU: the oracle restatement reproduces the LIVE reference's outputs recorded in
 tests/golden/ by oracle/make_golden.py (the oracle's pin)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -86,3 +88,18 @@ def test_lower_median_and_edge_semantics():
     # constant 0 -> all 7 contexts; constant 0.5 -> none (SURVEY.md A.4 iii)
     assert bool((oracle.get_contexts_dr(3, torch.zeros(1, 1, 4, 4), None).sum(0) == 7).all())
     assert bool((oracle.get_contexts_dr(3, torch.full((1, 1, 4, 4), 0.5), None).sum(0) == 0).all())
+
+
+def test_preprocess_oracle_matches_reference_fixture():
+    """oracle/preprocess.py (cv2 / numpy restatement of dpt.py:237-262) against the committed outputs of the live
+    reference class on seeded synthetic images (oracle/make_golden_preprocess.py)."""
+    import numpy as np
+    from oracle import preprocess as P
+    from oracle.make_golden_preprocess import CASES, synthetic_image, sub as psub
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_preprocess.npz")))
+    for name, h, w, size, keep, seed in CASES:
+        t, hw = P.image2tensor(synthetic_image(h, w, seed), size, keep_aspect_ratio=keep)
+        assert tuple(t.shape) == tuple(g[name + "/shape"]) and hw == (h, w)
+        assert np.array_equal(psub(t.numpy()), g[name + "/tensor_sub"]), name
+    assert P.get_size(640, 480, 518, 518) == (686, 518)
+    assert P.get_size(1242, 375, 518, 518) == (1722, 518)
