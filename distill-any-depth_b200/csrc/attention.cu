@@ -5,6 +5,8 @@
 //   fp32 mode : attention_f32_kernel below - verification mode, one query per thread, fp32 FFMA, expf.
 //
 // qkv layout: [B*N, 3*D] rows = tokens, columns = (3, heads, 64) as produced by the qkv GEMM.
+#include <cstdlib>
+
 #include "common.h"
 #include "elementwise.h"
 
@@ -77,8 +79,17 @@ int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, 
     DAD_REQUIRE(qkv && out && B > 0 && N > 0 && heads > 0, "attention: bad arguments");
     const int D = heads * HD;
     ProfScope prof(PROF_ATTN, 4.0 * B * static_cast<double>(N) * N * D, st);
-    if (is_bf16) {  // tcgen05 / TMEM kernel (attention_tc.cu)
-        DAD_TRY(attention_tc(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, st));
+    if (is_bf16) {
+        // tcgen05 / TMEM kernels.  Default: attention_tc.cu (2 CTAs / SM, S / P double-buffered in TMEM) - the faster
+        // one when logits stay within 2^16 of the first key tile's maximum (0.358 vs 0.371 ms per ViT-L 518^2 B=32
+        // launch, 1.205 vs 1.322 ms at 1036^2).  DAD_ATT_VARIANT=3 selects attention_tc3.cu (4 serial CTAs / SM, exact
+        // per-tile maximum): 1.7x faster than the default on heavy-tailed logits that force rescales (0.429 vs 0.728 ms).
+        const char* ev = getenv("DAD_ATT_VARIANT");  // read per call: tests switch it at run time
+        const int variant = ev ? atoi(ev) : 2;
+        if (variant == 3)
+            DAD_TRY(attention_tc3(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, st));
+        else
+            DAD_TRY(attention_tc(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, st));
         return DAD_OK;
     }
     {

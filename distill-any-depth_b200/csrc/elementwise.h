@@ -22,6 +22,7 @@ int preprocess_image(const uint8_t* src, int h, int w, long long pitch, int swap
 int resize_depth(const float* in, int B, int Hi, int Wi, int Ho, int Wo, float* out, cudaStream_t st);
 int minmax_normalize(const float* in, int B, long long L, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st);  // tcgen05 / TMEM
+int attention_tc3(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st); // 4 CTAs / SM variant
 int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, cudaStream_t st);
 
 }  // namespace dad

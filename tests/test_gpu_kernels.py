@@ -131,9 +131,16 @@ def test_conv_nhwc_matches_conv2d(B, H, W, C, Co, taps, mode):
     assert (out - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.fixture(params=[2, 3], ids=["pipelined2cta", "serial4cta"])
+def att_variant(request, monkeypatch):
+    """Both tcgen05 attention kernels (attention_tc.cu / attention_tc3.cu) go through the same tests."""
+    monkeypatch.setenv("DAD_ATT_VARIANT", str(request.param))
+    return request.param
+
+
 @pytest.mark.parametrize("B,N,heads", [(1, 64, 1), (2, 785, 6), (1, 1370, 16), (1, 26, 2), (1, 200, 3)])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_attention_matches_softmax_reference(B, N, heads, mode):
+def test_attention_matches_softmax_reference(B, N, heads, mode, att_variant):
     L = _lib()
     lib = L.load()
     D = heads * 64
@@ -152,7 +159,7 @@ def test_attention_matches_softmax_reference(B, N, heads, mode):
     assert (out.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
 
 
-def test_attention_lazy_rescale_path():
+def test_attention_lazy_rescale_path(att_variant):
     """Late key tiles with much larger logits force the reference-maximum rescale of O / l (TMEM round trip)."""
     L = _lib()
     lib = L.load()

@@ -38,9 +38,28 @@ __global__ void k(float* out, int iters, float seed) {
                 a[i] = __uint_as_float(u);
             } else if (MODE == 3) {
                 a[i] = ex2_poly(a[i]) - 1.0f;
-            } else {
+            } else if (MODE == 4) {
                 if ((i & 3) == 3) a[i] = ex2_poly(a[i]) - 1.0f;
                 else asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+            } else if (MODE == 5) {  // F2FP only: pack pairs to bf16x2 (round to nearest)
+                if ((i & 1) == 0) {
+                    uint32_t u;
+                    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(a[i + 1]), "f"(a[i]));
+                    a[i] = __uint_as_float(u & 0x3f803f80u) + 1.0f;
+                }
+            } else if (MODE == 6) {  // the softmax mix: one MUFU per element + one F2FP per pair
+                asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+                if ((i & 1) == 1) {
+                    uint32_t u;
+                    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(a[i]), "f"(a[i - 1]));
+                    a[i - 1] = __uint_as_float(u & 0x3f803f80u);
+                }
+            } else {                 // MUFU + truncating pack on the ALU (PRMT) + masked copy for the row sum (LOP3)
+                asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+                if ((i & 1) == 1) {
+                    const uint32_t u = __byte_perm(__float_as_uint(a[i - 1]), __float_as_uint(a[i]), 0x7632);
+                    a[i - 1] = __uint_as_float(u & 0x3f803f80u);
+                }
             }
         }
     }
@@ -74,5 +93,8 @@ int main() {
     run<2>("bf16x2", out, 2);
     run<3>("poly", out, 1);
     run<4>("mix3:1", out, 1);
+    run<5>("f2fp", out, 1);       // per-element rate (one cvt packs two)
+    run<6>("ex2+f2fp", out, 1);
+    run<7>("ex2+prmt", out, 1);
     return 0;
 }
