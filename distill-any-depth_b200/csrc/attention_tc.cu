@@ -92,6 +92,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();  // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
     if (warp == 4) {
         if (lane == 0) {
@@ -152,6 +153,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             __syncwarp();
             if (j + 2 < T) issue_qk(j + 2);
         }
+        pdl_launch_dependents();  // last MMA issued: the next kernel's prologue may overlap this CTA's drain
     } else {
         // -------------------------------------------------------------------- softmax (warps 0-3)
         const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
@@ -330,10 +332,10 @@ int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream
     }
     const dim3 grid(cdiv(N, BQ), heads, B);
     switch (poly) {
-        case 3: attention_tc_kernel<3><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
-        case 4: attention_tc_kernel<4><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
-        case 2: attention_tc_kernel<2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
-        default: attention_tc_kernel<0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm[0], tm[1], tm[2], out, N, D); break;
+        case 3: DAD_CHECK_CUDA(launch_pdl(attention_tc_kernel<3>, grid, dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N, D)); break;
+        case 4: DAD_CHECK_CUDA(launch_pdl(attention_tc_kernel<4>, grid, dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N, D)); break;
+        case 2: DAD_CHECK_CUDA(launch_pdl(attention_tc_kernel<2>, grid, dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N, D)); break;
+        default: DAD_CHECK_CUDA(launch_pdl(attention_tc_kernel<0>, grid, dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N, D)); break;
     }
     DAD_CHECK_LAUNCH();
     return DAD_OK;

@@ -83,6 +83,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();  // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
     if (warp == 4) {
         if (lane == 0) {
@@ -139,6 +140,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             __syncwarp();
         }
+        pdl_launch_dependents();  // last MMA issued: the next kernel's prologue may overlap this CTA's drain
     } else {
         // -------------------------------------------------------------------- softmax (warps 0-3), thread = query row
         const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
@@ -286,8 +288,7 @@ int attention_tc3(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStrea
     const dim3 grid(cdiv(N, BQ), heads, B);
     static const int pad = getenv("DAD_ATT_SMEM_PAD_KB") ? atoi(getenv("DAD_ATT_SMEM_PAD_KB")) * 1024 : 0;  // occupancy experiments
     if (pad) DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM + pad));
-    attention_tc3_kernel<<<grid, ATT_THREADS, ATT_SMEM + pad, st>>>(tm[0], tm[1], tm[2], out, N, D);
-    DAD_CHECK_LAUNCH();
+    DAD_CHECK_CUDA(launch_pdl(attention_tc3_kernel, grid, dim3(ATT_THREADS), ATT_SMEM + pad, st, tm[0], tm[1], tm[2], out, N, D));
     return DAD_OK;
 }
 

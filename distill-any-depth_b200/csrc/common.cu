@@ -19,6 +19,11 @@ int set_error(int code, const char* fmt, ...) {
 
 const char* last_error() { return g_err; }
 
+bool pdl_enabled() {
+    static const bool on = getenv("DAD_NO_PDL") == nullptr;
+    return on;
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {

@@ -63,6 +63,31 @@ struct ProfScope {
     ~ProfScope();
 };
 
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl() may begin (barrier init, TMEM
+// allocation, tensor-map prefetch) while its predecessor in the stream drains; it must execute pdl_wait() before it
+// touches global memory.  Kernels call pdl_launch_dependents() early so that the NEXT launch can do the same.  Without
+// the launch attribute both instructions are no-ops, so kernels stay valid under plain <<<>>> launches.
+bool pdl_enabled();  // false when DAD_NO_PDL is set (A/B switch)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long long cdivl(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -163,6 +163,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / complete_tx
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
     const int num_pair_tiles = ((g.num_m_tiles + 1) >> 1) * g.num_n_tiles;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -237,6 +238,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (as == 0) aphase ^= 1;
             }
         }
+        pdl_launch_dependents();  // last MMA issued (leader) / nothing to issue (peer): let the next kernel's prologue start
         __syncwarp();
     } else {
         // ---------------------------------------------------- epilogue (warps 2..9, both CTAs)
@@ -399,8 +401,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv2Args& a, d
     const int pairs = num_sms() / 2;
     const int grid = 2 * (pair_tiles < pairs ? pair_tiles : pairs);
     ProfScope prof(PROF_GEMM_TC, flops, stream);
-    conv_tc2_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
-    DAD_CHECK_LAUNCH();
+    DAD_CHECK_CUDA(launch_pdl(conv_tc2_kernel<BN>, dim3(grid), dim3(NUM_THREADS), Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, a));
     return DAD_OK;
 }
 

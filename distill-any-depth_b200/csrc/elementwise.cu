@@ -56,6 +56,7 @@ template <typename T, int VPT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* in, const float* w, const float* bvec, T* out,
                                                         float* out_f32, long long rows, int D, int out_period,
                                                         int in_period, int in_offset, float eps) {
+    pdl_wait();
     const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* in, const f
     }
     for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     const float rstd = rsqrtf(var / D + eps);
+    pdl_launch_dependents();  // row is in registers: only the stores remain
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
         const int idx = lane + j * 32;
@@ -108,6 +110,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int Hi, int Wi, int Ho,
                                                        int Wo, int C, float sh, float sw) {
     // grid: (x-chunks, output row groups, image); thread -> (output column, VEC-channel group) x BIL_ROWS rows
+    pdl_wait();
     const int cv = C / VEC;
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= Wo * cv) return;
@@ -291,14 +294,17 @@ int layernorm(const float* in, const float* w, const float* b, void* out, int is
     const unsigned grid = static_cast<unsigned>(cdivl(rows, 8));
     ProfScope prof(PROF_LN, static_cast<double>(rows) * D * (4 + (out ? (is_bf16 ? 2 : 4) : 0) + (out_f32 ? 4 : 0)), st);
     const int vpt = cdiv(D, 128);
+    cudaError_t ln_err = cudaSuccess;
 #define LN_LAUNCH(V)                                                                                              \
-    DISPATCH_T(is_bf16, (layernorm_kernel<T, V><<<grid, 256, 0, st>>>(in, w, b, reinterpret_cast<T*>(out), out_f32, \
-                                                                       rows, D, out_period, in_period, in_offset, eps)))
+    DISPATCH_T(is_bf16, (ln_err = launch_pdl(layernorm_kernel<T, V>, dim3(grid), dim3(256), 0, st, in, w, b,           \
+                                             reinterpret_cast<T*>(out), out_f32, rows, D, out_period, in_period, \
+                                             in_offset, eps)))
     if (vpt <= 3) LN_LAUNCH(3);
     else if (vpt <= 6) LN_LAUNCH(6);
     else if (vpt <= 8) LN_LAUNCH(8);
     else LN_LAUNCH(16);
 #undef LN_LAUNCH
+    DAD_CHECK_CUDA(ln_err);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
@@ -312,8 +318,8 @@ int bilinear_nhwc(const void* in, void* out, int is_bf16, int B, int Hi, int Wi,
     DAD_REQUIRE(Ho <= 65535 && B <= 65535, "bilinear: output height / batch too large for the launch grid");
     if (is_bf16) {
         const dim3 grid(cdiv(Wo * (C / 8), 256), cdiv(Ho, BIL_ROWS), B);
-        bilinear_kernel<bf16, 8><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), Hi, Wi, Ho,
-                                                       Wo, C, sh, sw);
+        DAD_CHECK_CUDA(launch_pdl(bilinear_kernel<bf16, 8>, grid, dim3(256), 0, st, reinterpret_cast<const bf16*>(in),
+                                  reinterpret_cast<bf16*>(out), Hi, Wi, Ho, Wo, C, sh, sw));
     } else {
         const dim3 grid(cdiv(Wo * (C / 4), 256), cdiv(Ho, BIL_ROWS), B);
         bilinear_kernel<float, 4><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), Hi, Wi,

@@ -114,6 +114,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / complete_tx
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
     const int num_tiles = g.num_m_tiles * g.num_n_tiles;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -174,6 +175,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (as == 0) aphase ^= 1;
             }
         }
+        pdl_launch_dependents();  // last MMA issued (leader) / nothing to issue (peer): let the next kernel's prologue start
         __syncwarp();
     } else {
         // ---------------------------------------------------- epilogue (warps 2..9, both CTAs): TMA store / reduce-add
@@ -272,8 +274,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
     const int pairs = num_sms() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
     ProfScope prof(PROF_GEMM_TC, flops, stream);
-    gemm_tc2_kernel<KIND><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, a);
-    DAD_CHECK_LAUNCH();
+    DAD_CHECK_CUDA(launch_pdl(gemm_tc2_kernel<KIND>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, tmC, a));
     return DAD_OK;
 }
 
