@@ -9,6 +9,7 @@
 // HDN-DR path computes each pixel's context membership on the fly from the per-image min/max
 // (no [7,B,1,H,W] mask tensor, no 7x replicated maps).
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.h"
 #include "losses.h"
@@ -53,6 +54,15 @@ struct SelArgs {
     float* s;              // [R] scales
     double* acc;           // [0] numerator, [1] (as double) denominator count
     int R;
+    // range-bin selection (run_select_lin): value-linear histogram -> candidates of the median's bin -> exact select
+    uint32_t* imm;         // [B][4] keys: pred min / max, gt min / max over the valid pixels of the image
+    uint32_t* lhist;       // [R][NB]
+    uint32_t* tbin;        // [R] bin that holds the wanted rank (0xFFFFFFFF: empty row)
+    uint32_t* trank;       // [R] rank inside that bin
+    uint32_t* cbin;        // [R] population of that bin
+    uint32_t* ccount;      // [R] append cursor of the candidate list
+    uint32_t* cand;        // [R][CAP] keys of the candidates
+    int NB, CAP;
 };
 
 __device__ __forceinline__ int row_of(const SelArgs& a, int arr, int b, int k) { return (arr * a.B + b) * a.K + k; }
@@ -277,8 +287,244 @@ __global__ void __launch_bounds__(THREADS) sel_scan_kernel(const SelArgs a, int 
     }
 }
 
-// ---------------------------------------------------------------- sum |x - t| over members
+// ================================================================ range-bin selection
+// The 4 x 8-bit radix passes above spend their time in warp-aggregated atomics (every member element takes part in
+// every one of the first passes).  For the medians of the loss path a cheaper exact scheme is used instead:
+//   1. per image: min / max of pred and gt over the valid pixels                                   (imgminmax_kernel)
+//   2. ONE histogram pass over NB value-linear bins of each row's range - bin(x) = int((x - lo) * NB / (hi - lo)) is
+//      monotone in x, so bins are value-ordered; occupancy is spread, plain shared-memory atomics do   (lin_hist_kernel)
+//   3. per row: the bin that holds the median rank, and the rank inside it                           (lin_scan_kernel)
+//   4. ONE pass that appends the keys of that bin's members to a small per-row list (~ n / NB of them) (compact_kernel)
+//   5. per row: exact radix select inside the list, in shared memory.  A list that overflows CAP (a degenerate
+//      distribution: constant images, heavy ties) is not used: the row's CTA streams the image instead - slow, exact
+//                                                                                                     (select_rows_kernel)
+__device__ __forceinline__ int lin_bin(float x, float lo, float scale, int NB) {
+    const int bq = static_cast<int>(__fmul_rn(__fsub_rn(x, lo), scale));
+    return min(max(bq, 0), NB - 1);
+}
+
+__global__ void __launch_bounds__(THREADS) imgminmax_kernel(const SelArgs a) {
+    const int b = blockIdx.y;
+    const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
+    const long long end = min(start + a.chunk, a.L);
+    uint32_t pmn = 0xFFFFFFFFu, pmx = 0u, gmn = 0xFFFFFFFFu, gmx = 0u;
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        if (a.mask && a.mask[b * a.L + i] == 0) continue;
+        const uint32_t kp = f2key(a.pred[b * a.L + i]);
+        pmn = min(pmn, kp); pmx = max(pmx, kp);
+        if (a.narr == 2) {
+            const uint32_t kg = f2key(a.gt[b * a.L + i]);
+            gmn = min(gmn, kg); gmx = max(gmx, kg);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        pmn = min(pmn, __shfl_xor_sync(0xffffffffu, pmn, o)); pmx = max(pmx, __shfl_xor_sync(0xffffffffu, pmx, o));
+        gmn = min(gmn, __shfl_xor_sync(0xffffffffu, gmn, o)); gmx = max(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && pmn <= pmx) {
+        atomicMin(&a.imm[4 * b], pmn); atomicMax(&a.imm[4 * b + 1], pmx);
+        if (a.narr == 2) {
+            atomicMin(&a.imm[4 * b + 2], gmn); atomicMax(&a.imm[4 * b + 3], gmx);
+            atomicMin(&a.minmax[2 * b], gmn); atomicMax(&a.minmax[2 * b + 1], gmx);
+        }
+    }
+}
+
+__global__ void init_imm_kernel(uint32_t* imm, uint32_t* minmax, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        imm[4 * i] = 0xFFFFFFFFu; imm[4 * i + 1] = 0u; imm[4 * i + 2] = 0xFFFFFFFFu; imm[4 * i + 3] = 0u;
+        minmax[2 * i] = 0xFFFFFFFFu; minmax[2 * i + 1] = 0u;
+    }
+}
+
+// binning range of every row of image b -> rlo / rsc (shared); DR gt rows use their context's own [lo, hi)
 template <int MODE>
+__device__ __forceinline__ void setup_ranges(const SelArgs& a, int b, const float* lo, const float* hi, float* rlo, float* rsc) {
+    const int nrow = a.narr * a.K;
+    if (threadIdx.x < nrow) {
+        const int arr = threadIdx.x / a.K, k = threadIdx.x - arr * a.K;
+        float l, h;
+        const uint32_t kmn = a.imm[4 * b + 2 * arr], kmx = a.imm[4 * b + 2 * arr + 1];
+        if (MODE == MODE_DR && arr == 1 && kmn <= kmx) { l = lo[k]; h = hi[k]; }
+        else { l = kmn <= kmx ? key2f(kmn) : 0.f; h = kmn <= kmx ? key2f(kmx) : 0.f; }
+        const float w = __fsub_rn(h, l);
+        rlo[threadIdx.x] = l;
+        const float sc = (w > 0.f && w < 3.0e38f) ? __fdiv_rn(static_cast<float>(a.NB), w) : 0.f;
+        rsc[threadIdx.x] = sc < 3.0e38f ? sc : 0.f;   // a denormal width would give an infinite scale
+    }
+    __syncthreads();
+}
+
+// MODE: hist (PHASE 0) or compaction (PHASE 1) over the members of every row
+template <int MODE, int PHASE>
+__global__ void __launch_bounds__(THREADS) lin_pass_kernel(const SelArgs a) {
+    extern __shared__ uint32_t sm[];
+    const int nrow = a.narr * a.K;
+    float* lo = reinterpret_cast<float*>(sm);          // [K]
+    float* hi = lo + a.K;                              // [K]
+    float* rlo = hi + a.K;                             // [nrow]
+    float* rsc = rlo + nrow;                           // [nrow]
+    uint32_t* tb = reinterpret_cast<uint32_t*>(rsc + nrow);  // [nrow] target bins (PHASE 1)
+    uint32_t* h = tb + nrow;                           // [nrow][NB] (PHASE 0)
+    const int b = blockIdx.y;
+    if (PHASE == 0)
+        for (int i = threadIdx.x; i < nrow * a.NB; i += THREADS) h[i] = 0;
+    if (PHASE == 1 && threadIdx.x < nrow) {
+        const int arr = threadIdx.x / a.K, k = threadIdx.x - arr * a.K;
+        tb[threadIdx.x] = a.tbin[row_of(a, arr, b, k)];
+    }
+    const bool has_valid = setup_thresholds<MODE>(a, b, lo, hi);
+    setup_ranges<MODE>(a, b, lo, hi, rlo, rsc);
+    const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
+    const long long end = min(start + a.chunk, a.L);
+    auto visit = [&](int row, int k, int arr, float x) {
+        const int bq = lin_bin(x, rlo[row], rsc[row], a.NB);
+        if (PHASE == 0) {
+            atomicAdd(&h[row * a.NB + bq], 1u);
+        } else if (static_cast<uint32_t>(bq) == tb[row]) {
+            const int r = row_of(a, arr, b, k);
+            const uint32_t pos = atomicAdd(&a.ccount[r], 1u);
+            if (pos < static_cast<uint32_t>(a.CAP)) a.cand[static_cast<long long>(r) * a.CAP + pos] = f2key(x);
+        }
+    };
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        const float p = a.pred[b * a.L + i];
+        const float g = (a.narr == 2 || MODE == MODE_DR) ? a.gt[b * a.L + i] : 0.f;
+        uint32_t bits = member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
+        while (bits) {
+            const int k = __ffs(bits) - 1;
+            bits &= bits - 1;
+            visit(k, k, 0, p);
+            if (a.narr == 2) visit(a.K + k, k, 1, g);
+        }
+    }
+    if (PHASE == 0) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nrow * a.NB; i += THREADS) {
+            const uint32_t v = h[i];
+            if (v) {
+                const int row = i / a.NB, arr = row / a.K, k = row - arr * a.K;
+                atomicAdd(&a.lhist[static_cast<long long>(row_of(a, arr, b, k)) * a.NB + (i - row * a.NB)], v);
+            }
+        }
+    }
+}
+
+// one warp per row: the bin that holds the lower-median rank
+__global__ void __launch_bounds__(THREADS) lin_scan_kernel(const SelArgs a) {
+    const int r = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= a.R) return;
+    const uint32_t* h = a.lhist + static_cast<long long>(r) * a.NB;
+    const int per = a.NB / 32;
+    uint32_t local = 0;
+    for (int j = 0; j < per; ++j) local += h[lane * per + j];
+    uint32_t incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) a.count[r] = total;
+    if (total == 0) {
+        if (lane == 0) { a.tbin[r] = 0xFFFFFFFFu; a.trank[r] = 0; a.cbin[r] = 0; a.t[r] = 0.f; }  // all-NaN row -> 0 (:490)
+        return;
+    }
+    const uint32_t k = (total - 1) / 2;
+    const uint32_t excl = incl - local;
+    if (k >= excl && k < incl) {
+        uint32_t cum = excl;
+        for (int j = 0; j < per; ++j) {
+            const uint32_t c = h[lane * per + j];
+            if (k < cum + c) { a.tbin[r] = lane * per + j; a.trank[r] = k - cum; a.cbin[r] = c; break; }
+            cum += c;
+        }
+    }
+}
+
+// one CTA per row: exact select of rank trank[r] among the members of bin tbin[r]
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) select_rows_kernel(const SelArgs a) {
+    extern __shared__ uint32_t sm[];
+    float* lo = reinterpret_cast<float*>(sm);          // [K]
+    float* hi = lo + a.K;
+    float* rlo = hi + a.K;                             // [nrow]
+    float* rsc = rlo + a.narr * a.K;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(rsc + a.narr * a.K);  // [256]
+    uint32_t* sel = hist + 256;                        // [2] prefix, rank
+    uint32_t* keys = sel + 2;                          // [CAP]
+    const int r = blockIdx.x;
+    const int arr = r / (a.B * a.K), b = (r / a.K) % a.B, k = r % a.K;
+    const uint32_t tbin = a.tbin[r];
+    if (tbin == 0xFFFFFFFFu) return;                   // empty row: t = 0 was written by the scan
+    const uint32_t n = a.cbin[r];
+    const bool listed = n <= static_cast<uint32_t>(a.CAP);
+    const int row = arr * a.K + k;
+    bool has_valid = true;
+    if (listed) {
+        for (uint32_t i = threadIdx.x; i < n; i += THREADS) keys[i] = a.cand[static_cast<long long>(r) * a.CAP + i];
+    } else {
+        has_valid = setup_thresholds<MODE>(a, b, lo, hi);
+        setup_ranges<MODE>(a, b, lo, hi, rlo, rsc);
+    }
+    if (threadIdx.x == 0) { sel[0] = 0u; sel[1] = a.trank[r]; }
+    __syncthreads();
+    const float* x = arr == 0 ? a.pred : a.gt;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[threadIdx.x] = 0;   // THREADS == 256
+        __syncthreads();
+        const uint32_t prefix = sel[0];
+        auto take = [&](uint32_t key) {
+            if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        };
+        if (listed) {
+            for (uint32_t i = threadIdx.x; i < n; i += THREADS) take(keys[i]);
+        } else {
+            for (long long i = threadIdx.x; i < a.L; i += THREADS) {
+                const float g = (a.narr == 2 || MODE == MODE_DR) ? a.gt[b * a.L + i] : 0.f;
+                const uint32_t bits = member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
+                if (!((bits >> k) & 1u)) continue;
+                const float v = x[b * a.L + i];
+                if (static_cast<uint32_t>(lin_bin(v, rlo[row], rsc[row], a.NB)) == tbin) take(f2key(v));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            uint32_t c[8], local = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; local += c[j]; }
+            uint32_t incl = local;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t kk = sel[1];
+            __syncwarp();  // every lane has read the rank before its owner overwrites it
+            const uint32_t excl = incl - local;
+            if (kk >= excl && kk < incl) {
+                uint32_t cum = excl;
+                int bin = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (kk >= cum + c[j]) { cum += c[j]; bin = j + 1; }
+                    else break;
+                }
+                sel[0] = prefix | (static_cast<uint32_t>(lane * 8 + bin) << shift);
+                sel[1] = kk - cum;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.t[r] = key2f(sel[0]);
+}
+
+// ---------------------------------------------------------------- sum |x - t| over members
+// KCAP bounds the per-thread accumulator arrays at compile time (8 covers SSI and HDN level <= 3; 21 the largest
+// explicit-context case), so the common cases do not pay for 21 predicated accumulations per pixel.
+template <int MODE, int KCAP>
 __global__ void __launch_bounds__(THREADS) mad_kernel(const SelArgs a) {
     extern __shared__ uint32_t sm[];
     const int nrow = a.narr * a.K;
@@ -293,9 +539,9 @@ __global__ void __launch_bounds__(THREADS) mad_kernel(const SelArgs a) {
     }
     __syncthreads();
     const bool has_valid = setup_thresholds<MODE>(a, b, lo, hi);
-    float accp[MAX_K], accg[MAX_K];
+    float accp[KCAP], accg[KCAP];
 #pragma unroll
-    for (int j = 0; j < MAX_K; ++j) { accp[j] = 0.f; accg[j] = 0.f; }
+    for (int j = 0; j < KCAP; ++j) { accp[j] = 0.f; accg[j] = 0.f; }
     const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
     const long long end = min(start + a.chunk, a.L);
     for (long long i = start + threadIdx.x; i < end; i += THREADS) {
@@ -304,7 +550,7 @@ __global__ void __launch_bounds__(THREADS) mad_kernel(const SelArgs a) {
         const uint32_t bits = member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
         if (!bits) continue;
 #pragma unroll
-        for (int k = 0; k < MAX_K; ++k) {
+        for (int k = 0; k < KCAP; ++k) {
             if (k < a.K && ((bits >> k) & 1u)) {
                 accp[k] += fabsf(p - tt[k]);
                 if (a.narr == 2) accg[k] += fabsf(g - tt[a.K + k]);
@@ -313,7 +559,7 @@ __global__ void __launch_bounds__(THREADS) mad_kernel(const SelArgs a) {
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < MAX_K; ++k) {
+    for (int k = 0; k < KCAP; ++k) {
         if (k < a.K) {
             float v = accp[k], w = accg[k];
             for (int o = 16; o; o >>= 1) {
@@ -440,12 +686,17 @@ struct Carver {
     }
 };
 
+constexpr int LIN_CAP = 4096;                      // candidate-list capacity per row
+inline int lin_nb(int K) { return K <= 8 ? 512 : 128; }  // value-linear bins per row (shared-memory histogram budget)
+
 size_t select_ws_bytes(int B, int K) {
     const size_t R = static_cast<size_t>(2) * B * K;
-    return 4096 + R * (4 * 256 * 4 + 4 + 4 + 4 + 4 + 8 + 4 + 6 * 256) + static_cast<size_t>(B) * 8 + 256;
+    const size_t radix = R * (4 * 256 * 4 + 4 + 4 + 4 + 4 + 8 + 4 + 6 * 256);
+    const size_t lin = R * (static_cast<size_t>(lin_nb(K)) * 4 + LIN_CAP * 4 + 16 + 256) + static_cast<size_t>(B) * 16 + 1024;
+    return 4096 + radix + lin + static_cast<size_t>(B) * 8 + 256;
 }
 
-int carve(SelArgs& a, void* ws, size_t ws_bytes, size_t* zero_bytes) {
+int carve(SelArgs& a, void* ws, size_t ws_bytes, size_t* zero_bytes, size_t* zero_small = nullptr) {
     const size_t need = select_ws_bytes(a.B, a.K);
     if (!ws || ws_bytes < need)
         return set_error(DAD_ERR_WORKSPACE, "loss workspace too small: need %zu bytes, got %zu", need, ws_bytes);
@@ -455,6 +706,7 @@ int carve(SelArgs& a, void* ws, size_t ws_bytes, size_t* zero_bytes) {
     // zero-initialised region first
     a.acc = c.take<double>(2);
     a.madsum = c.take<double>(a.R);
+    if (zero_small) *zero_small = c.used;   // all the range-bin path needs zeroed up front
     a.hist = c.take<uint32_t>(static_cast<size_t>(4) * a.R * 256);
     a.prefix = c.take<uint32_t>(a.R);
     a.krank = c.take<uint32_t>(a.R);
@@ -463,6 +715,16 @@ int carve(SelArgs& a, void* ws, size_t ws_bytes, size_t* zero_bytes) {
     a.t = c.take<float>(a.R);
     a.s = c.take<float>(a.R);
     a.minmax = c.take<uint32_t>(static_cast<size_t>(2) * a.B);
+    // range-bin selection state (lhist / ccount are zeroed by run_select_lin itself)
+    a.NB = lin_nb(a.K);
+    a.CAP = LIN_CAP;
+    a.imm = c.take<uint32_t>(static_cast<size_t>(4) * a.B);
+    a.tbin = c.take<uint32_t>(a.R);
+    a.trank = c.take<uint32_t>(a.R);
+    a.cbin = c.take<uint32_t>(a.R);
+    a.lhist = c.take<uint32_t>(static_cast<size_t>(a.R) * a.NB);
+    a.ccount = c.take<uint32_t>(a.R);
+    a.cand = c.take<uint32_t>(static_cast<size_t>(a.R) * a.CAP);
     return DAD_OK;
 }
 
@@ -497,7 +759,44 @@ int run_select(SelArgs& a, int mean_over_all, cudaStream_t st) {
         DAD_CHECK_LAUNCH();
     }
     const size_t sm_mad = static_cast<size_t>(nrow) * 4 + 2 * a.K * 4 + static_cast<size_t>(nrow) * 8 * 4;
-    mad_kernel<MODE><<<grid, THREADS, sm_mad, st>>>(a);
+    if (a.K <= 8) mad_kernel<MODE, 8><<<grid, THREADS, sm_mad, st>>>(a);
+    else mad_kernel<MODE, MAX_K><<<grid, THREADS, sm_mad, st>>>(a);
+    scale_kernel<<<cdiv(a.R, 128), 128, 0, st>>>(a, mean_over_all);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+// medians by range-bin selection (see the kernels above), then the same MAD / scale passes
+template <int MODE>
+int run_select_lin(SelArgs& a, int mean_over_all, cudaStream_t st) {
+    const int nrow = a.narr * a.K;
+    // larger chunks than the other passes: every CTA flushes nrow * NB bins
+    int chunk = a.chunk * 4;
+    if (chunk > a.L) chunk = static_cast<int>(cdivl(a.L, THREADS) * THREADS);
+    SelArgs h = a;
+    h.chunk = chunk;
+    const dim3 grid(static_cast<unsigned>(cdivl(a.L, a.chunk)), a.B);
+    const dim3 gridh(static_cast<unsigned>(cdivl(a.L, chunk)), a.B);
+    const size_t sm_pass = (2 * a.K + 3 * nrow) * 4 + static_cast<size_t>(nrow) * a.NB * 4;
+    const size_t sm_sel = (2 * a.K + 2 * nrow + 256 + 2 + a.CAP) * 4;
+    static bool done = false;
+    if (!done) {
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(lin_pass_kernel<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        done = true;
+    }
+    DAD_REQUIRE(sm_pass <= 64 * 1024, "loss: K=%d contexts need too much shared memory", a.K);
+    DAD_CHECK_CUDA(cudaMemsetAsync(a.lhist, 0, reinterpret_cast<uint8_t*>(a.ccount + a.R) - reinterpret_cast<uint8_t*>(a.lhist),
+                                   st));  // lhist and the ccount cursors behind it
+    init_imm_kernel<<<cdiv(a.B, 128), 128, 0, st>>>(a.imm, a.minmax, a.B);
+    imgminmax_kernel<<<grid, THREADS, 0, st>>>(a);
+    lin_pass_kernel<MODE, 0><<<gridh, THREADS, sm_pass, st>>>(h);
+    lin_scan_kernel<<<cdiv(a.R, THREADS / 32), THREADS, 0, st>>>(a);
+    lin_pass_kernel<MODE, 1><<<grid, THREADS, (2 * a.K + 3 * nrow) * 4, st>>>(a);
+    select_rows_kernel<MODE><<<a.R, THREADS, sm_sel, st>>>(a);
+    DAD_CHECK_LAUNCH();
+    const size_t sm_mad = static_cast<size_t>(nrow) * 4 + 2 * a.K * 4 + static_cast<size_t>(nrow) * 8 * 4;
+    if (a.K <= 8) mad_kernel<MODE, 8><<<grid, THREADS, sm_mad, st>>>(a);
+    else mad_kernel<MODE, MAX_K><<<grid, THREADS, sm_mad, st>>>(a);
     scale_kernel<<<cdiv(a.R, 128), 128, 0, st>>>(a, mean_over_all);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
@@ -522,8 +821,10 @@ int ssi_common(int mode, const float* pred, const float* gt, const uint8_t* mask
     a.pred = pred; a.gt = gt; a.mask = mask; a.ctx = ctx;
     a.B = B; a.K = K; a.level = level; a.narr = 2; a.L = L;
     a.chunk = pick_chunk(L, B);
-    size_t zero_bytes = 0;
-    DAD_TRY(carve(a, ws, ws_bytes, &zero_bytes));
+    size_t zero_bytes = 0, zero_small = 0;
+    DAD_TRY(carve(a, ws, ws_bytes, &zero_bytes, &zero_small));
+    static const bool radix = getenv("DAD_LOSS_RADIX") != nullptr;  // A/B switch: the 4 x 8-bit radix passes
+    if (!radix) zero_bytes = zero_small;
     // algorithmic bytes: pred + gt fp32 (+ 1-byte mask / K-byte contexts) per pixel
     ProfScope prof(PROF_LOSS, static_cast<double>(B) * L * (8.0 + (mask ? 1 : 0) + (ctx ? K : 0)), st,
                    (mode == MODE_DR ? 2 : 0) + 8 + 2 + 1 + ((out_scalar || partials) ? 1 : 0));
@@ -532,9 +833,16 @@ int ssi_common(int mode, const float* pred, const float* gt, const uint8_t* mask
     f.aligned_pred = aligned_pred; f.aligned_gt = aligned_gt; f.dense = dense;
     f.accumulate = (out_scalar || partials) ? 1 : 0;
     f.all_pixels = all_pixels;
-    if (mode == MODE_MASK) { DAD_TRY(run_select<MODE_MASK>(a, mean_over_all, st)); DAD_TRY(run_final<MODE_MASK>(a, f, st)); }
-    else if (mode == MODE_DR) { DAD_TRY(run_select<MODE_DR>(a, mean_over_all, st)); DAD_TRY(run_final<MODE_DR>(a, f, st)); }
-    else { DAD_TRY(run_select<MODE_CTX>(a, mean_over_all, st)); DAD_TRY(run_final<MODE_CTX>(a, f, st)); }
+    if (mode == MODE_MASK) {
+        DAD_TRY(radix ? run_select<MODE_MASK>(a, mean_over_all, st) : run_select_lin<MODE_MASK>(a, mean_over_all, st));
+        DAD_TRY(run_final<MODE_MASK>(a, f, st));
+    } else if (mode == MODE_DR) {
+        DAD_TRY(radix ? run_select<MODE_DR>(a, mean_over_all, st) : run_select_lin<MODE_DR>(a, mean_over_all, st));
+        DAD_TRY(run_final<MODE_DR>(a, f, st));
+    } else {
+        DAD_TRY(radix ? run_select<MODE_CTX>(a, mean_over_all, st) : run_select_lin<MODE_CTX>(a, mean_over_all, st));
+        DAD_TRY(run_final<MODE_CTX>(a, f, st));
+    }
     if (f.accumulate) {
         ratio_kernel<<<1, 1, 0, st>>>(a.acc, all_pixels ? 0.0 : 1e-6, out_scalar, partials, 0);
         DAD_CHECK_LAUNCH();
