@@ -24,6 +24,7 @@ constexpr int MODE_CTX = 2;   // K explicit u8 contexts [K, B, L]
 constexpr int MODE_RANK = 3;  // K order statistics of ONE array over the optional mask (quantile bins, HDN-DP)
 constexpr int MAX_K = 21;
 constexpr int THREADS = 256;
+constexpr int UNROLL = 4;     // pixels per thread whose loads are issued together in the streaming passes
 
 __device__ __forceinline__ uint32_t f2key(float f) {
     const uint32_t u = __float_as_uint(f);
@@ -308,13 +309,25 @@ __global__ void __launch_bounds__(THREADS) imgminmax_kernel(const SelArgs a) {
     const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
     const long long end = min(start + a.chunk, a.L);
     uint32_t pmn = 0xFFFFFFFFu, pmx = 0u, gmn = 0xFFFFFFFFu, gmx = 0u;
-    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
-        if (a.mask && a.mask[b * a.L + i] == 0) continue;
-        const uint32_t kp = f2key(a.pred[b * a.L + i]);
-        pmn = min(pmn, kp); pmx = max(pmx, kp);
-        if (a.narr == 2) {
-            const uint32_t kg = f2key(a.gt[b * a.L + i]);
-            gmn = min(gmn, kg); gmx = max(gmx, kg);
+    for (long long base = start + threadIdx.x; base < end; base += UNROLL * THREADS) {
+        float p[UNROLL], g[UNROLL];
+        bool in[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {  // all loads of the group are issued before any use
+            const long long i = base + u * THREADS;
+            in[u] = i < end && !(a.mask && a.mask[b * a.L + i] == 0);
+            p[u] = in[u] ? a.pred[b * a.L + i] : 0.f;
+            g[u] = (in[u] && a.narr == 2) ? a.gt[b * a.L + i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (!in[u]) continue;
+            const uint32_t kp = f2key(p[u]);
+            pmn = min(pmn, kp); pmx = max(pmx, kp);
+            if (a.narr == 2) {
+                const uint32_t kg = f2key(g[u]);
+                gmn = min(gmn, kg); gmx = max(gmx, kg);
+            }
         }
     }
     for (int o = 16; o; o >>= 1) {
@@ -388,15 +401,27 @@ __global__ void __launch_bounds__(THREADS) lin_pass_kernel(const SelArgs a) {
             if (pos < static_cast<uint32_t>(a.CAP)) a.cand[static_cast<long long>(r) * a.CAP + pos] = f2key(x);
         }
     };
-    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
-        const float p = a.pred[b * a.L + i];
-        const float g = (a.narr == 2 || MODE == MODE_DR) ? a.gt[b * a.L + i] : 0.f;
-        uint32_t bits = member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
-        while (bits) {
-            const int k = __ffs(bits) - 1;
-            bits &= bits - 1;
-            visit(k, k, 0, p);
-            if (a.narr == 2) visit(a.K + k, k, 1, g);
+    for (long long base = start + threadIdx.x; base < end; base += UNROLL * THREADS) {
+        float p[UNROLL], g[UNROLL];
+        uint32_t mb[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {  // all loads of the group are issued before any use
+            const long long i = base + u * THREADS;
+            const bool in = i < end;
+            p[u] = in ? a.pred[b * a.L + i] : 0.f;
+            g[u] = (in && (a.narr == 2 || MODE == MODE_DR)) ? a.gt[b * a.L + i] : 0.f;
+            mb[u] = in ? 1u : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (!mb[u]) continue;
+            uint32_t bits = member_bits<MODE>(a, b, base + u * THREADS, g[u], lo, hi, has_valid);
+            while (bits) {
+                const int k = __ffs(bits) - 1;
+                bits &= bits - 1;
+                visit(k, k, 0, p[u]);
+                if (a.narr == 2) visit(a.K + k, k, 1, g[u]);
+            }
         }
     }
     if (PHASE == 0) {
@@ -544,16 +569,28 @@ __global__ void __launch_bounds__(THREADS) mad_kernel(const SelArgs a) {
     for (int j = 0; j < KCAP; ++j) { accp[j] = 0.f; accg[j] = 0.f; }
     const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
     const long long end = min(start + a.chunk, a.L);
-    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
-        const float p = a.pred[b * a.L + i];
-        const float g = (a.narr == 2 || MODE == MODE_DR) ? a.gt[b * a.L + i] : 0.f;
-        const uint32_t bits = member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
-        if (!bits) continue;
+    for (long long base = start + threadIdx.x; base < end; base += UNROLL * THREADS) {
+        float pv[UNROLL], gv[UNROLL];
+        bool in[UNROLL];
 #pragma unroll
-        for (int k = 0; k < KCAP; ++k) {
-            if (k < a.K && ((bits >> k) & 1u)) {
-                accp[k] += fabsf(p - tt[k]);
-                if (a.narr == 2) accg[k] += fabsf(g - tt[a.K + k]);
+        for (int u = 0; u < UNROLL; ++u) {  // all loads of the group are issued before any use
+            const long long i = base + u * THREADS;
+            in[u] = i < end;
+            pv[u] = in[u] ? a.pred[b * a.L + i] : 0.f;
+            gv[u] = (in[u] && (a.narr == 2 || MODE == MODE_DR)) ? a.gt[b * a.L + i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (!in[u]) continue;
+            const float p = pv[u], g = gv[u];
+            const uint32_t bits = member_bits<MODE>(a, b, base + u * THREADS, g, lo, hi, has_valid);
+            if (!bits) continue;
+#pragma unroll
+            for (int k = 0; k < KCAP; ++k) {
+                if (k < a.K && ((bits >> k) & 1u)) {
+                    accp[k] += fabsf(p - tt[k]);
+                    if (a.narr == 2) accg[k] += fabsf(g - tt[a.K + k]);
+                }
             }
         }
     }
@@ -621,30 +658,44 @@ __global__ void __launch_bounds__(THREADS) final_kernel(const SelArgs a, const F
     unsigned long long cnt = 0;
     const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
     const long long end = min(start + a.chunk, a.L);
-    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
-        const float p = a.pred[b * a.L + i];
-        const float g = a.gt[b * a.L + i];
-        const uint32_t bits = f.all_pixels ? 1u : member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
-        if (a.K == 1) {
-            const float pa = (p - tt[0]) / inv[0];
-            const float ga = (g - tt[1]) / inv[1];
-            if (f.aligned_pred) f.aligned_pred[b * a.L + i] = pa;
-            if (f.aligned_gt) f.aligned_gt[b * a.L + i] = ga;
-            const float e = bits ? fabsf(pa - ga) : 0.f;
-            if (f.dense) f.dense[b * a.L + i] = e;
-            sum += e;
-            cnt += bits ? 1u : 0u;
-        } else if (bits) {
-            float e = 0.f;
-            for (int k = 0; k < a.K; ++k) {
-                if ((bits >> k) & 1u) {
+    for (long long base = start + threadIdx.x; base < end; base += UNROLL * THREADS) {
+        float pv[UNROLL], gv[UNROLL];
+        bool in[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {  // all loads of the group are issued before any use
+            const long long i = base + u * THREADS;
+            in[u] = i < end;
+            pv[u] = in[u] ? a.pred[b * a.L + i] : 0.f;
+            gv[u] = in[u] ? a.gt[b * a.L + i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (!in[u]) continue;
+            const long long i = base + u * THREADS;
+            const float p = pv[u], g = gv[u];
+            const uint32_t bits = f.all_pixels ? 1u : member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
+            if (a.K == 1) {
+                const float pa = (p - tt[0]) / inv[0];
+                const float ga = (g - tt[1]) / inv[1];
+                if (f.aligned_pred) f.aligned_pred[b * a.L + i] = pa;
+                if (f.aligned_gt) f.aligned_gt[b * a.L + i] = ga;
+                const float e = bits ? fabsf(pa - ga) : 0.f;
+                if (f.dense) f.dense[b * a.L + i] = e;
+                sum += e;
+                cnt += bits ? 1u : 0u;
+            } else if (bits) {
+                float e = 0.f;
+                uint32_t rest = bits;
+                while (rest) {  // member contexts in ascending order (3 of 7 for HDN-DR)
+                    const int k = __ffs(rest) - 1;
+                    rest &= rest - 1;
                     const float pa = (p - tt[k]) / inv[k];
                     const float ga = (g - tt[a.K + k]) / inv[a.K + k];
                     e += fabsf(pa - ga);
                 }
+                sum += e / static_cast<float>(__popc(bits));
+                cnt += 1u;
             }
-            sum += e / static_cast<float>(__popc(bits));
-            cnt += 1u;
         }
     }
     if (!f.accumulate) return;
@@ -770,8 +821,8 @@ int run_select(SelArgs& a, int mean_over_all, cudaStream_t st) {
 template <int MODE>
 int run_select_lin(SelArgs& a, int mean_over_all, cudaStream_t st) {
     const int nrow = a.narr * a.K;
-    // larger chunks than the other passes: every CTA flushes nrow * NB bins
-    int chunk = a.chunk * 4;
+    // every CTA flushes nrow * NB bins: keep the flush well below the pixel work (SSI: 1 K bins, HDN-DR: 7 K bins)
+    int chunk = a.chunk * (nrow * a.NB > 2048 ? 2 : 1);
     if (chunk > a.L) chunk = static_cast<int>(cdivl(a.L, THREADS) * THREADS);
     SelArgs h = a;
     h.chunk = chunk;
