@@ -104,12 +104,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* in, const f
 
 // ---------------------------------------------------------------- bilinear, align_corners=True (K14/K16)
 // NHWC, VEC channels per thread.  Index maths as ATen's area_pixel_compute_source_index.
-constexpr int BIL_ROWS = 8;  // output rows per thread (amortises index maths, keeps 8 independent row pairs in flight)
+constexpr int BIL_ROWS = 16;  // output rows per thread: a sliding window of two horizontally blended source rows serves them
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int Hi, int Wi, int Ho,
                                                        int Wo, int C, float sh, float sw) {
-    // grid: (x-chunks, output row groups, image); thread -> (output column, VEC-channel group) x BIL_ROWS rows
+    // grid: (x-chunks, output row groups, image); thread -> (output column, VEC-channel group) x BIL_ROWS rows.
+    // out = hy * (hx * a + lx * b) + ly * (hx * c + lx * d) in ATen's operation order.  The horizontal blends
+    // (hx * a + lx * b) of source rows y0 and y1 are kept in registers: when the next output row needs the same source
+    // rows (always, when upsampling) nothing is reloaded, when it moves down by one the lower row is reused - 0.5-0.6
+    // source rows are fetched and blended per output row instead of 2 (the kernel was issue-bound, not HBM-bound).
     pdl_wait();
     const int cv = C / VEC;
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -123,8 +127,17 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const T* __restrict__ in,
     const T* base = in + static_cast<long long>(b) * Hi * Wi * C + c * VEC;
     T* obase = out + static_cast<long long>(b) * Ho * Wo * C + static_cast<long long>(ox) * C + c * VEC;
     struct alignas(16) Pack { T v[VEC]; };
+    const int rowpitch = Wi * C;
+    const int o0 = x0 * C, o1 = x1 * C;
+    auto hblend = [&](int y, float (&h)[VEC]) {   // h = hx * in[y, x0] + lx * in[y, x1]
+        const T* r = base + static_cast<long long>(y) * rowpitch;
+        const Pack a = *reinterpret_cast<const Pack*>(r + o0), bq = *reinterpret_cast<const Pack*>(r + o1);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) h[j] = hx * to_f(a.v[j]) + lx * to_f(bq.v[j]);
+    };
+    float h0[VEC], h1[VEC];
+    int cy0 = -1, cy1 = -1;   // source rows currently held in h0 / h1
     const int oy0 = blockIdx.y * BIL_ROWS;
-#pragma unroll 4
     for (int r = 0; r < BIL_ROWS; ++r) {
         const int oy = oy0 + r;
         if (oy >= Ho) break;
@@ -132,14 +145,27 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const T* __restrict__ in,
         const int y0 = static_cast<int>(fy);
         const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0);
         const float ly = fy - y0, hy = 1.f - ly;
-        const T* r0 = base + static_cast<long long>(y0) * Wi * C;
-        const T* r1 = base + static_cast<long long>(y1) * Wi * C;
-        const Pack a = *reinterpret_cast<const Pack*>(r0 + x0 * C), bq = *reinterpret_cast<const Pack*>(r0 + x1 * C);
-        const Pack cq = *reinterpret_cast<const Pack*>(r1 + x0 * C), d = *reinterpret_cast<const Pack*>(r1 + x1 * C);
+        if (y0 != cy0) {          // (block-uniform branches: every thread of the block has the same oy)
+            if (y0 == cy1) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) h0[j] = h1[j];
+            } else {
+                hblend(y0, h0);
+            }
+            cy0 = y0;
+        }
+        if (y1 != cy1) {
+            if (y1 == y0) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) h1[j] = h0[j];
+            } else {
+                hblend(y1, h1);
+            }
+            cy1 = y1;
+        }
         Pack o;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j)
-            o.v[j] = from_f<T>(hy * (hx * to_f(a.v[j]) + lx * to_f(bq.v[j])) + ly * (hx * to_f(cq.v[j]) + lx * to_f(d.v[j])));
+        for (int j = 0; j < VEC; ++j) o.v[j] = from_f<T>(hy * h0[j] + ly * h1[j]);
         *reinterpret_cast<Pack*>(obase + static_cast<long long>(oy) * Wo * C) = o;
     }
 }
