@@ -43,6 +43,7 @@ PROTOTYPES = {
     "dad_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dad_gemm_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dad_conv_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dad_conv_nhwc_ex": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dad_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "dad_launch_count": (_c.c_longlong, []),
     "dad_profile_enable": (None, [_i]),

@@ -104,6 +104,17 @@ int dad_minmax_normalize(const float* in, int B, int64_t L, float* out, void* ws
     return dad::minmax_normalize(in, B, L, out, ws, wsb, ST(stream));
 }
 
+int dad_conv_nhwc_ex(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
+                     int Co, int taps, int stride, int mode, void* stream) {
+    if (mode != 0 && stride != 1)
+        return dad::set_error(DAD_ERR_UNSUPPORTED, "dad_conv_nhwc_ex: strided convolution exists in the tensor-core engine only");
+    dad::GemmProblem p;
+    p.A = in; p.conv = 1; p.B = B; p.H = H; p.W = W; p.C = C; p.taps = taps; p.ldp = C; p.stride = stride;
+    p.Wt = Wpacked; p.N = Co; p.Kp = taps * dad::cdiv(C, 64) * 64;
+    p.epi.bias = bias; p.epi.out = out; p.epi.ldc = Co;
+    return mode == 0 ? dad::gemm_tc(p, ST(stream)) : dad::gemm_simt(p, ST(stream));
+}
+
 int dad_attention(const void* qkv, void* out, int B, int N, int heads, int mode, void* stream) {
     return dad::attention(qkv, out, mode == 0, B, N, heads, ST(stream));
 }

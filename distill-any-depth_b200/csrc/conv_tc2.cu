@@ -409,7 +409,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv2Args& a, d
 
 bool conv_tc2_eligible(const GemmProblem& p) {
     static const bool off = getenv("DAD_NO_CONV2") != nullptr;  // A/B switch
-    if (off || !p.conv || p.taps != 9 || (p.N % 128) != 0 || p.C % 8 != 0 || p.ldp % 8 != 0) return false;
+    if (off || !p.conv || p.stride != 1 || p.taps != 9 || (p.N % 128) != 0 || p.C % 8 != 0 || p.ldp % 8 != 0) return false;
     const Epilogue& e = p.epi;
     if (e.scat_k || e.rowtab || e.head_out || e.gamma || e.act == ACT_GELU || !e.out) return false;
     if ((e.res1 && !e.res1_bf16) || (e.res2 && !e.res2_bf16)) return false;  // the pipelined epilogue keeps bf16 residuals raw

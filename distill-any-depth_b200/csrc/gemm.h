@@ -50,6 +50,7 @@ struct GemmProblem {
     // conv (stride 1, "same" zero padding): NHWC with `ldp` elements between pixels
     int B = 0, H = 0, W = 0, C = 0, taps = 1;
     long long ldp = 0;
+    int stride = 1;           // 3x3 only: output is ((H - 1) / stride + 1) x ((W - 1) / stride + 1) (gemm_tc; stride 1 or 2)
     // weights
     const void* Wt = nullptr; // [N, Kp] K-major; bf16 (tc) or fp32 (simt)
     int N = 0;

@@ -38,7 +38,7 @@ struct TcArgs {
     Epilogue epi;
     int M, N;
     int num_k_blocks;
-    int conv, taps, cchunks, pad;
+    int conv, taps, cchunks, pad, stride;
     int B, H, W;
     int tw_log2, th;        // spatial tile (conv): TW = 1 << tw_log2, TH = 128 / TW
     int tiles_x, tiles_y;
@@ -173,7 +173,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         int dy = 0, dx = 0;
                         if (g.taps == 9) { dy = tap / 3; dx = tap - dy * 3; }
                         ptx::tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], cc * BK,
-                                         x0 + dx - g.pad, y0 + dy - g.pad, b);
+                                         x0 * g.stride + dx - g.pad, y0 * g.stride + dy - g.pad, b);
                     } else {
                         ptx::tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, mt * BM);
                     }
@@ -553,19 +553,24 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     if (p.conv) {
         DAD_REQUIRE(p.taps == 1 || p.taps == 9, "gemm_tc: taps must be 1 or 9");
         DAD_REQUIRE(p.C % 8 == 0 && p.ldp % 8 == 0, "gemm_tc: conv C/ldp must be multiples of 8");
+        DAD_REQUIRE(p.stride == 1 || (p.stride == 2 && p.taps == 9), "gemm_tc: stride %d unsupported", p.stride);
         a.taps = p.taps;
+        a.stride = p.stride;
         a.pad = p.taps == 9 ? 1 : 0;
+        // output extent ("same" padding): H x W at stride 1, ((H - 1) / 2 + 1) x ((W - 1) / 2 + 1) at stride 2
+        const int Ho = (p.H - 1) / p.stride + 1, Wo = (p.W - 1) / p.stride + 1;
         a.cchunks = cdiv(p.C, BK);
         a.num_k_blocks = a.taps * a.cchunks;
         DAD_REQUIRE(p.Kp == a.num_k_blocks * BK, "gemm_tc: conv weights must be packed to Kp=%d (got %d)",
                     a.num_k_blocks * BK, p.Kp);
-        a.B = p.B; a.H = p.H; a.W = p.W;
-        a.M = p.B * p.H * p.W;
+        a.B = p.B; a.H = Ho; a.W = Wo;   // the kernel tiles and stores OUTPUT pixels
+        a.M = p.B * Ho * Wo;
         a.flops = 2.0 * a.M * p.N * (static_cast<double>(p.taps) * p.C);
+        DAD_REQUIRE(p.stride == 1 || !p.epi.scat_k, "gemm_tc: strided conv with a scatter epilogue is unsupported");
         static const bool halo_off = getenv("DAD_NO_HALO") != nullptr;      // bring-up A/B switches
         // (measured on B200: UMMA applies the 128B swizzle to absolute shared-memory address bits, exactly like TMA,
         // so the row-shifted halo views need base_offset = 0 in their descriptors)
-        halo = !halo_off && p.taps == 9 && bn <= 64 && cdiv(p.N, bn) == 1 &&
+        halo = !halo_off && p.stride == 1 && p.taps == 9 && bn <= 64 && cdiv(p.N, bn) == 1 &&
                static_cast<long long>(9) * cdiv(p.C, BK) * bn * BK * 2 <= WRES_BYTES;  // weights fit in smem
         if (halo) {  // 16 x 8 output pixels per tile, one 18 x 16 halo box per channel chunk
             a.tw_log2 = 3;
@@ -575,19 +580,22 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
             long long best = -1;
             for (int l2 = 3; l2 <= 7; ++l2) {
                 const int tw = 1 << l2, th = BM / tw;
-                const long long area = static_cast<long long>(cdiv(p.W, tw)) * tw * cdiv(p.H, th) * th;
+                const long long area = static_cast<long long>(cdiv(Wo, tw)) * tw * cdiv(Ho, th) * th;
                 if (best < 0 || area < best) { best = area; a.tw_log2 = l2; a.th = th; }
             }
         }
         const int tw = 1 << a.tw_log2;
-        a.tiles_x = cdiv(p.W, tw);
-        a.tiles_y = cdiv(p.H, a.th);
+        a.tiles_x = cdiv(Wo, tw);
+        a.tiles_y = cdiv(Ho, a.th);
         a.num_m_tiles = p.B * a.tiles_x * a.tiles_y;
         const cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
         const cuuint64_t strides[3] = {(cuuint64_t)p.ldp * 2, (cuuint64_t)p.ldp * 2 * p.W,
                                        (cuuint64_t)p.ldp * 2 * p.W * p.H};
-        const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(halo ? HALO_W : tw), (cuuint32_t)(halo ? HALO_H : a.th), 1};
-        DAD_TRY(make_tmap_bf16(&tmA, p.A, 4, dims, strides, box));
+        // stride 2: the box walks 2 * t - 1 input pixels and picks every second one (t elements land in shared memory)
+        const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(halo ? HALO_W : (tw - 1) * p.stride + 1),
+                                   (cuuint32_t)(halo ? HALO_H : (a.th - 1) * p.stride + 1), 1};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
+        DAD_TRY(make_tmap(&tmA, 0, p.A, 4, dims, strides, box, estr));
     } else {
         DAD_REQUIRE(p.M > 0 && p.K > 0 && p.lda >= p.K && p.lda % 8 == 0, "gemm_tc: bad linear dims M=%d K=%d lda=%lld",
                     p.M, p.K, p.lda);
@@ -626,15 +634,15 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         if (scat_tma) {
             const int tw = 1 << a.tw_log2, k = e.scat_k, Co = e.scat_Co;
             const cuuint64_t dims[5] = {(cuuint64_t)k * Co, (cuuint64_t)p.W, (cuuint64_t)k, (cuuint64_t)p.H, (cuuint64_t)p.B};
-            const cuuint64_t sx = (cuuint64_t)k * Co * 2, sky = sx * p.W, sy = sky * k, sb = sy * p.H;
+            const cuuint64_t sx = (cuuint64_t)k * Co * 2, sky = sx * p.W, sy = sky * k, sb = sy * p.H;  // stride 1 only
             const cuuint64_t strides[4] = {sx, sky, sy, sb};
             const cuuint32_t box[5] = {64u, (cuuint32_t)tw, 1u, (cuuint32_t)a.th, 1u};
             DAD_TRY(make_tmap(&tmC, 0, p.epi.out, 5, dims, strides, box));
         } else if (p.conv) {
             const int tw = 1 << a.tw_log2;
-            const cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
-            const cuuint64_t strides[3] = {(cuuint64_t)p.epi.ldc * es, (cuuint64_t)p.epi.ldc * es * p.W,
-                                           (cuuint64_t)p.epi.ldc * es * p.W * p.H};
+            const cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)p.B};
+            const cuuint64_t strides[3] = {(cuuint64_t)p.epi.ldc * es, (cuuint64_t)p.epi.ldc * es * a.W,
+                                           (cuuint64_t)p.epi.ldc * es * a.W * a.H};
             const cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)tw, (cuuint32_t)a.th, 1};
             DAD_TRY(make_tmap(&tmC, f32 ? 1 : 0, p.epi.out, 4, dims, strides, box));
         } else {

@@ -253,9 +253,9 @@ public:
 
     // conv3x3 / conv1x1 (stride 1) on an NHWC tensor through the GEMM engine
     int conv(int mode, const void* in, int B, int H, int W, int C, const Mat& m, int taps, const Epilogue& e, bool dry,
-             cudaStream_t st) {
+             cudaStream_t st, int stride = 1) {
         GemmProblem p;
-        p.A = in; p.conv = 1; p.B = B; p.H = H; p.W = W; p.C = C; p.taps = taps; p.ldp = C;
+        p.A = in; p.conv = 1; p.B = B; p.H = H; p.W = W; p.C = C; p.taps = taps; p.ldp = C; p.stride = stride;
         p.Wt = m.w[mode]; p.N = m.N; p.Kp = m.Kp;
         p.epi = e;
         if (p.epi.ldc == 0) p.epi.ldc = m.N;
@@ -422,12 +422,20 @@ public:
             } else if (j == 3) {
                 const int Cp = cdiv(oc[3], 64) * 64;
                 const long long rows = static_cast<long long>(B) * hs[3] * wsz[3];
-                void* col = ar.take(rows * 9 * Cp * es);
-                rj = ar.take(rows * oc[3] * es);
-                debug_label("im2col_s2");
-                if (!dry) DAD_TRY(im2col_s2(pj, col, bf, B, ph, pw, oc[3], Cp, st));
-                Epilogue e3; e3.bias = P(h + "resize_layers.3.bias"); e3.out = rj; e3.out_bf16 = bf;
-                DAD_TRY(linear(mode, col, rows, 9 * Cp, resize3, e3, dry, st));
+                Epilogue e3; e3.bias = P(h + "resize_layers.3.bias"); e3.out_bf16 = bf;
+                if (mode == 0) {
+                    // implicit GEMM straight from the NHWC map: the TMA box walks the input with element stride 2
+                    rj = ar.take(rows * oc[3] * es);
+                    e3.out = rj;
+                    DAD_TRY(conv(mode, pj, B, ph, pw, oc[3], resize3, 9, e3, dry, st, 2));
+                } else {
+                    void* col = ar.take(rows * 9 * Cp * es);
+                    rj = ar.take(rows * oc[3] * es);
+                    e3.out = rj;
+                    debug_label("im2col_s2");
+                    if (!dry) DAD_TRY(im2col_s2(pj, col, bf, B, ph, pw, oc[3], Cp, st));
+                    DAD_TRY(linear(mode, col, rows, 9 * Cp, resize3, e3, dry, st));
+                }
             }
             const size_t n = static_cast<size_t>(B) * hs[j] * wsz[j] * F;
             lrn[j] = ar.take(n * es);

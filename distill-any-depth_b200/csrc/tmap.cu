@@ -21,10 +21,12 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 int make_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims,
-              const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+              const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* elem_strides) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (elem_strides)
+        for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
         return set_error(DAD_ERR_INVALID, "TMA base address %p not 16-byte aligned", base);
     for (int i = 0; i < rank - 1; ++i)

@@ -8,8 +8,9 @@
 namespace dad {
 
 // dtype: 0 = bf16, 1 = fp32
+// elem_strides (optional, per dimension): traversal step of the box; ceil(box[i] / elem_strides[i]) elements are loaded
 int make_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims,
-              const cuuint64_t* strides_bytes, const cuuint32_t* box);
+              const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr);
 inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
                           const cuuint64_t* strides_bytes, const cuuint32_t* box) {
     return make_tmap(m, 0, base, rank, dims, strides_bytes, box);

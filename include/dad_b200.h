@@ -142,6 +142,10 @@ int dad_gemm_ex(const void* A, const void* W, const float* bias, const float* ga
 /* conv3x3 / 1x1 (stride 1, zero padding) on NHWC input [B,H,W,C] with packed weights [Co, taps*Cp]. */
 int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
                   int Co, int taps, int mode, void* stream);
+/* Same with a stride (1 or 2; 3x3 "same" padding): out is [B, (H-1)/stride+1, (W-1)/stride+1, Co].  Stride 2 is the
+ * resize_layers[3] convolution (dpt.py:101-106), an implicit GEMM whose TMA box walks the input with element stride 2. */
+int dad_conv_nhwc_ex(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
+                     int Co, int taps, int stride, int mode, void* stream);
 /* attention over qkv [B*N, 3*heads*64] (q pre-scaled) -> out [B*N, heads*64]; bf16 bits (mode 0) or fp32. */
 int dad_attention(const void* qkv, void* out, int B, int N, int heads, int mode, void* stream);
 

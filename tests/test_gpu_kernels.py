@@ -131,6 +131,28 @@ def test_conv_nhwc_matches_conv2d(B, H, W, C, Co, taps, mode):
     assert (out - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("B,H,W,C,Co", [(2, 37, 37, 128, 128), (1, 28, 28, 768, 768), (3, 9, 14, 64, 256), (1, 5, 5, 384, 64)])
+def test_conv_stride2_matches_conv2d(B, H, W, C, Co):
+    """resize_layers[3] (dpt.py:101-106): 3x3 stride-2 pad-1 convolution as an implicit GEMM (TMA element strides)."""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(H * W + C)
+    x = torch.randn(B, C, H, W, device="cuda", generator=g)
+    w = torch.randn(Co, C, 3, 3, device="cuda", generator=g) * 0.05
+    bias = torch.randn(Co, device="cuda", generator=g)
+    xq, wq = x.bfloat16(), w.bfloat16()
+    x_nhwc = xq.permute(0, 2, 3, 1).contiguous()
+    wp = pack_conv_weight(wq.float(), torch.bfloat16)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.full((B, Ho, Wo, Co), float("nan"), device="cuda")
+    L.check(lib.dad_conv_nhwc_ex(L.ptr(x_nhwc), L.ptr(wp), L.ptr(bias), L.ptr(out), B, H, W, C, Co, 9, 2, 0,
+                                 L.stream_ptr()), "dad_conv_nhwc_ex")
+    torch.cuda.synchronize()
+    ref = F.conv2d(xq.double(), wq.double(), bias.double(), stride=2, padding=1).float().permute(0, 2, 3, 1)
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
 @pytest.fixture(params=[2, 3], ids=["pipelined2cta", "serial4cta"])
 def att_variant(request, monkeypatch):
     """Both tcgen05 attention kernels (attention_tc.cu / attention_tc3.cu) go through the same tests."""
