@@ -29,6 +29,25 @@ int dad_contexts_dr(int level, const float* gt, const uint8_t* mask, int B, int6
     return dad::contexts_dr(level, gt, mask, B, L, ctx_out, ws, wsb, ST(stream));
 }
 
+int dad_ssi_loss_bwd(const float* pred, const float* gt, const uint8_t* mask, int rows, int64_t L, const float* grad_out,
+                     float* grad_pred, void* ws, size_t wsb, void* stream) {
+    return dad::ssi_loss_bwd(pred, gt, mask, rows, L, grad_out, grad_pred, ws, wsb, ST(stream));
+}
+
+int dad_hdn_loss_dr_bwd(int level, const float* pred, const float* gt, const uint8_t* mask, int B, int64_t L,
+                        const float* grad_out, float* grad_pred, void* ws, size_t wsb, void* stream) {
+    return dad::hdn_loss_dr_bwd(level, pred, gt, mask, B, L, grad_out, grad_pred, ws, wsb, ST(stream));
+}
+
+int dad_hdn_loss_bwd(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, int64_t L, const float* grad_out,
+                     float* grad_pred, void* ws, size_t wsb, void* stream) {
+    return dad::hdn_loss_ctx_bwd(pred, gt, ctx, K, B, L, grad_out, grad_pred, ws, wsb, ST(stream));
+}
+
+int dad_grad_loss_bwd(const float* depth, int B, int H, int W, const float* grad_out, float* grad_depth, void* stream) {
+    return dad::grad_loss_bwd(depth, B, H, W, grad_out, grad_depth, ST(stream));
+}
+
 int dad_contexts_dp(int level, const float* gt, const uint8_t* mask, int B, int64_t L, uint8_t* ctx_out, void* ws,
                     size_t wsb, void* stream) {
     return dad::contexts_dp(level, gt, mask, B, L, ctx_out, ws, wsb, ST(stream));

@@ -64,6 +64,9 @@ struct SelArgs {
     uint32_t* ccount;      // [R] append cursor of the candidate list
     uint32_t* cand;        // [R][CAP] keys of the candidates
     int NB, CAP;
+    // backward (gradient w.r.t. pred; gt is the detached teacher map)
+    double* racc;          // [B*K][3]  E = sum w*sgn, G = sum w*sgn*(p - t), S = sum sign(p - t) over the members of the row
+    unsigned int* jstar;   // [B*K]     lowest member index holding the median value (where d median / d p lives)
 };
 
 __device__ __forceinline__ int row_of(const SelArgs& a, int arr, int b, int k) { return (arr * a.B + b) * a.K + k; }
@@ -743,7 +746,7 @@ inline int lin_nb(int K) { return K <= 8 ? 512 : 128; }  // value-linear bins pe
 size_t select_ws_bytes(int B, int K) {
     const size_t R = static_cast<size_t>(2) * B * K;
     const size_t radix = R * (4 * 256 * 4 + 4 + 4 + 4 + 4 + 8 + 4 + 6 * 256);
-    const size_t lin = R * (static_cast<size_t>(lin_nb(K)) * 4 + LIN_CAP * 4 + 16 + 256) + static_cast<size_t>(B) * 16 + 1024;
+    const size_t lin = R * (static_cast<size_t>(lin_nb(K)) * 4 + LIN_CAP * 4 + 16 + 256 + 32) + static_cast<size_t>(B) * 16 + 2048;
     return 4096 + radix + lin + static_cast<size_t>(B) * 8 + 256;
 }
 
@@ -776,6 +779,8 @@ int carve(SelArgs& a, void* ws, size_t ws_bytes, size_t* zero_bytes, size_t* zer
     a.lhist = c.take<uint32_t>(static_cast<size_t>(a.R) * a.NB);
     a.ccount = c.take<uint32_t>(a.R);
     a.cand = c.take<uint32_t>(static_cast<size_t>(a.R) * a.CAP);
+    a.racc = c.take<double>(static_cast<size_t>(a.B) * a.K * 3);
+    a.jstar = c.take<unsigned int>(static_cast<size_t>(a.B) * a.K);
     return DAD_OK;
 }
 
@@ -899,6 +904,236 @@ int ssi_common(int mode, const float* pred, const float* gt, const uint8_t* mask
         DAD_CHECK_LAUNCH();
     }
     return DAD_OK;
+}
+
+// ================================================================ backward of SSI / HDN w.r.t. pred
+// Forward (tools/train_distillation.py:449-542, 686-707), per row r = (image, context k) with members M_r:
+//   t = lower median of p over M_r,  s = sum_{M_r} |p - t| / (n + 1),  pa_i = (p_i - t) / (s + 1e-6)
+//   L = (1 / (N + 1e-6)) * sum_i (1 / c_i) * sum_{k contains i} |pa_ik - ga_ik|      (c_i = 1, N = sum mask for SSI)
+// PyTorch's autograd through nanmedian routes d t / d p to the selected element j*, and |.| has sign(0) = 0, so with
+//   e_ik = sgn(pa_ik - ga_ik) / c_i,  E = sum e,  G = sum e * (p - t),  S = sum_{M_r} sign(p - t):
+//   dL/dp_j * (N + 1e-6) = sum_{k contains j} [ e_jk / (s+eps) - G / (s+eps)^2 * sign(p_j - t) / (n+1) ]
+//                          + [j == j*_k] * ( -E / (s+eps) + G / (s+eps)^2 * S / (n+1) )
+// Pass 1 reduces E, G, S per row and finds j* (lowest member index holding the median value); pass 2 writes the map.
+struct BwdArgs {
+    const float* gout;   // upstream gradient of the scalar loss (device)
+    float* grad;         // [B, L]
+};
+
+__device__ __forceinline__ float fsign(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+template <int MODE, int KCAP>
+__global__ void __launch_bounds__(THREADS) bwd_reduce_kernel(const SelArgs a) {
+    extern __shared__ uint32_t sm[];
+    const int nrow = 2 * a.K;
+    float* tt = reinterpret_cast<float*>(sm);  // [2K] medians (pred rows, then gt rows)
+    float* den = tt + nrow;                    // [2K] s + 1e-6
+    float* lo = den + nrow;
+    float* hi = lo + a.K;
+    float* red = hi + a.K;                     // [3K][8 warps]
+    __shared__ unsigned long long red_cnt[8];
+    const int b = blockIdx.y;
+    if (threadIdx.x < nrow) {
+        const int arr = threadIdx.x / a.K, k = threadIdx.x - arr * a.K;
+        tt[threadIdx.x] = a.t[row_of(a, arr, b, k)];
+        den[threadIdx.x] = a.s[row_of(a, arr, b, k)] + 1e-6f;
+    }
+    __syncthreads();
+    const bool has_valid = setup_thresholds<MODE>(a, b, lo, hi);
+    float accE[KCAP], accG[KCAP], accS[KCAP];
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) { accE[j] = 0.f; accG[j] = 0.f; accS[j] = 0.f; }
+    unsigned long long cnt = 0;
+    const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
+    const long long end = min(start + a.chunk, a.L);
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        const float p = a.pred[b * a.L + i], g = a.gt[b * a.L + i];
+        const uint32_t bits = member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
+        if (!bits) continue;
+        cnt += 1u;
+        const float w = 1.0f / static_cast<float>(__popc(bits));
+#pragma unroll
+        for (int k = 0; k < KCAP; ++k) {
+            if (k < a.K && ((bits >> k) & 1u)) {
+                const float dp = p - tt[k];
+                const float pa = dp / den[k], ga = (g - tt[a.K + k]) / den[a.K + k];
+                const float e = w * fsign(pa - ga);
+                accE[k] += e;
+                accG[k] += e * dp;
+                accS[k] += fsign(dp);
+                if (dp == 0.f) atomicMin(&a.jstar[b * a.K + k], static_cast<unsigned int>(i));
+            }
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < KCAP; ++k) {
+        if (k < a.K) {
+            float e = accE[k], gq = accG[k], sq = accS[k];
+            for (int o = 16; o; o >>= 1) {
+                e += __shfl_xor_sync(0xffffffffu, e, o);
+                gq += __shfl_xor_sync(0xffffffffu, gq, o);
+                sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            }
+            if (lane == 0) { red[(3 * k) * 8 + warp] = e; red[(3 * k + 1) * 8 + warp] = gq; red[(3 * k + 2) * 8 + warp] = sq; }
+        }
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) red_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x < 3 * a.K) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += static_cast<double>(red[threadIdx.x * 8 + w]);
+        const int k = threadIdx.x / 3, q = threadIdx.x - 3 * k;
+        if (v != 0.0) atomicAdd(&a.racc[(static_cast<long long>(b) * a.K + k) * 3 + q], v);
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long c = 0;
+        for (int w = 0; w < 8; ++w) c += red_cnt[w];
+        atomicAdd(&a.acc[1], static_cast<double>(c));
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) bwd_apply_kernel(const SelArgs a, const BwdArgs w) {
+    extern __shared__ uint32_t sm[];
+    const int nrow = 2 * a.K;
+    float* tt = reinterpret_cast<float*>(sm);   // [2K]
+    float* den = tt + nrow;                     // [2K]
+    float* lo = den + nrow;
+    float* hi = lo + a.K;
+    float* cS = hi + a.K;                       // [K]  G / (s+eps)^2 / (n+1)       (coefficient of sign(p - t))
+    float* cJ = cS + a.K;                       // [K]  -E / (s+eps) + cS * S       (extra term at j*)
+    unsigned int* js = reinterpret_cast<unsigned int*>(cJ + a.K);  // [K]
+    const int b = blockIdx.y;
+    if (threadIdx.x < nrow) {
+        const int arr = threadIdx.x / a.K, k = threadIdx.x - arr * a.K;
+        tt[threadIdx.x] = a.t[row_of(a, arr, b, k)];
+        den[threadIdx.x] = a.s[row_of(a, arr, b, k)] + 1e-6f;
+    }
+    if (threadIdx.x < a.K) {
+        const int k = threadIdx.x;
+        const double* r = a.racc + (static_cast<long long>(b) * a.K + k) * 3;
+        const double d = static_cast<double>(a.s[row_of(a, 0, b, k)]) + 1e-6;
+        const double n1 = static_cast<double>(a.count[row_of(a, 0, b, k)]) + 1.0;
+        const double cs = r[1] / (d * d) / n1;
+        cS[k] = static_cast<float>(cs);
+        cJ[k] = static_cast<float>(-r[0] / d + cs * r[2]);
+        js[k] = a.jstar[b * a.K + k];
+    }
+    __syncthreads();
+    const bool has_valid = setup_thresholds<MODE>(a, b, lo, hi);
+    const float scale = *w.gout / static_cast<float>(a.acc[1] + 1e-6);
+    const long long start = static_cast<long long>(blockIdx.x) * a.chunk;
+    const long long end = min(start + a.chunk, a.L);
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        const float p = a.pred[b * a.L + i], g = a.gt[b * a.L + i];
+        uint32_t bits = member_bits<MODE>(a, b, i, g, lo, hi, has_valid);
+        float gsum = 0.f;
+        if (bits) {
+            const float wgt = 1.0f / static_cast<float>(__popc(bits));
+            while (bits) {
+                const int k = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float dp = p - tt[k];
+                const float pa = dp / den[k], ga = (g - tt[a.K + k]) / den[a.K + k];
+                gsum += wgt * fsign(pa - ga) / den[k] - cS[k] * fsign(dp);
+                if (static_cast<unsigned int>(i) == js[k]) gsum += cJ[k];
+            }
+        }
+        w.grad[b * a.L + i] = gsum * scale;
+    }
+}
+
+__global__ void init_jstar_kernel(unsigned int* jstar, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) jstar[i] = 0xFFFFFFFFu;
+}
+
+template <int MODE>
+int run_backward(SelArgs& a, const BwdArgs& w, cudaStream_t st) {
+    DAD_TRY(run_select_lin<MODE>(a, 0, st));   // medians, scales, counts (the forward's statistics, recomputed)
+    const dim3 grid(static_cast<unsigned>(cdivl(a.L, a.chunk)), a.B);
+    DAD_CHECK_CUDA(cudaMemsetAsync(a.racc, 0, static_cast<size_t>(a.B) * a.K * 3 * 8, st));
+    init_jstar_kernel<<<cdiv(a.B * a.K, 128), 128, 0, st>>>(a.jstar, a.B * a.K);
+    const size_t sm_r = (static_cast<size_t>(4) * a.K + 2 * a.K + static_cast<size_t>(3) * a.K * 8) * 4;
+    if (a.K <= 8) bwd_reduce_kernel<MODE, 8><<<grid, THREADS, sm_r, st>>>(a);
+    else bwd_reduce_kernel<MODE, MAX_K><<<grid, THREADS, sm_r, st>>>(a);
+    const size_t sm_a = (static_cast<size_t>(4) * a.K + 2 * a.K + 3 * a.K) * 4;
+    bwd_apply_kernel<MODE><<<grid, THREADS, sm_a, st>>>(a, w);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int ssi_backward_common(int mode, const float* pred, const float* gt, const uint8_t* mask, const uint8_t* ctx, int K, int level,
+                        int B, long long L, const float* gout, float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st) {
+    DAD_REQUIRE(pred && gt && gout && grad_pred, "loss backward: null argument");
+    DAD_REQUIRE(B > 0 && L > 0 && L < (1LL << 32) - 1, "loss backward: bad size (B=%d, L=%lld)", B, L);
+    DAD_REQUIRE(K >= 1 && K <= MAX_K, "loss backward: K=%d contexts unsupported (max %d)", K, MAX_K);
+    SelArgs a{};
+    a.pred = pred; a.gt = gt; a.mask = mask; a.ctx = ctx;
+    a.B = B; a.K = K; a.level = level; a.narr = 2; a.L = L;
+    a.chunk = pick_chunk(L, B);
+    size_t zero_bytes = 0, zero_small = 0;
+    DAD_TRY(carve(a, ws, ws_bytes, &zero_bytes, &zero_small));
+    ProfScope prof(PROF_LOSS, static_cast<double>(B) * L * (12.0 + (mask ? 1 : 0) + (ctx ? K : 0)), st, 14);
+    DAD_CHECK_CUDA(cudaMemsetAsync(ws, 0, zero_small, st));
+    BwdArgs w{gout, grad_pred};
+    if (mode == MODE_MASK) return run_backward<MODE_MASK>(a, w, st);
+    if (mode == MODE_DR) return run_backward<MODE_DR>(a, w, st);
+    return run_backward<MODE_CTX>(a, w, st);
+}
+
+// ---------------------------------------------------------------- Sobel gradient loss backward
+// L = mean exp(-m), m = sqrt(gx^2 + gy^2 + 1e-6):  a = dL/dg = -exp(-m) * g / (m * N);  dL/dd = corr^T(ax, kx) + corr^T(ay, ky)
+__global__ void __launch_bounds__(THREADS) sobel_bwd_kernel(const float* d, int H, int W, const float* gout, double n_inv,
+                                                            float* grad) {
+    constexpr int TX = 32, TY = 8;
+    __shared__ float sd[TY + 4][TX + 4];
+    __shared__ float sax[TY + 2][TX + 2], say[TY + 2][TX + 2];
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const float* img = d + static_cast<long long>(b) * H * W;
+    for (int i = threadIdx.x; i < (TY + 4) * (TX + 4); i += THREADS) {
+        const int ly = i / (TX + 4), lx = i - ly * (TX + 4);
+        const int y = y0 + ly - 2, x = x0 + lx - 2;
+        sd[ly][lx] = (y >= 0 && y < H && x >= 0 && x < W) ? img[static_cast<long long>(y) * W + x] : 0.f;
+    }
+    __syncthreads();
+    const float c = -(*gout) * static_cast<float>(n_inv);
+    for (int i = threadIdx.x; i < (TY + 2) * (TX + 2); i += THREADS) {
+        const int ly = i / (TX + 2), lx = i - ly * (TX + 2);
+        const int y = y0 + ly - 1, x = x0 + lx - 1;
+        float ax = 0.f, ay = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < W) {   // gradient magnitude exists only at real pixels
+            const float (*r)[TX + 4] = reinterpret_cast<const float (*)[TX + 4]>(&sd[ly][lx]);  // window origin (y-1, x-1)
+            const float gx = (r[0][2] - r[0][0]) + 2.f * (r[1][2] - r[1][0]) + (r[2][2] - r[2][0]);
+            const float gy = (r[2][0] - r[0][0]) + 2.f * (r[2][1] - r[0][1]) + (r[2][2] - r[0][2]);
+            const float m = sqrtf(gx * gx + gy * gy + 1e-6f);
+            const float f = c * expf(-m) / m;
+            ax = f * gx;
+            ay = f * gy;
+        }
+        sax[ly][lx] = ax;
+        say[ly][lx] = ay;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x < W && y < H) {
+        // d gx(y', x') / d d(y, x) = kx[y - y' + 1][x - x' + 1]; sum over the 3 x 3 neighbours (y', x')
+        float gsum = 0.f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int u = -dy + 1, v = -dx + 1;                           // kernel tap seen from the neighbour
+                const float kx = (v == 2 ? 1.f : (v == 0 ? -1.f : 0.f)) * (u == 1 ? 2.f : 1.f);
+                const float ky = (u == 2 ? 1.f : (u == 0 ? -1.f : 0.f)) * (v == 1 ? 2.f : 1.f);
+                gsum += kx * sax[ly + 1 + dy][lx + 1 + dx] + ky * say[ly + 1 + dy][lx + 1 + dx];
+            }
+        grad[(static_cast<long long>(b) * H + y) * W + x] = gsum;
+    }
 }
 
 // ---------------------------------------------------------------- HDN-DR context export (bool [K,B,L])
@@ -1219,6 +1454,31 @@ int contexts_dr(int level, const float* gt, const uint8_t* mask, int B, long lon
     init_minmax_kernel<<<cdiv(B, 128), 128, 0, st>>>(a.minmax, B);
     minmax_kernel<<<grid, THREADS, 0, st>>>(gt, mask, L, a.chunk, a.minmax);
     contexts_dr_kernel<<<grid, THREADS, 0, st>>>(a, ctx_out);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int ssi_loss_bwd(const float* pred, const float* gt, const uint8_t* mask, int rows, long long L, const float* gout,
+                 float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return ssi_backward_common(MODE_MASK, pred, gt, mask, nullptr, 1, 0, rows, L, gout, grad_pred, ws, ws_bytes, st);
+}
+
+int hdn_loss_dr_bwd(int level, const float* pred, const float* gt, const uint8_t* mask, int B, long long L, const float* gout,
+                    float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st) {
+    DAD_REQUIRE(level >= 1 && level <= 4, "hdn_loss_dr_bwd: level=%d unsupported (1..4)", level);
+    return ssi_backward_common(MODE_DR, pred, gt, mask, nullptr, (1 << level) - 1, level, B, L, gout, grad_pred, ws, ws_bytes, st);
+}
+
+int hdn_loss_ctx_bwd(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, long long L, const float* gout,
+                     float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return ssi_backward_common(MODE_CTX, pred, gt, nullptr, ctx, K, 0, B, L, gout, grad_pred, ws, ws_bytes, st);
+}
+
+int grad_loss_bwd(const float* depth, int B, int H, int W, const float* gout, float* grad_depth, cudaStream_t st) {
+    DAD_REQUIRE(depth && gout && grad_depth && B > 0 && H > 0 && W > 0 && B <= 65535, "grad_loss_bwd: bad arguments");
+    ProfScope prof(PROF_LOSS, static_cast<double>(B) * H * W * 8, st);
+    const dim3 grid(cdiv(W, 32), cdiv(H, 8), B);
+    sobel_bwd_kernel<<<grid, THREADS, 0, st>>>(depth, H, W, gout, 1.0 / (static_cast<double>(B) * H * W), grad_depth);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

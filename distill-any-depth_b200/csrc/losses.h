@@ -17,6 +17,14 @@ int hdn_loss_ctx(const float* pred, const float* gt, const uint8_t* ctx, int K, 
                  double* partials, void* ws, size_t ws_bytes, cudaStream_t st);
 int contexts_dr(int level, const float* gt, const uint8_t* mask, int B, long long L, uint8_t* ctx_out, void* ws,
                 size_t ws_bytes, cudaStream_t st);
+// backward w.r.t. pred (gt detached); `gout` = device pointer to the upstream gradient of the scalar loss
+int ssi_loss_bwd(const float* pred, const float* gt, const uint8_t* mask, int rows, long long L, const float* gout,
+                 float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st);
+int hdn_loss_dr_bwd(int level, const float* pred, const float* gt, const uint8_t* mask, int B, long long L, const float* gout,
+                    float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st);
+int hdn_loss_ctx_bwd(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, long long L, const float* gout,
+                     float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st);
+int grad_loss_bwd(const float* depth, int B, int H, int W, const float* gout, float* grad_depth, cudaStream_t st);
 // quantile-bin (DP) and spatial-grid (DS) HDN contexts; the HDN loss over them goes through hdn_loss_ctx
 int contexts_dp(int level, const float* gt, const uint8_t* mask, int B, long long L, uint8_t* ctx_out, void* ws,
                 size_t ws_bytes, cudaStream_t st);

@@ -98,6 +98,93 @@ def _ssi(depth_preds, depth_gt, mask_valid, dense, want_partials=False):
     return (dense_out if dense else out), part
 
 
+# ------------------------------------------------------------------------------------------ autograd (8f N1, first slice)
+# The scalar SSI / HDN / gradient-preservation losses are differentiable w.r.t. the prediction, so they can sit in the
+# reference's training loop on top of any autograd student; the target map is treated as detached (it is the no_grad
+# teacher output there).  Backward kernels: csrc/losses.cu (bwd_reduce_kernel / bwd_apply_kernel / sobel_bwd_kernel).
+def _gout(g, device):
+    return g.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
+
+
+class _SSIFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, gt, mask):
+        out, _ = _ssi(pred.detach(), gt, mask, False)
+        ctx.save_for_backward(pred.detach(), gt.detach(), mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, gt, mask = ctx.saved_tensors
+        p, t = _f32(pred, "depth_preds"), _f32(gt, "depth_gt")
+        rows, L = _rows_L(p)
+        m = _mask_u8(mask, p)
+        grad = torch.empty_like(p)
+        ws = _workspace(p.device, rows, 1)
+        go = _gout(g, p.device)
+        _lib.check(_lib.load().dad_ssi_loss_bwd(_lib.ptr(p), _lib.ptr(t), _lib.ptr(m), rows, L, _lib.ptr(go), _lib.ptr(grad),
+                                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "SSILoss.backward")
+        return grad.reshape(pred.shape).to(pred.dtype), None, None
+
+
+class _HDNFn(torch.autograd.Function):
+    """mode 'dr': contexts from (level, gt, mask) on the fly; mode 'ctx': explicit bool [K,B,1,H,W] contexts."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, mode, level, mask_or_ctx):
+        ctx.mode, ctx.level = mode, level
+        if mode == "dr":
+            out = hdn_loss_dr(pred.detach(), gt, mask_or_ctx, level)
+        else:
+            out, _ = _hdn(pred.detach(), gt, mask_or_ctx)
+        ctx.save_for_backward(pred.detach(), gt.detach(), mask_or_ctx if mask_or_ctx is not None else torch.empty(0))
+        ctx.has_aux = mask_or_ctx is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, gt, aux = ctx.saved_tensors
+        aux = aux if ctx.has_aux else None
+        p, t = _f32(pred, "depth_preds"), _f32(gt, "depth_gt")
+        B, L = p.shape[0], p.shape[2] * p.shape[3]
+        grad = torch.empty_like(p)
+        go = _gout(g, p.device)
+        lib = _lib.load()
+        if ctx.mode == "dr":
+            m = _mask_u8(aux, t)
+            ws = _workspace(p.device, B, 2 ** ctx.level - 1)
+            _lib.check(lib.dad_hdn_loss_dr_bwd(ctx.level, _lib.ptr(p), _lib.ptr(t), _lib.ptr(m), B, L, _lib.ptr(go),
+                                               _lib.ptr(grad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "hdn backward")
+        else:
+            K = aux.shape[0]
+            c8 = _mask_u8(aux, aux)
+            ws = _workspace(p.device, B, K)
+            _lib.check(lib.dad_hdn_loss_bwd(_lib.ptr(p), _lib.ptr(t), _lib.ptr(c8), K, B, L, _lib.ptr(go), _lib.ptr(grad),
+                                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "hdn backward")
+        return grad.reshape(pred.shape).to(pred.dtype), None, None, None, None
+
+
+class _GradFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth):
+        ctx.save_for_backward(depth.detach())
+        return _grad(depth.detach())[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (depth,) = ctx.saved_tensors
+        d = _f32(depth, "depth")
+        grad = torch.empty_like(d)
+        go = _gout(g, d.device)
+        _lib.check(_lib.load().dad_grad_loss_bwd(_lib.ptr(d), d.shape[0], d.shape[2], d.shape[3], _lib.ptr(go),
+                                                 _lib.ptr(grad), _lib.stream_ptr()), "gradient_preservation_loss.backward")
+        return grad.to(depth.dtype)
+
+
+def _wants_grad(t):
+    return isinstance(t, torch.Tensor) and t.requires_grad and torch.is_grad_enabled()
+
+
 class SSILoss(nn.Module):
     """Scale-shift-invariant MAE (``:675-684``); ``window_size`` is stored and unused, as upstream."""
 
@@ -106,6 +193,10 @@ class SSILoss(nn.Module):
         self.window_size = window_size
 
     def forward(self, depth_preds, depth_gt, mask_valid, dense=False):
+        if _wants_grad(depth_preds):
+            if dense:
+                raise NotImplementedError("SSILoss(dense=True) has no backward here; the scalar loss and the HDN loss do")
+            return _SSIFn.apply(depth_preds, depth_gt, mask_valid)
         return _ssi(depth_preds, depth_gt, mask_valid, dense)[0]
 
 
@@ -159,12 +250,21 @@ def _hdn(depth_preds, depth_gt, mask_valid_list, want_partials=False):
 
 def compute_hdn_loss(ssi_loss, depth_preds, depth_gt, mask_valid_list):
     """``:686-707``.  ``ssi_loss`` is accepted for signature parity (the kernel *is* SSI-MAE)."""
+    if _wants_grad(depth_preds):
+        tag = getattr(mask_valid_list, "_dad_dr", None)
+        if tag is not None and tag[1] == depth_gt.data_ptr() and tag[2] == depth_gt._version \
+                and tag[3] == tuple(depth_gt.shape) \
+                and (tag[4] is None or tag[4] == (tag[5].data_ptr(), tag[5]._version)):
+            return _HDNFn.apply(depth_preds, depth_gt, "dr", tag[0], tag[5])
+        return _HDNFn.apply(depth_preds, depth_gt, "ctx", 0, mask_valid_list)
     return _hdn(depth_preds, depth_gt, mask_valid_list)[0]
 
 
 def hdn_loss_dr(depth_preds, depth_gt, mask_valid=None, level=3, want_partials=False):
     """Fused ``compute_hdn_loss(SSILoss(), p, g, get_contexts_dr(level, g, mask))`` (training call
     site ``:1547-1553``) without materialising the contexts."""
+    if _wants_grad(depth_preds) and not want_partials:
+        return _HDNFn.apply(depth_preds, depth_gt, "dr", level, mask_valid)
     p, g = _f32(depth_preds, "depth_preds"), _f32(depth_gt, "depth_gt")
     B, L = p.shape[0], p.shape[2] * p.shape[3]
     m = _mask_u8(mask_valid, g)
@@ -228,6 +328,8 @@ def _grad(depth, want_partials=False):
 
 def gradient_preservation_loss(depth):
     """``:430-446``."""
+    if _wants_grad(depth):
+        return _GradFn.apply(depth)
     return _grad(depth)[0]
 
 

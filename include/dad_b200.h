@@ -119,6 +119,20 @@ int dad_distill_loss(const float* student, const float* teacher, int strategy, i
                      float* out_scalar, double* partials, float* norm_student, float* norm_teacher, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ loss gradients (first slice)
+ * d loss / d pred of the scalar losses above, with the target map detached (it is the no_grad teacher output at the
+ * training call sites, tools/train_distillation.py:1512-1553).  `grad_out` is a DEVICE pointer to the upstream
+ * gradient of the scalar; the statistics (medians, scales) are recomputed, so no state is carried from the forward.
+ * The semantics are PyTorch autograd's on the reference code: d median / d p lives on the selected element (lowest
+ * index on ties), |x| has gradient 0 at 0, masked elements get 0.  Workspace as for the forward call. */
+int dad_ssi_loss_bwd(const float* pred, const float* gt, const uint8_t* mask, int rows, int64_t L, const float* grad_out,
+                     float* grad_pred, void* workspace, size_t workspace_bytes, void* stream);
+int dad_hdn_loss_dr_bwd(int level, const float* pred, const float* gt, const uint8_t* mask, int B, int64_t L,
+                        const float* grad_out, float* grad_pred, void* workspace, size_t workspace_bytes, void* stream);
+int dad_hdn_loss_bwd(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, int64_t L, const float* grad_out,
+                     float* grad_pred, void* workspace, size_t workspace_bytes, void* stream);
+int dad_grad_loss_bwd(const float* depth, int B, int H, int W, const float* grad_out, float* grad_depth, void* stream);
+
 /* ------------------------------------------------------------------ pre- / post-processing
  * DepthAnythingV2.image2tensor (depth_anything_v2/dpt.py:237-262; util/transform.py:109-148): uint8 HWC image
  * (device pointer, `pitch_bytes` per row; swap_rb = 1 for a BGR source) -> /255 -> cv2.resize(INTER_CUBIC) to

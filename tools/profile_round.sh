@@ -8,7 +8,7 @@ set -u
 TAG=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --graph 0"
 $CMD > $OUT/plain_$TAG.json 2> $OUT/plain_$TAG.err || { echo "plain bench failed"; tail -5 $OUT/plain_$TAG.err; exit 1; }
 cat $OUT/plain_$TAG.json
 # launch list: all launches (weight packing, 3+3 warm-ups, timed steps, profile pass)
@@ -17,7 +17,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 echo "launch list rc=$? rows=$(wc -l < $OUT/launches_$TAG.csv)"
 # full-set capture: SKIP launches = packing + first forwards; then one whole forward+loss (~240 launches).
 # DAD_NCU_SKIP can be tuned; the summary script keys on kernel names, not on positions.
-SKIP=${DAD_NCU_SKIP:-1500}
+SKIP=${DAD_NCU_SKIP:-1200}
 COUNT=${DAD_NCU_COUNT:-245}
 timeout 1500 ncu --set full --clock-control none -s $SKIP -c $COUNT -f -o /tmp/full_$TAG \
     $CMD > $OUT/ncu_full_$TAG.log 2>&1
