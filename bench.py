@@ -198,6 +198,7 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the ONE JSON line (NCCL logs to stdout)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
