@@ -36,6 +36,8 @@ PROTOTYPES = {
     "dad_hdn_loss_dr_bwd": (_i, [_i, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dad_hdn_loss_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dad_grad_loss_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "dad_feat_cos_loss_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "dad_distill_loss_bwd": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dad_preprocess_image": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dad_resize_depth": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "dad_minmax_normalize": (_i, [_vp, _i, _i64, _vp, _vp, _sz, _vp]),

@@ -44,6 +44,16 @@ int dad_hdn_loss_bwd(const float* pred, const float* gt, const uint8_t* ctx, int
     return dad::hdn_loss_ctx_bwd(pred, gt, ctx, K, B, L, grad_out, grad_pred, ws, wsb, ST(stream));
 }
 
+int dad_feat_cos_loss_bwd(const float* student, const float* teacher, int B, int N, int Ds, int Dt, const float* grad_out,
+                          float* grad_student, void* stream) {
+    return dad::feat_cos_loss_bwd(student, teacher, B, N, Ds, Dt, grad_out, grad_student, ST(stream));
+}
+
+int dad_distill_loss_bwd(const float* student, const float* teacher, int strategy, int num_segments, int B, int64_t L,
+                         const float* grad_out, float* grad_student, void* ws, size_t wsb, void* stream) {
+    return dad::distill_loss_bwd(student, teacher, strategy, num_segments, B, L, grad_out, grad_student, ws, wsb, ST(stream));
+}
+
 int dad_grad_loss_bwd(const float* depth, int B, int H, int W, const float* grad_out, float* grad_depth, void* stream) {
     return dad::grad_loss_bwd(depth, B, H, W, grad_out, grad_depth, ST(stream));
 }

@@ -65,6 +65,7 @@ struct SelArgs {
     uint32_t* cand;        // [R][CAP] keys of the candidates
     int NB, CAP;
     // backward (gradient w.r.t. pred; gt is the detached teacher map)
+    int mean_all;          // global_normalize: s = sum |x - t| / L instead of / (n + 1)
     double* racc;          // [B*K][3]  E = sum w*sgn, G = sum w*sgn*(p - t), S = sum sign(p - t) over the members of the row
     unsigned int* jstar;   // [B*K]     lowest member index holding the median value (where d median / d p lives)
 };
@@ -1015,7 +1016,7 @@ __global__ void __launch_bounds__(THREADS) bwd_apply_kernel(const SelArgs a, con
         const int k = threadIdx.x;
         const double* r = a.racc + (static_cast<long long>(b) * a.K + k) * 3;
         const double d = static_cast<double>(a.s[row_of(a, 0, b, k)]) + 1e-6;
-        const double n1 = static_cast<double>(a.count[row_of(a, 0, b, k)]) + 1.0;
+        const double n1 = a.mean_all ? static_cast<double>(a.L) : static_cast<double>(a.count[row_of(a, 0, b, k)]) + 1.0;
         const double cs = r[1] / (d * d) / n1;
         cS[k] = static_cast<float>(cs);
         cJ[k] = static_cast<float>(-r[0] / d + cs * r[2]);
@@ -1052,7 +1053,7 @@ __global__ void init_jstar_kernel(unsigned int* jstar, int n) {
 
 template <int MODE>
 int run_backward(SelArgs& a, const BwdArgs& w, cudaStream_t st) {
-    DAD_TRY(run_select_lin<MODE>(a, 0, st));   // medians, scales, counts (the forward's statistics, recomputed)
+    DAD_TRY(run_select_lin<MODE>(a, a.mean_all, st));   // medians, scales, counts (the forward's statistics, recomputed)
     const dim3 grid(static_cast<unsigned>(cdivl(a.L, a.chunk)), a.B);
     DAD_CHECK_CUDA(cudaMemsetAsync(a.racc, 0, static_cast<size_t>(a.B) * a.K * 3 * 8, st));
     init_jstar_kernel<<<cdiv(a.B * a.K, 128), 128, 0, st>>>(a.jstar, a.B * a.K);
@@ -1066,13 +1067,14 @@ int run_backward(SelArgs& a, const BwdArgs& w, cudaStream_t st) {
 }
 
 int ssi_backward_common(int mode, const float* pred, const float* gt, const uint8_t* mask, const uint8_t* ctx, int K, int level,
-                        int B, long long L, const float* gout, float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st) {
+                        int B, long long L, const float* gout, float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st,
+                        int mean_all = 0) {
     DAD_REQUIRE(pred && gt && gout && grad_pred, "loss backward: null argument");
     DAD_REQUIRE(B > 0 && L > 0 && L < (1LL << 32) - 1, "loss backward: bad size (B=%d, L=%lld)", B, L);
     DAD_REQUIRE(K >= 1 && K <= MAX_K, "loss backward: K=%d contexts unsupported (max %d)", K, MAX_K);
     SelArgs a{};
     a.pred = pred; a.gt = gt; a.mask = mask; a.ctx = ctx;
-    a.B = B; a.K = K; a.level = level; a.narr = 2; a.L = L;
+    a.B = B; a.K = K; a.level = level; a.narr = 2; a.L = L; a.mean_all = mean_all;
     a.chunk = pick_chunk(L, B);
     size_t zero_bytes = 0, zero_small = 0;
     DAD_TRY(carve(a, ws, ws_bytes, &zero_bytes, &zero_small));
@@ -1407,12 +1409,175 @@ __global__ void __launch_bounds__(THREADS) hyb_final_kernel(const HybArgs h) {
     (void)present;
 }
 
+// ---------------------------------------------------------------- backward: plain / hybrid-normalised L1, feature cosine
+__global__ void __launch_bounds__(THREADS) l1_bwd_kernel(const float* a, const float* b, long long n, const float* gout,
+                                                         float* grad) {
+    const float c = *gout / static_cast<float>(n);
+    for (long long i = static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * THREADS)
+        grad[i] = c * fsign(a[i] - b[i]);
+}
+
+// hybrid_normalize (:217-249) backward w.r.t. x[0]; x[1] is normalised by its own statistics and detached.
+//   ns_i = (d_i - mu_g) / (sigma_g + 1e-6) with g = the LAST segment containing i;  mu_g, sigma_g over ALL members of g
+//   e_i = sgn(ns_i - nt_i) / (B L);  A_g = sum_{g(i)=g} e_i;  Gq_g = sum_{g(i)=g} e_i (d_i - mu_g);  Sg_g = sum_{M_g} sign(d - mu_g)
+//   dL/dd_j = e_j / den_g(j) + sum_{g contains j} [ -A_g / (den_g cnt_g) - Gq_g / den_g^2 * (sign(d_j - mu_g) - Sg_g / cnt_g) / cnt_g ]
+struct HybBwd {
+    double* racc;        // [B][nseg][3]  A, Gq, Sg
+    const float* gout;
+    float* grad;
+};
+
+__device__ __forceinline__ void hyb_load_stats(const HybArgs& h, int b, float (*bnd)[MAX_SEG + 1], float (*mean)[MAX_SEG],
+                                               float (*den)[MAX_SEG], float (*cnt)[MAX_SEG]) {
+    if (threadIdx.x < 2) {
+        const int arr = threadIdx.x;
+        seg_bounds(key2f(h.minmax[(arr * h.B + b) * 2]), key2f(h.minmax[(arr * h.B + b) * 2 + 1]), h.nseg, bnd[arr]);
+        for (int s = 0; s < h.nseg; ++s) {
+            const long long o = (static_cast<long long>(arr) * h.B + b) * h.nseg + s;
+            const float c = static_cast<float>(h.segcnt[o]) + 1e-6f;
+            cnt[arr][s] = c;
+            mean[arr][s] = static_cast<float>(h.segsum[o]) / c;
+            den[arr][s] = static_cast<float>(h.segmad[o]) / c + 1e-6f;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(THREADS) hyb_bwd_reduce_kernel(const HybArgs h, const HybBwd w) {
+    const int b = blockIdx.y;
+    __shared__ float bnd[2][MAX_SEG + 1], mean[2][MAX_SEG], den[2][MAX_SEG], cnt[2][MAX_SEG];
+    __shared__ float red[3][MAX_SEG][8];
+    hyb_load_stats(h, b, bnd, mean, den, cnt);
+    float aA[MAX_SEG], aG[MAX_SEG], aS[MAX_SEG];
+#pragma unroll
+    for (int s = 0; s < MAX_SEG; ++s) { aA[s] = 0.f; aG[s] = 0.f; aS[s] = 0.f; }
+    const long long start = static_cast<long long>(blockIdx.x) * h.chunk;
+    const long long end = min(start + h.chunk, h.L);
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        const float d = h.x[0][static_cast<long long>(b) * h.L + i], t = h.x[1][static_cast<long long>(b) * h.L + i];
+        float ns = 0.f, nt = 0.f;
+        int gs = -1;
+        for (int s = 0; s < h.nseg; ++s) {
+            if (d >= bnd[0][s] && d <= bnd[0][s + 1]) { ns = (d - mean[0][s]) / den[0][s]; gs = s; }
+            if (t >= bnd[1][s] && t <= bnd[1][s + 1]) nt = (t - mean[1][s]) / den[1][s];
+        }
+        const float e = fsign(ns - nt);
+#pragma unroll
+        for (int s = 0; s < MAX_SEG; ++s) {
+            if (s < h.nseg && d >= bnd[0][s] && d <= bnd[0][s + 1]) {
+                aS[s] += fsign(d - mean[0][s]);
+                if (s == gs) { aA[s] += e; aG[s] += e * (d - mean[0][s]); }
+            }
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < MAX_SEG; ++s) {
+        if (s < h.nseg) {
+            float v0 = aA[s], v1 = aG[s], v2 = aS[s];
+            for (int o = 16; o; o >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            }
+            if (lane == 0) { red[0][s][warp] = v0; red[1][s][warp] = v1; red[2][s][warp] = v2; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * h.nseg) {
+        const int s = threadIdx.x / 3, q = threadIdx.x - 3 * s;
+        double v = 0.0;
+        for (int k = 0; k < 8; ++k) v += red[q][s][k];
+        if (v != 0.0) atomicAdd(&w.racc[(static_cast<long long>(b) * h.nseg + s) * 3 + q], v);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) hyb_bwd_apply_kernel(const HybArgs h, const HybBwd w) {
+    const int b = blockIdx.y;
+    __shared__ float bnd[2][MAX_SEG + 1], mean[2][MAX_SEG], den[2][MAX_SEG], cnt[2][MAX_SEG];
+    __shared__ float cA[MAX_SEG], cG[MAX_SEG], cS[MAX_SEG];
+    hyb_load_stats(h, b, bnd, mean, den, cnt);
+    if (threadIdx.x < h.nseg) {
+        const int s = threadIdx.x;
+        const double* r = w.racc + (static_cast<long long>(b) * h.nseg + s) * 3;
+        const double dn = den[0][s], c = cnt[0][s];
+        cA[s] = static_cast<float>(-r[0] / (dn * c));           // mean term, per member
+        cG[s] = static_cast<float>(r[1] / (dn * dn) / c);      // coefficient of (sign(d - mu) - Sg / cnt)
+        cS[s] = static_cast<float>(r[2] / c);
+    }
+    __syncthreads();
+    const float scale = *w.gout / (static_cast<float>(h.B) * static_cast<float>(h.L));
+    const long long start = static_cast<long long>(blockIdx.x) * h.chunk;
+    const long long end = min(start + h.chunk, h.L);
+    for (long long i = start + threadIdx.x; i < end; i += THREADS) {
+        const float d = h.x[0][static_cast<long long>(b) * h.L + i], t = h.x[1][static_cast<long long>(b) * h.L + i];
+        float ns = 0.f, nt = 0.f, gsum = 0.f;
+        int gs = -1;
+        for (int s = 0; s < h.nseg; ++s) {
+            if (d >= bnd[0][s] && d <= bnd[0][s + 1]) {
+                ns = (d - mean[0][s]) / den[0][s];
+                gs = s;
+                gsum += cA[s] - cG[s] * (fsign(d - mean[0][s]) - cS[s]);
+            }
+            if (t >= bnd[1][s] && t <= bnd[1][s + 1]) nt = (t - mean[1][s]) / den[1][s];
+        }
+        if (gs >= 0) gsum += fsign(ns - nt) / den[0][gs];
+        w.grad[static_cast<long long>(b) * h.L + i] = gsum * scale;
+    }
+}
+
+// feature cosine backward w.r.t. s:  d(1 - mean cos) / d a = -(1 / (B D)) * (v / n_b - cos * a / n_a) / n_a  per column
+__global__ void __launch_bounds__(THREADS) featcos_bwd_kernel(const float* s, const float* t, int N, int Ds, int Dt, int D, int B,
+                                                              const float* gout, float* grad) {
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int warp = threadIdx.x >> 5;
+    float st = 0.f, ss = 0.f, tt = 0.f;
+    int cs = 0, ct = 0;
+    if (c < D) {
+        cs = (Ds == D) ? c : min(static_cast<int>(floorf(c * (static_cast<float>(Ds) / D))), Ds - 1);
+        ct = (Dt == D) ? c : min(static_cast<int>(floorf(c * (static_cast<float>(Dt) / D))), Dt - 1);
+        const float* sp = s + static_cast<long long>(b) * N * Ds + cs;
+        const float* tp = t + static_cast<long long>(b) * N * Dt + ct;
+        for (int n = warp; n < N; n += 8) {
+            const float a = sp[static_cast<long long>(n) * Ds], v = tp[static_cast<long long>(n) * Dt];
+            st = fmaf(a, v, st); ss = fmaf(a, a, ss); tt = fmaf(v, v, tt);
+        }
+    }
+    __shared__ float red[3][8][32];
+    __shared__ float col[3][32];   // 1 / n_a, 1 / n_b, cos
+    red[0][warp][threadIdx.x & 31] = st; red[1][warp][threadIdx.x & 31] = ss; red[2][warp][threadIdx.x & 31] = tt;
+    __syncthreads();
+    if (warp == 0) {
+        float a = 0.f, q = 0.f, r = 0.f;
+        for (int w = 0; w < 8; ++w) { a += red[0][w][threadIdx.x]; q += red[1][w][threadIdx.x]; r += red[2][w][threadIdx.x]; }
+        const float na = sqrtf(q), nb = sqrtf(r);
+        const bool ok = na > 1e-12f && nb > 1e-12f;   // a zero column has no direction: its gradient is left at 0
+        col[0][threadIdx.x] = ok ? 1.0f / na : 0.f;
+        col[1][threadIdx.x] = ok ? 1.0f / nb : 0.f;
+        col[2][threadIdx.x] = ok ? a / (na * nb) : 0.f;
+    }
+    __syncthreads();
+    if (c < D) {
+        const float ia = col[0][threadIdx.x & 31], ib = col[1][threadIdx.x & 31], cosv = col[2][threadIdx.x & 31];
+        const float k = -(*gout) / (static_cast<float>(B) * static_cast<float>(D));
+        const float* sp = s + static_cast<long long>(b) * N * Ds + cs;
+        const float* tp = t + static_cast<long long>(b) * N * Dt + ct;
+        float* gp = grad + static_cast<long long>(b) * N * Ds + cs;
+        for (int n = warp; n < N; n += 8) {
+            const float a = sp[static_cast<long long>(n) * Ds], v = tp[static_cast<long long>(n) * Dt];
+            gp[static_cast<long long>(n) * Ds] = k * (v * ib - cosv * a * ia) * ia;
+        }
+    }
+}
+
 }  // namespace
 
 // ================================================================== public (internal C++) API
 size_t loss_workspace_bytes(int B, int K) {
     const size_t sel = select_ws_bytes(B, K < 1 ? 1 : K);
-    const size_t hyb = 4096 + static_cast<size_t>(B) * (2 * 2 * 4 + 3 * 2 * MAX_SEG * 8) + 1024;
+    const size_t hyb = 4096 + static_cast<size_t>(B) * (2 * 2 * 4 + 3 * 2 * MAX_SEG * 8 + 3 * MAX_SEG * 8) + 2048;
     return (sel > hyb ? sel : hyb) + 1024;
 }
 
@@ -1595,6 +1760,63 @@ int distill_loss(const float* student, const float* teacher, int strategy, int n
     hyb_final_kernel<<<grid, THREADS, 0, st>>>(h);
     set_den_kernel<<<1, 1, 0, st>>>(h.acc, static_cast<double>(B) * L);
     ratio_kernel<<<1, 1, 0, st>>>(h.acc, 0.0, out_scalar, partials, 0);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int feat_cos_loss_bwd(const float* s, const float* t, int B, int N, int Ds, int Dt, const float* gout, float* grad_s,
+                      cudaStream_t st) {
+    DAD_REQUIRE(s && t && gout && grad_s && B > 0 && N > 0 && Ds > 0 && Dt > 0, "feat_cos_loss_bwd: bad arguments");
+    const int D = Ds < Dt ? Ds : Dt;
+    ProfScope prof(PROF_LOSS, 4.0 * B * N * (2.0 * Ds + Dt), st, 2);
+    if (Ds != D) DAD_CHECK_CUDA(cudaMemsetAsync(grad_s, 0, static_cast<size_t>(B) * N * Ds * 4, st));  // unselected channels
+    featcos_bwd_kernel<<<dim3(cdiv(D, 32), B), THREADS, 0, st>>>(s, t, N, Ds, Dt, D, B, gout, grad_s);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int distill_loss_bwd(const float* student, const float* teacher, int strategy, int num_segments, int B, long long L,
+                     const float* gout, float* grad_student, void* ws, size_t ws_bytes, cudaStream_t st) {
+    DAD_REQUIRE(student && teacher && gout && grad_student && B > 0 && L > 0, "distill_loss_bwd: bad arguments");
+    DAD_REQUIRE(ws && ws_bytes >= loss_workspace_bytes(B, 1), "distill_loss_bwd: workspace too small");
+    if (strategy == 1)  // global: the SSI machinery with mean-over-all statistics and a plain mean
+        return ssi_backward_common(MODE_MASK, student, teacher, nullptr, nullptr, 1, 0, B, L, gout, grad_student, ws, ws_bytes,
+                                   st, 1);
+    if (strategy == 0) {
+        const long long n = static_cast<long long>(B) * L;
+        const int grid = static_cast<int>(cdivl(n, THREADS * 8) < 148 * 8 ? cdivl(n, THREADS * 8) : 148 * 8);
+        ProfScope prof(PROF_LOSS, static_cast<double>(n) * 12, st);
+        l1_bwd_kernel<<<grid < 1 ? 1 : grid, THREADS, 0, st>>>(student, teacher, n, gout, grad_student);
+        DAD_CHECK_LAUNCH();
+        return DAD_OK;
+    }
+    DAD_REQUIRE(strategy == 2, "distill_loss_bwd: unknown strategy %d", strategy);
+    DAD_REQUIRE(num_segments >= 1 && num_segments <= MAX_SEG, "distill_loss_bwd: num_segments=%d unsupported (1..%d)",
+                num_segments, MAX_SEG);
+    ProfScope prof(PROF_LOSS, static_cast<double>(B) * L * 12, st, 8);
+    HybArgs h{};
+    h.x[0] = student; h.x[1] = teacher; h.B = B; h.nseg = num_segments; h.L = L;
+    h.chunk = pick_chunk(L, B);
+    Carver c(ws, ws_bytes);
+    h.acc = c.take<double>(2);
+    h.segsum = c.take<double>(static_cast<size_t>(2) * B * num_segments);
+    h.segcnt = c.take<double>(static_cast<size_t>(2) * B * num_segments);
+    h.segmad = c.take<double>(static_cast<size_t>(2) * B * num_segments);
+    HybBwd w{};
+    w.racc = c.take<double>(static_cast<size_t>(B) * num_segments * 3);
+    w.gout = gout; w.grad = grad_student;
+    const size_t zero_bytes = c.used;
+    h.minmax = c.take<uint32_t>(static_cast<size_t>(4) * B);
+    DAD_CHECK_CUDA(cudaMemsetAsync(ws, 0, zero_bytes, st));
+    const dim3 grid(static_cast<unsigned>(cdivl(L, h.chunk)), B);
+    init_minmax_kernel<<<cdiv(2 * B, 128), 128, 0, st>>>(h.minmax, 2 * B);
+    minmax_kernel<<<grid, THREADS, 0, st>>>(student, nullptr, L, h.chunk, h.minmax);
+    minmax_kernel<<<grid, THREADS, 0, st>>>(teacher, nullptr, L, h.chunk, h.minmax + 2 * B);
+    const dim3 grid2(grid.x, B, 2);
+    hyb_stats_kernel<<<grid2, THREADS, 0, st>>>(h, 0);
+    hyb_stats_kernel<<<grid2, THREADS, 0, st>>>(h, 1);
+    hyb_bwd_reduce_kernel<<<grid, THREADS, 0, st>>>(h, w);
+    hyb_bwd_apply_kernel<<<grid, THREADS, 0, st>>>(h, w);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

@@ -24,6 +24,10 @@ int hdn_loss_dr_bwd(int level, const float* pred, const float* gt, const uint8_t
                     float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st);
 int hdn_loss_ctx_bwd(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, long long L, const float* gout,
                      float* grad_pred, void* ws, size_t ws_bytes, cudaStream_t st);
+int feat_cos_loss_bwd(const float* s, const float* t, int B, int N, int Ds, int Dt, const float* gout, float* grad_s,
+                      cudaStream_t st);
+int distill_loss_bwd(const float* student, const float* teacher, int strategy, int num_segments, int B, long long L,
+                     const float* gout, float* grad_student, void* ws, size_t ws_bytes, cudaStream_t st);
 int grad_loss_bwd(const float* depth, int B, int H, int W, const float* gout, float* grad_depth, cudaStream_t st);
 // quantile-bin (DP) and spatial-grid (DS) HDN contexts; the HDN loss over them goes through hdn_loss_ctx
 int contexts_dp(int level, const float* gt, const uint8_t* mask, int B, long long L, uint8_t* ctx_out, void* ws,

@@ -181,6 +181,55 @@ class _GradFn(torch.autograd.Function):
         return grad.to(depth.dtype)
 
 
+class _FeatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student, teacher):
+        ctx.save_for_backward(student.detach(), teacher.detach())
+        return _feat(student.detach(), teacher.detach())[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        student, teacher = ctx.saved_tensors
+        s, t = _f32(student, "student_features"), _f32(teacher, "teacher_features")
+        grad = torch.empty_like(s)
+        go = _gout(g, s.device)
+        _lib.check(_lib.load().dad_feat_cos_loss_bwd(_lib.ptr(s), _lib.ptr(t), s.shape[0], s.shape[1], s.shape[2], t.shape[2],
+                                                     _lib.ptr(go), _lib.ptr(grad), _lib.stream_ptr()),
+                   "feature_distillation_loss.backward")
+        return grad.to(student.dtype), None
+
+
+class _DistillFn(torch.autograd.Function):
+    """distillation_loss(a, b, strategy): gradients w.r.t. whichever of the two maps require them (the local-global term
+    of the training loop feeds two student outputs, tools/train_distillation.py:1524-1529)."""
+
+    @staticmethod
+    def forward(ctx, a, b, strategy, num_segments):
+        ctx.strategy, ctx.nseg = strategy, num_segments
+        ctx.save_for_backward(a.detach(), b.detach())
+        return _distill(a.detach(), b.detach(), strategy, num_segments)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        fa, fb = _f32(a, "student_depth"), _f32(b, "teacher_depth")
+        B, L = fa.shape[0], fa.shape[1] * fa.shape[2] * fa.shape[3]
+        go = _gout(g, fa.device)
+        lib = _lib.load()
+        out = []
+        for need, x, y in ((ctx.needs_input_grad[0], fa, fb), (ctx.needs_input_grad[1], fb, fa)):
+            if not need:
+                out.append(None)
+                continue
+            grad = torch.empty_like(x)
+            ws = _workspace(x.device, B, 1)
+            _lib.check(lib.dad_distill_loss_bwd(_lib.ptr(x), _lib.ptr(y), _STRATEGY[ctx.strategy], int(ctx.nseg), B, L,
+                                                _lib.ptr(go), _lib.ptr(grad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       "distillation_loss.backward")
+            out.append(grad)
+        return out[0], out[1], None, None
+
+
 def _wants_grad(t):
     return isinstance(t, torch.Tensor) and t.requires_grad and torch.is_grad_enabled()
 
@@ -356,12 +405,16 @@ def feature_distillation_loss(student_features, teacher_features, device=None):
         for s, t in zip(student_features, teacher_features):
             if s is None or t is None:
                 continue
-            v = _feat(s, t)[0]
+            v = _FeatFn.apply(s, t) if _wants_grad(s) else _feat(s, t)[0]
             tot = v if tot is None else tot + v
             n += 1
         if tot is None:
             return torch.tensor(0.0, device=device)
         return tot / max(n, 1)
+    if _wants_grad(student_features):
+        if student_features.dim() != 3 or teacher_features.dim() != 3 or student_features.shape[1] != teacher_features.shape[1]:
+            raise NotImplementedError("feature_distillation_loss: only [B,N,Ds] vs [B,N,Dt] tensors are on the hot path")
+        return _FeatFn.apply(student_features, teacher_features)
     return _feat(student_features, teacher_features)[0]
 
 
@@ -385,6 +438,10 @@ def _distill(student_depth, teacher_depth, norm_strategy, num_segments=4, want_p
 
 def distillation_loss(student_depth, teacher_depth, norm_strategy, num_segments=4):
     """``:271-282``."""
+    if _wants_grad(student_depth) or _wants_grad(teacher_depth):
+        if norm_strategy not in _STRATEGY:
+            raise ValueError(f"Unknown normalization strategy: {norm_strategy}")
+        return _DistillFn.apply(student_depth, teacher_depth, norm_strategy, num_segments)
     return _distill(student_depth, teacher_depth, norm_strategy, num_segments)[0]
 
 

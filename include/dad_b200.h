@@ -132,6 +132,13 @@ int dad_hdn_loss_dr_bwd(int level, const float* pred, const float* gt, const uin
 int dad_hdn_loss_bwd(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, int64_t L, const float* grad_out,
                      float* grad_pred, void* workspace, size_t workspace_bytes, void* stream);
 int dad_grad_loss_bwd(const float* depth, int B, int H, int W, const float* grad_out, float* grad_depth, void* stream);
+/* feature_distillation_loss: gradient w.r.t. the student features [B,N,Ds] (channels dropped by the nearest resize get 0) */
+int dad_feat_cos_loss_bwd(const float* student, const float* teacher, int B, int N, int Ds, int Dt, const float* grad_out,
+                          float* grad_student, void* stream);
+/* distillation_loss: gradient w.r.t. its FIRST map (swap the arguments for the second: the loss is symmetric).
+ * Segment / median statistics of both maps are recomputed; each map is normalised by its own statistics. */
+int dad_distill_loss_bwd(const float* student, const float* teacher, int strategy, int num_segments, int B, int64_t L,
+                         const float* grad_out, float* grad_student, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ pre- / post-processing
  * DepthAnythingV2.image2tensor (depth_anything_v2/dpt.py:237-262; util/transform.py:109-148): uint8 HWC image

@@ -87,7 +87,7 @@ def test_losses_backpropagate_into_an_autograd_student():
             loss = 0.8 * d.compute_hdn_loss(ssi, depth, t, d.get_contexts_dr(3, t, None)) \
                 + 0.2 * d.gradient_preservation_loss(depth) + ssi(depth, t, torch.ones_like(t, dtype=torch.bool))
         loss.backward()
-        grads.append((float(loss), w.grad.detach().cpu()))
+        grads.append((loss.item(), w.grad.detach().cpu()))
     assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[0][0])
     _close(grads[1][1], grads[0][1], tol=1e-3)
 
@@ -106,3 +106,51 @@ def test_gradients_at_baseline_size_obey_the_invariances():
         mass = (g.abs() * P.abs()).flatten(1).sum(1) + 1e-12
         assert ((g.flatten(1).sum(1)).abs() <= 1e-3 * g.abs().flatten(1).sum(1) + 1e-9).all(), name
         assert (((g * P).flatten(1).sum(1)).abs() <= 1e-3 * mass).all(), name
+
+
+@pytest.mark.parametrize("strategy", ["none", "global", "hybrid", "local"])
+def test_distillation_loss_gradients_match_autograd(strategy):
+    d = dad()
+    a, b, _ = synthetic.make_depth_pair(3, 40, 56, seed=11)
+    a = a * 3 + 0.2
+    for which in ("first", "both"):
+        ac, bc = a.clone().requires_grad_(True), b.clone().requires_grad_(which == "both")
+        (2.0 * oracle.distillation_loss(ac, bc, strategy)).backward()
+        ag, bg = a.clone().cuda().requires_grad_(True), b.clone().cuda().requires_grad_(which == "both")
+        (2.0 * d.distillation_loss(ag, bg, strategy)).backward()
+        _close(ag.grad.cpu(), ac.grad)
+        if which == "both":
+            _close(bg.grad.cpu(), bc.grad)
+
+
+@pytest.mark.parametrize("Ds,Dt", [(96, 128), (128, 96), (64, 64)])
+def test_feature_distillation_loss_gradient_matches_autograd(Ds, Dt):
+    d = dad()
+    s, t = synthetic.make_features(2, 49, Ds, seed=5), synthetic.make_features(2, 49, Dt, seed=6)
+    sc = s.clone().requires_grad_(True)
+    oracle.feature_distillation_loss(sc, t).backward()
+    sg = s.clone().cuda().requires_grad_(True)
+    d.feature_distillation_loss(sg, t.cuda()).backward()
+    _close(sg.grad.cpu(), sc.grad, tol=1e-4)
+
+
+def test_training_loss_of_the_reference_loop_backpropagates():
+    """The five-term batch loss of tools/train_distillation.py:1517-1566 (hybrid SC / LG + feature + gradient + HDN) on
+    leaf tensors standing in for the student outputs: gradients equal autograd on the oracle."""
+    d = dad()
+    sd, td, _ = synthetic.make_depth_pair(2, 56, 56, seed=21)
+    sg_, _, _ = synthetic.make_depth_pair(2, 56, 56, seed=22)
+    sf, tf = synthetic.make_features(2, 16, 96, seed=23), synthetic.make_features(2, 16, 128, seed=24)
+    res = []
+    for dev, L in (("cpu", oracle), ("cuda", d)):
+        a, a2, f = (x.clone().to(dev).requires_grad_(True) for x in (sd, sg_, sf))
+        t, tfeat = td.to(dev), tf.to(dev)
+        ssi = L.SSILoss()
+        loss = 0.5 * L.distillation_loss(a, t, "hybrid") + 0.5 * L.distillation_loss(a2, a, "hybrid") \
+            + 1.0 * L.feature_distillation_loss(f, tfeat) + 0.2 * L.gradient_preservation_loss(a) \
+            + 0.8 * L.compute_hdn_loss(ssi, a, t, L.get_contexts_dr(3, t, None))
+        loss.backward()
+        res.append((loss.item(), a.grad.cpu(), a2.grad.cpu(), f.grad.cpu()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[0][0])
+    for i in (1, 2, 3):
+        _close(res[1][i], res[0][i])
