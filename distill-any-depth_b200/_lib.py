@@ -26,6 +26,10 @@ PROTOTYPES = {
     "dad_forward_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
     "dad_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "dad_model_debug_capture": (_i, [_vp, _c.c_char_p, _vp, _i64]),
+    "dad_model_set_grad": (_i, [_vp, _c.c_char_p, _vp, _i64]),
+    "dad_train_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
+    "dad_forward_train": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "dad_backward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "dad_loss_workspace_bytes": (_sz, [_i, _i]),
     "dad_masked_shift_and_scale": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dad_ssi_loss": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),

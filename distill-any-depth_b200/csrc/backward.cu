@@ -1,0 +1,640 @@
+// Training-backward kernels of the fp32 verification engine.  The reference obtains these
+// gradients from PyTorch autograd over depth_anything_v2/dpt.py:150-225 / dinov2.py:212-321 / util/blocks.py:29-148
+// (tools/train_distillation.py:1556-1575); here each adjoint is written out: one strided FFMA GEMM covers every
+// data-gradient / weight-gradient contraction (including the implicit-im2col weight gradient of the convolutions),
+// the rest are HBM-bound row / pixel kernels.  Parameter gradients ACCUMULATE (atomicAdd) into caller-owned buffers.
+#include <algorithm>
+
+#include "backward.h"
+
+namespace dad {
+
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__global__ void __launch_bounds__(256) sgemm_kernel(const SGemm g, int ksplit, int kchunk) {
+    __shared__ float sA[TK][TM + 4];
+    __shared__ float sB[TK][TN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int z = blockIdx.z / ksplit, ks = blockIdx.z - z * ksplit;
+    const int z1 = z / g.nb2, z2 = z - z1 * g.nb2;
+    const float* A = g.A + z1 * g.a1 + z2 * g.a2;
+    const float* B = g.B + z1 * g.b1 + z2 * g.b2;
+    float* C = g.C + z1 * g.c1 + z2 * g.c2;
+    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+    const int kbeg = ks * kchunk;
+    const int kend = min(g.K, kbeg + kchunk);
+
+    // loader maps: consecutive threads walk the contiguous axis of each operand
+    const bool a_kfast = g.sak == 1;
+    const int a_m = a_kfast ? (tid >> 2) : (tid & 63);
+    const int a_k = a_kfast ? (tid & 3) * 4 : (tid >> 6) * 4;
+    const bool b_kfast = !g.conv_taps && g.sbk == 1;
+    const int b_n = b_kfast ? (tid >> 2) : (tid & 63);
+    const int b_k = b_kfast ? (tid & 3) * 4 : (tid >> 6) * 4;
+    const int am = m0 + a_m, bn = n0 + b_n;
+    int cc = 0, cdy = 0, cdx = 0;
+    if (g.conv_taps) {
+        const int tap = bn / g.convC;
+        cc = bn - tap * g.convC;
+        if (g.conv_taps == 9) { cdy = tap / 3 - 1; cdx = tap - (tap / 3) * 3 - 1; }
+    }
+    const int hw = g.convHo * g.convWo;
+
+    float acc[4][4] = {};
+    for (int k0 = kbeg; k0 < kend; k0 += TK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = k0 + a_k + i;
+            sA[a_k + i][a_m] = (am < g.M && k < kend) ? A[am * g.sam + k * g.sak] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = k0 + b_k + i;
+            float v = 0.f;
+            if (bn < g.N && k < kend) {
+                if (!g.conv_taps) {
+                    v = B[k * g.sbk + bn * g.sbn];
+                } else {
+                    const int b = k / hw;
+                    const int r = k - b * hw;
+                    const int oy = r / g.convWo, ox = r - oy * g.convWo;
+                    const int y = oy * g.conv_stride + cdy, x = ox * g.conv_stride + cdx;
+                    if (y >= 0 && y < g.convH && x >= 0 && x < g.convW)
+                        v = B[((static_cast<long long>(b) * g.convH + y) * g.convW + x) * g.convC + cc];
+                }
+            }
+            sB[b_k + i][b_n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            long long idx;
+            if (g.cmap == 0) {
+                idx = m * g.scm + n * g.scn;
+            } else if (g.cmap == 1) {
+                const int tap = n / g.convC, c = n - tap * g.convC;
+                idx = (static_cast<long long>(m) * g.convC + c) * g.conv_taps + tap;
+            } else {
+                const int t = m / g.ct_CoP, co = m - t * g.ct_CoP;
+                if (co >= g.ct_Co) continue;
+                idx = (static_cast<long long>(n) * g.ct_Co + co) * g.ct_kk + t;
+            }
+            const float v = g.alpha * acc[i][j];
+            if (!g.accumulate) C[idx] = v;
+            else if (ksplit > 1) atomicAdd(C + idx, v);
+            else C[idx] += v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- column sums (bias / LayerScale gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* X, long long ldx, const float* Y, long long ldy, long long rows,
+                                                     int N, float* out, const float* scale, float* scaled_out) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + cx;
+    float s = 0.f;
+    if (n < N) {
+        const float sc = scale ? scale[n] : 1.f;
+        for (long long r = static_cast<long long>(blockIdx.y) * 8 + ry; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
+            const float x = X[r * ldx + n];
+            s += Y ? x * Y[r * ldy + n] : x;
+            if (scaled_out) scaled_out[r * ldx + n] = x * sc;
+        }
+    }
+    red[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && n < N && out) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][cx];
+        atomicAdd(out + n, t);
+    }
+}
+
+// ---------------------------------------------------------------- LayerNorm backward
+template <int VPT>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* x, const float* w, const float* dy, float* dx, float* dw,
+                                                     float* db, long long rows, int D, int out_period, int in_period,
+                                                     int in_offset, float eps) {
+    __shared__ float sw[2048];
+    __shared__ float sb[2048];
+    for (int i = threadIdx.x; i < D; i += 256) { sw[i] = 0.f; sb[i] = 0.f; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long gw = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const long long nw = static_cast<long long>(gridDim.x) * 8;
+    float4 wv[VPT], aw[VPT], ab[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        const int idx = lane + j * 32;
+        wv[j] = (idx * 4 < D) ? reinterpret_cast<const float4*>(w)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        aw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long long r = gw; r < rows; r += nw) {
+        const long long ir = (r / out_period) * in_period + in_offset + r % out_period;
+        const float4* src = reinterpret_cast<const float4*>(x + ir * D);
+        const float4* gsrc = reinterpret_cast<const float4*>(dy + r * D);
+        float4 v[VPT], gq[VPT];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int idx = lane + j * 32;
+            if (idx * 4 < D) {
+                v[j] = src[idx];
+                gq[j] = gsrc[idx];
+                sum += v[j].x + v[j].y + v[j].z + v[j].w;
+            } else {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                gq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / D;
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int idx = lane + j * 32;
+            if (idx * 4 < D) {
+                const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+                var += a * a + b * b + c * c + d * d;
+            }
+        }
+        for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        const float rstd = rsqrtf(var / D + eps);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int idx = lane + j * 32;
+            if (idx * 4 < D) {
+                // v <- xhat; accumulate dw / db; gq <- dy * w
+                v[j].x = (v[j].x - mean) * rstd; v[j].y = (v[j].y - mean) * rstd;
+                v[j].z = (v[j].z - mean) * rstd; v[j].w = (v[j].w - mean) * rstd;
+                aw[j].x += gq[j].x * v[j].x; aw[j].y += gq[j].y * v[j].y; aw[j].z += gq[j].z * v[j].z; aw[j].w += gq[j].w * v[j].w;
+                ab[j].x += gq[j].x; ab[j].y += gq[j].y; ab[j].z += gq[j].z; ab[j].w += gq[j].w;
+                gq[j].x *= wv[j].x; gq[j].y *= wv[j].y; gq[j].z *= wv[j].z; gq[j].w *= wv[j].w;
+                s1 += gq[j].x + gq[j].y + gq[j].z + gq[j].w;
+                s2 += gq[j].x * v[j].x + gq[j].y * v[j].y + gq[j].z * v[j].z + gq[j].w * v[j].w;
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        const float m1 = s1 / D, m2 = s2 / D;
+        float4* dst = reinterpret_cast<float4*>(dx + ir * D);
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int idx = lane + j * 32;
+            if (idx * 4 < D) {
+                float4 o = dst[idx];
+                o.x += rstd * (gq[j].x - m1 - v[j].x * m2);
+                o.y += rstd * (gq[j].y - m1 - v[j].y * m2);
+                o.z += rstd * (gq[j].z - m1 - v[j].z * m2);
+                o.w += rstd * (gq[j].w - m1 - v[j].w * m2);
+                dst[idx] = o;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        const int idx = lane + j * 32;
+        if (idx * 4 < D) {
+            atomicAdd(&sw[idx * 4 + 0], aw[j].x); atomicAdd(&sw[idx * 4 + 1], aw[j].y);
+            atomicAdd(&sw[idx * 4 + 2], aw[j].z); atomicAdd(&sw[idx * 4 + 3], aw[j].w);
+            atomicAdd(&sb[idx * 4 + 0], ab[j].x); atomicAdd(&sb[idx * 4 + 1], ab[j].y);
+            atomicAdd(&sb[idx * 4 + 2], ab[j].z); atomicAdd(&sb[idx * 4 + 3], ab[j].w);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += 256) {
+        if (dw) atomicAdd(dw + i, sw[i]);
+        if (db) atomicAdd(db + i, sb[i]);
+    }
+}
+
+// ---------------------------------------------------------------- small elementwise kernels
+__global__ void __launch_bounds__(256) ls_residual_kernel(const float* xold, const float* y, const float* gamma, float* xnew,
+                                                          long long n, int D) {
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i < n) xnew[i] = xold[i] + y[i] * gamma[i % D];   // x + ls(y), ls(y) = y * gamma (layer_scale.py:27-28)
+}
+
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* pre, float* out, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i < n) { const float x = pre[i]; out[i] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+}
+
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* pre, const float* dout, float* dpre, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i < n) {
+        const float x = pre[i];
+        const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+        const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+        dpre[i] = dout[i] * (cdf + x * pdf);
+    }
+}
+
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* g, const float* y, const float* add, float* out, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i < n) out[i] = (add ? add[i] : 0.f) + (y[i] > 0.f ? g[i] : 0.f);
+}
+
+__global__ void __launch_bounds__(256) add_kernel(float* dst, const float* src, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
+// ---------------------------------------------------------------- attention probabilities
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long rows, int T) {
+    const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float* row = S + r * T;
+    float m = -INFINITY;
+    for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = 0.f;
+    for (int j = lane; j < T; j += 32) { const float e = expf(row[j] - m); row[j] = e; l += e; }
+    for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float inv = 1.f / l;
+    for (int j = lane; j < T; j += 32) row[j] *= inv;
+}
+
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* P, float* dP, long long rows, int T) {
+    const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* p = P + r * T;
+    float* d = dP + r * T;
+    float s = 0.f;
+    for (int j = lane; j < T; j += 32) s = fmaf(p[j], d[j], s);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int j = lane; j < T; j += 32) d[j] = p[j] * (d[j] - s);
+}
+
+// ---------------------------------------------------------------- bilinear adjoint (align_corners=True)
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* gout, float* gin, int B, int Hi, int Wi, int Ho, int Wo,
+                                                           int C, float sh, float sw) {
+    const int cv = C / 4;
+    const long long total = static_cast<long long>(B) * Ho * Wo * cv;
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % cv);
+    long long p = i / cv;
+    const int ox = static_cast<int>(p % Wo);
+    p /= Wo;
+    const int oy = static_cast<int>(p % Ho);
+    const int b = static_cast<int>(p / Ho);
+    const float fy = sh * oy, fx = sw * ox;   // index maths of bilinear_kernel (ATen area_pixel_compute_source_index)
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float ly = fy - y0, hy = 1.f - ly, lx = fx - x0, hx = 1.f - lx;
+    const float4 g = *reinterpret_cast<const float4*>(gout + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C + c * 4);
+    float* base = gin + static_cast<long long>(b) * Hi * Wi * C + c * 4;
+    const float wq[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+    const long long off[4] = {(static_cast<long long>(y0) * Wi + x0) * C, (static_cast<long long>(y0) * Wi + x1) * C,
+                              (static_cast<long long>(y1) * Wi + x0) * C, (static_cast<long long>(y1) * Wi + x1) * C};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float* d = base + off[q];
+        atomicAdd(d + 0, wq[q] * g.x); atomicAdd(d + 1, wq[q] * g.y);
+        atomicAdd(d + 2, wq[q] * g.z); atomicAdd(d + 3, wq[q] * g.w);
+    }
+}
+
+// ---------------------------------------------------------------- output head adjoint
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* gdepth, const float* depth, const float* t32, const float* w2,
+                                                       float* dt32, float* dw2, float* db2, long long P) {
+    __shared__ float sacc[33];
+    if (threadIdx.x < 33) sacc[threadIdx.x] = 0.f;
+    __syncthreads();
+    float wv[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) wv[c] = w2[c];
+    float aw[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) aw[c] = 0.f;
+    float abias = 0.f;
+    for (long long p = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; p < P; p += static_cast<long long>(gridDim.x) * 256) {
+        const float g = depth[p] > 0.f ? gdepth[p] : 0.f;   // relu(relu(z)): one mask
+        abias += g;
+        const float4* src = reinterpret_cast<const float4*>(t32 + p * 32);
+        float4* dst = reinterpret_cast<float4*>(dt32 + p * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = src[j];
+            aw[4 * j] += g * t.x; aw[4 * j + 1] += g * t.y; aw[4 * j + 2] += g * t.z; aw[4 * j + 3] += g * t.w;
+            dst[j] = make_float4(t.x > 0.f ? g * wv[4 * j] : 0.f, t.y > 0.f ? g * wv[4 * j + 1] : 0.f,
+                                 t.z > 0.f ? g * wv[4 * j + 2] : 0.f, t.w > 0.f ? g * wv[4 * j + 3] : 0.f);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        float v = aw[c];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[c], v);
+    }
+    for (int o = 16; o; o >>= 1) abias += __shfl_xor_sync(0xffffffffu, abias, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[32], abias);
+    __syncthreads();
+    if (threadIdx.x < 32 && dw2) atomicAdd(dw2 + threadIdx.x, sacc[threadIdx.x]);
+    if (threadIdx.x == 32 && db2) atomicAdd(db2, sacc[32]);
+}
+
+// ---------------------------------------------------------------- ConvTranspose / strided-conv helpers
+__global__ void __launch_bounds__(256) convT_gather_kernel(const float* dout, float* G, int B, int H, int W, int k, int Co,
+                                                           int CoP) {
+    const long long total = static_cast<long long>(B) * H * W * k * k * CoP;
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int co = static_cast<int>(i % CoP);
+    long long q = i / CoP;
+    const int t = static_cast<int>(q % (k * k));
+    q /= (k * k);
+    const int x = static_cast<int>(q % W);
+    q /= W;
+    const int y = static_cast<int>(q % H);
+    const int b = static_cast<int>(q / H);
+    const int ky = t / k, kx = t - ky * k;
+    float v = 0.f;
+    if (co < Co) v = dout[((static_cast<long long>(b) * (k * H) + k * y + ky) * (k * W) + k * x + kx) * Co + co];
+    G[i] = v;
+}
+
+__global__ void __launch_bounds__(256) col2im_s2_kernel(const float* dcol, float* din, int B, int H, int W, int C, int Cp, int Ho,
+                                                        int Wo) {
+    const long long total = static_cast<long long>(B) * H * W * C;
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % C);
+    long long q = i / C;
+    const int x = static_cast<int>(q % W);
+    q /= W;
+    const int y = static_cast<int>(q % H);
+    const int b = static_cast<int>(q / H);
+    float s = 0.f;
+    for (int dy = 0; dy < 3; ++dy) {
+        const int ty = y + 1 - dy;
+        if (ty < 0 || (ty & 1)) continue;
+        const int oy = ty >> 1;
+        if (oy >= Ho) continue;
+        for (int dx = 0; dx < 3; ++dx) {
+            const int tx = x + 1 - dx;
+            if (tx < 0 || (tx & 1)) continue;
+            const int ox = tx >> 1;
+            if (ox >= Wo) continue;
+            s += dcol[((static_cast<long long>(b) * Ho + oy) * Wo + ox) * 9 * Cp + (dy * 3 + dx) * Cp + c];
+        }
+    }
+    din[i] = s;
+}
+
+__global__ void __launch_bounds__(256) pack_conv_dgrad_kernel(const float* w, float* out, int Co, int Ci, int taps, int CoP) {
+    const long long total = static_cast<long long>(Ci) * taps * CoP;
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int co = static_cast<int>(i % CoP);
+    const int t = static_cast<int>((i / CoP) % taps);
+    const int ci = static_cast<int>(i / (static_cast<long long>(CoP) * taps));
+    out[i] = co < Co ? w[(static_cast<long long>(co) * Ci + ci) * taps + (taps - 1 - t)] : 0.f;
+}
+
+__global__ void __launch_bounds__(256) batch_sum_rows_kernel(const float* G, float* dtab, int B, int T, int D) {
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= static_cast<long long>(T) * D) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += G[static_cast<long long>(b) * T * D + i];
+    dtab[i] = s;
+}
+
+// adjoint of pos_table_kernel (elementwise.cu): same bicubic taps, scattered
+__device__ __forceinline__ float bcubic1(float x) { const float A = -0.75f; return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float bcubic2(float x) { const float A = -0.75f; return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+__global__ void __launch_bounds__(256) pos_table_bwd_kernel(const float* dtab, float* dpos, float* dcls, float* dpbias, int D, int S,
+                                                            int oh, int ow, int identity, float inv_sy, float inv_sx) {
+    const int t = blockIdx.x;
+    for (int d = threadIdx.x; d < D; d += 256) {
+        const float g = dtab[static_cast<long long>(t) * D + d];
+        if (t == 0) {
+            if (dcls) atomicAdd(dcls + d, g);
+            if (dpos) atomicAdd(dpos + d, g);
+            continue;
+        }
+        if (dpbias) atomicAdd(dpbias + d, g);
+        if (!dpos) continue;
+        const int p = t - 1;
+        if (identity) {
+            atomicAdd(dpos + static_cast<long long>(1 + p) * D + d, g);
+        } else {
+            const int oy = p / ow, ox = p - oy * ow;
+            const float fy = inv_sy * (oy + 0.5f) - 0.5f, fx = inv_sx * (ox + 0.5f) - 0.5f;
+            const int iy = static_cast<int>(floorf(fy)), ix = static_cast<int>(floorf(fx));
+            const float ty = fy - iy, tx = fx - ix;
+            const float wy[4] = {bcubic2(ty + 1.f), bcubic1(ty), bcubic1(1.f - ty), bcubic2(2.f - ty)};
+            const float wx[4] = {bcubic2(tx + 1.f), bcubic1(tx), bcubic1(1.f - tx), bcubic2(2.f - tx)};
+            for (int i = 0; i < 4; ++i) {
+                const int yy = min(max(iy - 1 + i, 0), S - 1);
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = min(max(ix - 1 + j, 0), S - 1);
+                    atomicAdd(dpos + static_cast<long long>(1 + yy * S + xx) * D + d, wy[i] * wx[j] * g);
+                }
+            }
+        }
+    }
+}
+
+inline unsigned blocks_for(long long n) { return static_cast<unsigned>(cdivl(n, 256)); }
+
+}  // namespace
+
+int sgemm(const SGemm& g, cudaStream_t st) {
+    DAD_REQUIRE(g.A && g.B && g.C && g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "sgemm: bad operands");
+    if (g.conv_taps) {
+        DAD_REQUIRE((g.conv_taps == 1 || g.conv_taps == 9) && g.convC > 0 && g.N == g.conv_taps * g.convC && g.convHo > 0 &&
+                        g.convWo > 0 && g.K % (g.convHo * g.convWo) == 0,
+                    "sgemm: bad implicit-conv operand");
+    }
+    const int batch = g.nb1 * g.nb2;
+    const long long tiles = static_cast<long long>(cdiv(g.M, TM)) * cdiv(g.N, TN) * batch;
+    int ksplit = 1, kchunk = cdiv(g.K, TK) * TK;
+    if (g.accumulate && g.K >= 4096 && tiles < 2LL * num_sms()) {
+        ksplit = static_cast<int>(std::min<long long>(cdiv(g.K, 2048), cdivl(4LL * num_sms(), tiles)));
+        kchunk = cdiv(cdiv(g.K, ksplit), TK) * TK;
+        ksplit = cdiv(g.K, kchunk);
+    }
+    DAD_REQUIRE(static_cast<long long>(batch) * ksplit <= 65535 && cdiv(g.N, TN) <= 65535, "sgemm: grid too large");
+    const dim3 grid(cdiv(g.M, TM), cdiv(g.N, TN), batch * ksplit);
+    ProfScope prof(PROF_GEMM_SIMT, 2.0 * g.M * g.N * static_cast<double>(g.K) * batch, st);
+    sgemm_kernel<<<grid, 256, 0, st>>>(g, ksplit, kchunk);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int colsum(const float* X, long long ldx, const float* Y, long long ldy, long long rows, int N, float* out, const float* scale,
+           float* scaled_out, cudaStream_t st) {
+    DAD_REQUIRE(X && rows > 0 && N > 0 && (out || scaled_out), "colsum: bad arguments");
+    const dim3 grid(cdiv(N, 32), static_cast<unsigned>(std::min<long long>(cdivl(rows, 64), 1024)));
+    ProfScope prof(PROF_ELEM, static_cast<double>(rows) * N * 4 * (1 + (Y ? 1 : 0) + (scaled_out ? 1 : 0)), st);
+    colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, rows, N, out, scale, scaled_out);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, long long rows, int D,
+                  int out_period, int in_period, int in_offset, float eps, cudaStream_t st) {
+    DAD_REQUIRE(x && w && dy && dx && D % 4 == 0 && D <= 2048, "layernorm_bwd: bad arguments (D=%d)", D);
+    const unsigned grid = static_cast<unsigned>(std::min<long long>(cdivl(rows, 8), 4LL * num_sms()));
+    ProfScope prof(PROF_LN, static_cast<double>(rows) * D * 16, st);
+    const int vpt = cdiv(D, 128);
+#define LNB(V) ln_bwd_kernel<V><<<grid, 256, 0, st>>>(x, w, dy, dx, dw, db, rows, D, out_period, in_period, in_offset, eps)
+    if (vpt <= 3) LNB(3);
+    else if (vpt <= 6) LNB(6);
+    else if (vpt <= 8) LNB(8);
+    else LNB(16);
+#undef LNB
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int ls_residual(const float* xold, const float* y, const float* gamma, float* xnew, long long rows, int D, cudaStream_t st) {
+    const long long n = rows * D;
+    ProfScope prof(PROF_ELEM, static_cast<double>(n) * 12, st);
+    ls_residual_kernel<<<blocks_for(n), 256, 0, st>>>(xold, y, gamma, xnew, n, D);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int gelu_fwd(const float* pre, float* out, long long n, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(n) * 8, st);
+    gelu_fwd_kernel<<<blocks_for(n), 256, 0, st>>>(pre, out, n);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int gelu_bwd(const float* pre, const float* dout, float* dpre, long long n, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(n) * 12, st);
+    gelu_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(pre, dout, dpre, n);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int relu_bwd(const float* g, const float* y, const float* add, float* out, long long n, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(n) * (add ? 16 : 12), st);
+    relu_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(g, y, add, out, n);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int add_inplace(float* dst, const float* src, long long n, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(n) * 12, st);
+    add_kernel<<<blocks_for(n), 256, 0, st>>>(dst, src, n);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int softmax_rows(float* S, long long rows, int T, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(rows) * T * 8, st);
+    softmax_rows_kernel<<<blocks_for(rows * 32), 256, 0, st>>>(S, rows, T);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int softmax_bwd_rows(const float* P, float* dP, long long rows, int T, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(rows) * T * 12, st);
+    softmax_bwd_rows_kernel<<<blocks_for(rows * 32), 256, 0, st>>>(P, dP, rows, T);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int bilinear_bwd(const float* gout, float* gin, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st) {
+    DAD_REQUIRE(C % 4 == 0, "bilinear_bwd: C=%d must be a multiple of 4", C);
+    const float sh = Ho > 1 ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.f;
+    const float sw = Wo > 1 ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.f;
+    const long long total = static_cast<long long>(B) * Ho * Wo * (C / 4);
+    ProfScope prof(PROF_ELEM, static_cast<double>(B) * C * 4 * (static_cast<double>(Hi) * Wi + static_cast<double>(Ho) * Wo), st);
+    bilinear_bwd_kernel<<<blocks_for(total), 256, 0, st>>>(gout, gin, B, Hi, Wi, Ho, Wo, C, sh, sw);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int head_bwd(const float* gdepth, const float* depth, const float* t32, const float* w2, float* dt32, float* dw2, float* db2,
+             long long P, cudaStream_t st) {
+    const unsigned grid = static_cast<unsigned>(std::min<long long>(cdivl(P, 256), 8LL * num_sms()));
+    ProfScope prof(PROF_ELEM, static_cast<double>(P) * (8 + 256), st);
+    head_bwd_kernel<<<grid, 256, 0, st>>>(gdepth, depth, t32, w2, dt32, dw2, db2, P);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int convT_gather(const float* dout, float* G, int B, int H, int W, int k, int Co, int CoP, cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * H * W * k * k * CoP;
+    ProfScope prof(PROF_ELEM, static_cast<double>(total) * 8, st);
+    convT_gather_kernel<<<blocks_for(total), 256, 0, st>>>(dout, G, B, H, W, k, Co, CoP);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int col2im_s2(const float* dcol, float* din, int B, int H, int W, int C, int Cp, cudaStream_t st) {
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long total = static_cast<long long>(B) * H * W * C;
+    ProfScope prof(PROF_ELEM, static_cast<double>(total) * 4 + static_cast<double>(B) * Ho * Wo * 9 * Cp * 4, st);
+    col2im_s2_kernel<<<blocks_for(total), 256, 0, st>>>(dcol, din, B, H, W, C, Cp, Ho, Wo);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int pack_conv_dgrad(const float* w, float* out, int Co, int Ci, int taps, int CoP, cudaStream_t st) {
+    const long long total = static_cast<long long>(Ci) * taps * CoP;
+    ProfScope prof(PROF_ELEM, static_cast<double>(total) * 8, st);
+    pack_conv_dgrad_kernel<<<blocks_for(total), 256, 0, st>>>(w, out, Co, Ci, taps, CoP);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int batch_sum_rows(const float* G, float* dtab, int B, int T, int D, cudaStream_t st) {
+    const long long n = static_cast<long long>(T) * D;
+    ProfScope prof(PROF_ELEM, static_cast<double>(n) * 4 * (B + 1), st);
+    batch_sum_rows_kernel<<<blocks_for(n), 256, 0, st>>>(G, dtab, B, T, D);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int pos_table_bwd(const float* dtab, float* dpos, float* dcls, float* dpbias, int D, int H, int W, cudaStream_t st) {
+    const int S = 37;
+    const int ph = H / 14, pw = W / 14;
+    const int identity = (ph * pw == S * S && H == W) ? 1 : 0;
+    const double sfy = (static_cast<double>(ph) + 0.1) / S, sfx = (static_cast<double>(pw) + 0.1) / S;
+    ProfScope prof(PROF_ELEM, static_cast<double>(1 + ph * pw) * D * 8, st);
+    pos_table_bwd_kernel<<<1 + ph * pw, 256, 0, st>>>(dtab, dpos, dcls, dpbias, D, S, ph, pw, identity,
+                                                      static_cast<float>(1.0 / sfy), static_cast<float>(1.0 / sfx));
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+}  // namespace dad

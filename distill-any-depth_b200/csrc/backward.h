@@ -1,0 +1,64 @@
+// Internal interface of the training-backward kernels (gradient of the student forward,
+// reference tools/train_distillation.py:1556-1575 = autograd over depth_anything_v2/dpt.py:150-225).
+// fp32 verification engine: every kernel is plain FFMA fp32 on row-major / NHWC fp32 tensors.
+#pragma once
+#include "common.h"
+
+namespace dad {
+
+// Batched, fully strided GEMM   C[z][m, n] (+)= alpha * sum_k A[z][m, k] * B[z][k, n]
+// element (m, k) of A at A + za + m*sam + k*sak (likewise B, C); batch z = z1 * nb2 + z2 with offsets
+// z1 * x1 + z2 * x2 per operand.  Optionally B is an IMPLICIT operand (the im2col view of an NHWC tensor) and the
+// C index goes through a weight-layout map, which turns the kernel into the weight-gradient pass of a convolution.
+struct SGemm {
+    const float* A = nullptr;
+    const float* B = nullptr;
+    float* C = nullptr;
+    int M = 0, N = 0, K = 0;
+    long long sam = 0, sak = 0, sbk = 0, sbn = 0, scm = 0, scn = 0;
+    int nb1 = 1, nb2 = 1;
+    long long a1 = 0, a2 = 0, b1 = 0, b2 = 0, c1 = 0, c2 = 0;
+    float alpha = 1.f;
+    int accumulate = 0;  // 1: C += result (the K loop may then be split over CTAs, atomicAdd)
+    // implicit B: k = output pixel (b, oy, ox) of a 3x3 (pad 1) or 1x1 window with `conv_stride`, n = tap * convC + c
+    //             -> B = In[b, oy*stride + dy - 1, ox*stride + dx - 1, c] (0 outside); In is NHWC [*, convH, convW, convC]
+    int conv_taps = 0, convC = 0, convH = 0, convW = 0, convHo = 0, convWo = 0, conv_stride = 1;
+    // C index map: 0 strided; 1 conv weight [Co][Ci][taps]: m = co, n = tap*convC + c -> (m*convC + c)*taps + tap;
+    //              2 ConvTranspose weight [Ci][Co][kk]: m = t*ct_CoP + co, n = ci -> (n*ct_Co + co)*ct_kk + t (co < ct_Co)
+    int cmap = 0, ct_CoP = 0, ct_Co = 0, ct_kk = 0;
+};
+int sgemm(const SGemm& g, cudaStream_t st);
+
+// out[n] += sum_r X[r*ldx + n] * (Y ? Y[r*ldy + n] : 1);  if `scaled_out`: scaled_out[r*ldx + n] = X[r*ldx + n] * scale[n]
+int colsum(const float* X, long long ldx, const float* Y, long long ldy, long long rows, int N, float* out,
+           const float* scale, float* scaled_out, cudaStream_t st);
+// LayerNorm backward, row mapping as layernorm(): dy row r <-> x row ir.  dx[ir] += ..., dw += ..., db += ...
+int layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, long long rows, int D,
+                  int out_period, int in_period, int in_offset, float eps, cudaStream_t st);
+// xnew = xold + gamma * y   (LayerScale + residual of the training forward)
+int ls_residual(const float* xold, const float* y, const float* gamma, float* xnew, long long rows, int D, cudaStream_t st);
+int gelu_fwd(const float* pre, float* out, long long n, cudaStream_t st);
+int gelu_bwd(const float* pre, const float* dout, float* dpre, long long n, cudaStream_t st);
+// out = (add ? add : 0) + g * (y > 0)
+int relu_bwd(const float* g, const float* y, const float* add, float* out, long long n, cudaStream_t st);
+int add_inplace(float* dst, const float* src, long long n, cudaStream_t st);
+// row-wise softmax of S [rows, T] in place; and dS = P * (dP - sum_j P*dP) in place of dP
+int softmax_rows(float* S, long long rows, int T, cudaStream_t st);
+int softmax_bwd_rows(const float* P, float* dP, long long rows, int T, cudaStream_t st);
+// adjoint of bilinear_nhwc (align_corners=True): gin [B,Hi,Wi,C] must be zero-filled by the caller
+int bilinear_bwd(const float* gout, float* gin, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st);
+// output head: depth = relu(dot(t32, w2) + b2), t32 = relu(conv + b) saved.  dt32 [P,32]; dw2 [32] / db2 [1] accumulate
+int head_bwd(const float* gdepth, const float* depth, const float* t32, const float* w2, float* dt32, float* dw2,
+             float* db2, long long P, cudaStream_t st);
+// ConvTranspose k=s: G[(b,y,x), t*CoP + co] = dOut[b, k*y+ky, k*x+kx, co] (0 for co >= Co)
+int convT_gather(const float* dout, float* G, int B, int H, int W, int k, int Co, int CoP, cudaStream_t st);
+// stride-2 3x3 conv: din[b,y,x,c] = sum over taps of dcol[(b,oy,ox), tap*Cp + c] with y = 2*oy+dy-1, x = 2*ox+dx-1
+int col2im_s2(const float* dcol, float* din, int B, int H, int W, int C, int Cp, cudaStream_t st);
+// dgrad weights of a stride-1 conv: w [Co][Ci][taps] -> out [Ci][taps][CoP], out[ci][t][co] = w[co][ci][taps-1-t]
+int pack_conv_dgrad(const float* w, float* out, int Co, int Ci, int taps, int CoP, cudaStream_t st);
+// dtab[t, d] = sum_b G[(b*T + t), d]
+int batch_sum_rows(const float* G, float* dtab, int B, int T, int D, cudaStream_t st);
+// gradients of pos_table(): cls_token, pos_embed (bicubic adjoint), patch-embed bias; all accumulate (any may be null)
+int pos_table_bwd(const float* dtab, float* dpos, float* dcls, float* dpbias, int D, int H, int W, cudaStream_t st);
+
+}  // namespace dad

@@ -13,6 +13,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "backward.h"
 #include "elementwise.h"
 #include "gemm.h"
 
@@ -72,6 +73,7 @@ public:
     float* bqkv_scaled = nullptr;                       // [depth][3D] qkv bias with q part * 64^-0.5
     std::map<std::pair<int, int>, float*> pos_tables;   // (H, W) -> [1 + ph*pw, D]
     std::unordered_map<std::string, std::pair<float*, long long>> captures;
+    std::unordered_map<std::string, std::pair<float*, long long>> grads;   // caller-owned fp32 gradient accumulators
 
     // packed matrices
     Mat patch;
@@ -483,6 +485,53 @@ public:
     }
 };
 
+#include "train.inl"
+
+namespace {
+
+int train_checks(Model& m, int B, int H, int W, int mode) {
+    if (mode != 1)
+        return set_error(DAD_ERR_UNSUPPORTED, "the training forward / backward runs in the fp32 engine only (mode 1, precision='fp32')");
+    DAD_REQUIRE(B > 0 && H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0,
+                "input must be [B,3,H,W] with H, W positive multiples of 14 (got B=%d H=%d W=%d)", B, H, W);
+    DAD_REQUIRE(static_cast<long long>(B) * (1 + (H / 14) * (W / 14)) < (1LL << 31) / 4, "batch too large for 32-bit row indices");
+    (void)m;
+    return DAD_OK;
+}
+
+int train_workspace(Model& m, int B, int H, int W, int mode, size_t* need) {
+    DAD_TRY(train_checks(m, B, H, W, mode));
+    size_t peak = 0;
+    {
+        Bump ar(nullptr, 0, true);
+        Tape t;
+        Trainer tr(m, B, H, W, true, nullptr);
+        DAD_TRY(tr.forward(nullptr, nullptr, nullptr, ar, t));
+        peak = ar.peak;
+    }
+    {
+        Bump ar(nullptr, 0, true);
+        Tape t;
+        Trainer tr(m, B, H, W, true, nullptr);
+        DAD_TRY(tr.backward(nullptr, nullptr, ar, t));
+        if (ar.peak > peak) peak = ar.peak;
+    }
+    *need = peak + 1024;
+    return DAD_OK;
+}
+
+int train_ready(Model& m, int B, int H, int W, int mode, void* ws, size_t ws_bytes) {
+    size_t need = 0;
+    DAD_TRY(train_workspace(m, B, H, W, mode, &need));
+    if (ws_bytes < need) return set_error(DAD_ERR_WORKSPACE, "training workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    const auto pit = m.pos_tables.find(std::make_pair(H, W));
+    DAD_REQUIRE(m.packed[1] && pit != m.pos_tables.end() && pit->second != nullptr, "call dad_model_prepare(mode, H, W) first");
+    DAD_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
+    return DAD_OK;
+}
+
+}  // namespace
+
 }  // namespace dad
 
 // ====================================================================== C ABI (model part)
@@ -520,6 +569,49 @@ int dad_model_debug_capture(dad_model* m, const char* name, float* dst, int64_t 
     if (!dst) mm->captures.erase(name);
     else mm->captures[name] = {dst, numel};
     return DAD_OK;
+}
+
+int dad_model_set_grad(dad_model* m, const char* name, float* dev_ptr, int64_t numel) {
+    if (!m || !name) return dad::set_error(DAD_ERR_INVALID, "null argument");
+    auto* mm = reinterpret_cast<dad::Model*>(m);
+    if (!dev_ptr) { mm->grads.erase(name); return DAD_OK; }
+    auto it = mm->master.find(name);
+    if (it == mm->master.end()) return dad::set_error(DAD_ERR_INVALID, "set_grad: unknown parameter %s", name);
+    if (it->second.second != numel)
+        return dad::set_error(DAD_ERR_INVALID, "set_grad: %s has %lld elements, gradient buffer has %lld", name,
+                              it->second.second, static_cast<long long>(numel));
+    mm->grads[name] = {dev_ptr, numel};
+    return DAD_OK;
+}
+
+size_t dad_train_workspace_bytes(dad_model* m, int B, int H, int W, int mode) {
+    if (!m) return 0;
+    size_t need = 0;
+    if (dad::train_workspace(*reinterpret_cast<dad::Model*>(m), B, H, W, mode, &need) != DAD_OK) return 0;
+    return need;
+}
+
+int dad_forward_train(dad_model* m, const float* x, int B, int H, int W, int mode, float* depth_out, float* feat_out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    if (!m) return dad::set_error(DAD_ERR_INVALID, "null model");
+    if (!x || !depth_out) return dad::set_error(DAD_ERR_INVALID, "forward_train: null input/output");
+    auto& mm = *reinterpret_cast<dad::Model*>(m);
+    DAD_TRY(dad::train_ready(mm, B, H, W, mode, workspace, workspace_bytes));
+    dad::Bump ar(workspace, workspace_bytes, false);
+    dad::Tape t;
+    dad::Trainer tr(mm, B, H, W, false, reinterpret_cast<cudaStream_t>(stream));
+    return tr.forward(x, depth_out, feat_out, ar, t);
+}
+
+int dad_backward(dad_model* m, int B, int H, int W, int mode, const float* grad_depth, const float* grad_feat, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    if (!m) return dad::set_error(DAD_ERR_INVALID, "null model");
+    auto& mm = *reinterpret_cast<dad::Model*>(m);
+    DAD_TRY(dad::train_ready(mm, B, H, W, mode, workspace, workspace_bytes));
+    dad::Bump ar(workspace, workspace_bytes, false);
+    dad::Tape t;
+    dad::Trainer tr(mm, B, H, W, false, reinterpret_cast<cudaStream_t>(stream));
+    return tr.backward(grad_depth, grad_feat, ar, t);
 }
 
 size_t dad_forward_workspace_bytes(dad_model* m, int B, int H, int W, int mode) {

@@ -6,7 +6,10 @@ working) and the ``(depth, features)`` tuple return, but ``forward`` runs the wh
 ``libdad_b200.so`` (tcgen05 GEMM / implicit-GEMM conv engine, fused attention, fused output head).
 The sub-modules below are parameter containers only; none of them has a forward of its own.
 
-Forward-only: outputs are detached (training backward is out of scope).
+Training: in ``precision = "fp32"`` the outputs are differentiable with respect to the
+parameters - ``loss.backward()`` (tools/train_distillation.py:1556-1575) runs ``dad_backward`` behind a
+``torch.autograd.Function`` and fills ``.grad`` of every parameter the reference's autograd would reach.  In
+``precision = "bf16"`` the forward is inference-only and its outputs are detached.
 """
 import ctypes
 import math
@@ -193,6 +196,10 @@ class _NativeDepthModel(nn.Module):
         except Exception:
             pass
 
+    # parameters the reference forward never touches (autograd leaves their .grad = None): the mask token
+    # (del_mask_token / masks=None, dinov2.py:212-218) and refinenet4's first RCU (no skip input, blocks.py:137-141)
+    _UNUSED = ("mask_token", "refinenet4.resConfUnit1.")
+
     def _run(self, x, captures=None):
         if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
             raise ValueError("expected an image batch of shape [B, 3, H, W]")
@@ -205,6 +212,68 @@ class _NativeDepthModel(nn.Module):
         if self.precision not in _MODES:
             raise ValueError("precision must be 'bf16' or 'fp32'")
         mode = _MODES[self.precision]
+        if mode == 1 and captures is None and torch.is_grad_enabled():
+            live = [(k, p) for k, p in self.named_parameters()
+                    if p.requires_grad and not any(u in k for u in self._UNUSED)]
+            if live:
+                return _TrainForward.apply(self, x, tuple(k for k, _ in live), *[p for _, p in live])
+        return self._run_native(x, mode, captures)
+
+    def _train_begin(self, x):
+        """dad_forward_train: same outputs as the inference forward, activations kept on a tape tensor."""
+        B, _, H, W = x.shape
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            self._ensure_handle()
+            self._sync_weights(x.device)
+            st = _lib.stream_ptr()
+            if (1, H, W) not in self._prepared:
+                _lib.check(lib.dad_model_prepare(self._handle, 1, H, W, st), "dad_model_prepare")
+                self._prepared.add((1, H, W))
+            need = int(lib.dad_train_workspace_bytes(self._handle, B, H, W, 1))
+            if need == 0:
+                _lib.check(-1, "dad_train_workspace_bytes")
+            tape = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
+            off = (-tape.data_ptr()) % 1024
+            xin = x.detach()
+            if xin.dtype != torch.float32 or not xin.is_contiguous():
+                xin = xin.float().contiguous()
+            D = ENCODERS[self._desc["encoder"]]["embed_dim"]
+            depth = torch.empty(B, 1, H, W, dtype=torch.float32, device=x.device)
+            feat = torch.empty(B, (H // 14) * (W // 14), D, dtype=torch.float32, device=x.device)
+            _lib.check(lib.dad_forward_train(self._handle, _lib.ptr(xin), B, H, W, 1, _lib.ptr(depth), _lib.ptr(feat),
+                                             ctypes.c_void_p(tape.data_ptr() + off), tape.numel() - off, st),
+                       "dad_forward_train")
+        return depth, feat, tape
+
+    def _train_backward(self, tape, shape, names, gdepth, gfeat):
+        """dad_backward: returns one fp32 gradient tensor per name (accumulated by the library from zero)."""
+        B, H, W = shape
+        lib = _lib.load()
+        own = dict(self.named_parameters())
+        grads = []
+        with torch.cuda.device(tape.device):
+            st = _lib.stream_ptr()
+            registered = []
+            try:
+                for k in names:
+                    g = torch.zeros(own[k].shape, dtype=torch.float32, device=tape.device)
+                    grads.append(g)
+                    sk = self._student_key(k).encode()
+                    _lib.check(lib.dad_model_set_grad(self._handle, sk, _lib.ptr(g), g.numel()), f"set_grad({k})")
+                    registered.append(sk)
+                off = (-tape.data_ptr()) % 1024
+                gd = gdepth.float().contiguous()
+                gf = None if gfeat is None else gfeat.float().contiguous()
+                _lib.check(lib.dad_backward(self._handle, B, H, W, 1, _lib.ptr(gd), _lib.ptr(gf),
+                                            ctypes.c_void_p(tape.data_ptr() + off), tape.numel() - off, st), "dad_backward")
+            finally:
+                for sk in registered:
+                    lib.dad_model_set_grad(self._handle, sk, None, 0)
+        return grads
+
+    def _run_native(self, x, mode, captures=None):
+        B, _, H, W = x.shape
         lib = _lib.load()
         with torch.cuda.device(x.device):
             self._ensure_handle()
@@ -237,6 +306,31 @@ class _NativeDepthModel(nn.Module):
                 for name in (captures or {}):
                     lib.dad_model_debug_capture(self._handle, name.encode(), None, 0)
         return depth, feat
+
+
+class _TrainForward(torch.autograd.Function):
+    """Differentiable fp32 forward: forward = dad_forward_train (tape), backward = dad_backward."""
+
+    @staticmethod
+    def forward(ctx, model, x, names, *params):
+        depth, feat, tape = model._train_begin(x)
+        ctx.model, ctx.tape, ctx.names = model, tape, names
+        ctx.shape = (x.shape[0], x.shape[2], x.shape[3])
+        ctx.versions = tuple(p._version for p in params)
+        ctx.params = params
+        return depth, feat
+
+    @staticmethod
+    def backward(ctx, gdepth, gfeat):
+        if ctx.tape is None:
+            raise RuntimeError("backward through the native forward a second time: the activation tape was freed")
+        if tuple(p._version for p in ctx.params) != ctx.versions:
+            raise RuntimeError("a parameter was modified between the native forward and its backward")
+        if gdepth is None:
+            gdepth = torch.zeros(ctx.shape[0], 1, ctx.shape[1], ctx.shape[2], device=ctx.tape.device)
+        grads = ctx.model._train_backward(ctx.tape, ctx.shape, ctx.names, gdepth, gfeat)
+        ctx.tape = None
+        return (None, None, None, *grads)
 
 
 class DepthAnythingV2(_NativeDepthModel):

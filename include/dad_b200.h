@@ -75,6 +75,22 @@ int dad_forward(dad_model* m, const float* x, int B, int H, int W, int mode, flo
  * ("tokens", "block0", "block_last", "layer_rn1".."layer_rn4", "path_4", "path_1"); dst = NULL clears. */
 int dad_model_debug_capture(dad_model* m, const char* name, float* dst, int64_t numel);
 
+/* ------------------------------------------------------------------ training forward / backward
+ * Replaces `loss.backward()` over the student forward (tools/train_distillation.py:1556-1575; autograd through
+ * dpt.py:150-225, dinov2.py:212-321, util/blocks.py:29-148).  fp32 engine only (mode = DAD_MODE_FP32; mode 0 returns
+ * DAD_ERR_UNSUPPORTED).  dad_forward_train computes the same outputs as dad_forward and keeps the activations it
+ * needs on a tape inside `workspace`; dad_backward, given the SAME workspace (untouched in between) and the upstream
+ * gradients of both outputs, ACCUMULATES d loss / d parameter into the fp32 buffers registered per parameter with
+ * dad_model_set_grad (student state-dict key; numel must match; dev_ptr = NULL unregisters, i.e. freezes it).
+ * Nothing is allocated or synchronised; weights must not change between the two calls. */
+int dad_model_set_grad(dad_model* m, const char* name, float* dev_ptr, int64_t numel);
+size_t dad_train_workspace_bytes(dad_model* m, int B, int H, int W, int mode);
+int dad_forward_train(dad_model* m, const float* x, int B, int H, int W, int mode, float* depth_out, float* feat_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* grad_depth [B,1,H,W] fp32 (required), grad_feat [B,(H/14)(W/14),D] fp32 (may be NULL = no gradient) */
+int dad_backward(dad_model* m, int B, int H, int W, int mode, const float* grad_depth, const float* grad_feat,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ losses
  * All maps are fp32 [rows, L] (rows = B*C images, L = H*W pixels). */
 size_t dad_loss_workspace_bytes(int rows, int num_contexts);

@@ -18,6 +18,13 @@ from helpers import rel_depth_err
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    # forward-only checks: keep the fp32 reference forwards on the inference path (no activation tape)
+    with torch.no_grad():
+        yield
+
+
 def build(preset, seed, teacher=False, head_bias=0.25):
     import distill_any_depth_b200 as d
     kw = synthetic.MODEL_PRESETS[preset]

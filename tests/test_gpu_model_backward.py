@@ -1,0 +1,148 @@
+"""Gradient of the student forward w.r.t. its parameters (`loss.backward()` of
+tools/train_distillation.py:1556-1575) against PyTorch autograd run on the CPU oracle, whose graph restates the
+reference modules op for op (dpt.py:150-225, dinov2.py:212-321, util/blocks.py:29-148).
+
+Tolerance: every parameter's gradient within 1e-3 of that tensor's largest |entry| (plus 1e-6 of the largest gradient
+entry of the whole model, for tensors whose gradient is ~0); fp32 sums of 10^3..10^5 terms in a different order than
+ATen's, and atomics in the split-K weight gradients.  Typical measured error is 1e-6..1e-5."""
+import json
+import os
+
+import pytest
+import torch
+
+import oracle
+from distill_any_depth_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def dad():
+    import distill_any_depth_b200 as d
+    return d
+
+
+def _log(name, rec):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_backward.jsonl"), "a") as f:
+        f.write(json.dumps(dict(case=name, **rec)) + "\n")
+
+
+def _objective(depth, feat, wd, wf):
+    # a generic scalar of BOTH outputs: fixed random cotangents, so every path of the graph carries a gradient
+    return (depth * wd).sum() + (feat * wf).sum()
+
+
+def _oracle_grads(sd, x, encoder, wd, wf):
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    depth, feat = oracle.depth_anything_forward(x, leaves, encoder)
+    _objective(depth, feat, wd, wf).backward()
+    return depth.detach(), feat.detach(), {k: v.grad for k, v in leaves.items()}
+
+
+def _compare(name, grads, ref, tol=1e-3):
+    gmax = max(float(g.abs().max()) for g in ref.values() if g is not None)
+    worst, bad = (0.0, None), []
+    for k, r in ref.items():
+        g = grads.get(k)
+        if r is None:
+            assert g is None, f"{k}: the reference leaves .grad = None"
+            continue
+        assert g is not None, f"{k}: no gradient"
+        err = float((g.cpu() - r).abs().max())
+        scale = float(r.abs().max())
+        rel = err / (scale + 1e-6 * gmax + 1e-30)
+        if rel > worst[0]:
+            worst = (rel, k)
+        if not (err <= tol * scale + 1e-6 * gmax):
+            bad.append((k, err, scale))
+    _log(name, dict(worst_rel=worst[0], worst_param=worst[1], n_params=len(ref), n_bad=len(bad), bad=bad[:40]))
+    assert not bad, f"{len(bad)} parameter gradients off: {bad[:8]}"
+
+
+@pytest.mark.parametrize("preset,B,H,W,seed", [("vits", 2, 70, 98, 0), ("vits", 1, 518, 518, 1), ("vitb", 2, 56, 56, 3)])
+def test_parameter_gradients_match_autograd(preset, B, H, W, seed):
+    d = dad()
+    kw = synthetic.MODEL_PRESETS[preset]
+    sd = synthetic.make_state_dict(seed=seed, **kw)
+    x = synthetic.make_images(B, H, W, seed=77)
+    g = torch.Generator().manual_seed(5)
+    D = sd["pretrained.cls_token"].shape[-1]
+    wd = torch.randn(B, 1, H, W, generator=g)
+    wf = torch.randn(B, (H // 14) * (W // 14), D, generator=g) * 0.05
+    d_ref, f_ref, ref = _oracle_grads(sd, x, kw["encoder"], wd, wf)
+
+    m = d.DepthAnythingV2(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    m.precision = "fp32"
+    depth, feat = m(x.cuda())
+    assert depth.requires_grad and feat.requires_grad
+    den = d_ref.abs().clamp(min=0.1 * float(d_ref.abs().max()))
+    assert float(((depth.detach().cpu() - d_ref).abs() / den).max()) <= 1e-4   # the training forward IS the fp32 forward
+    assert float((feat.detach().cpu() - f_ref).abs().max()) <= 1e-4 * float(f_ref.abs().max())
+    _objective(depth, feat, wd.cuda(), wf.cuda()).backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    _compare(f"{preset}_{B}x{H}x{W}", grads, ref)
+
+
+def test_training_step_losses_backpropagate_into_the_student():
+    """The reference loop's student update (tools/train_distillation.py:1509-1575, teacher map detached): SSI + HDN-DR
+    + gradient-preservation on the depth, cosine feature loss on the tokens; .grad of every parameter vs autograd."""
+    d = dad()
+    kw = synthetic.MODEL_PRESETS["vits"]
+    sd = synthetic.make_state_dict(seed=0, **kw)
+    B, H, W = 2, 70, 98
+    x = synthetic.make_images(B, H, W, seed=1234)
+    g = torch.Generator().manual_seed(11)
+    teacher = torch.rand(B, 1, H, W, generator=g) * 2 + 0.1
+    tfeat = torch.randn(B, (H // 14) * (W // 14), 384, generator=g)
+    mask = torch.ones(B, 1, H, W, dtype=torch.bool)
+
+    def total(mod, depth, feat, T, TF, MK):
+        return (mod.SSILoss()(depth, T, MK) + 0.5 * mod.compute_hdn_loss(mod.SSILoss(), depth, T, mod.get_contexts_dr(3, T, None))
+                + 0.2 * mod.gradient_preservation_loss(depth) + 0.8 * mod.feature_distillation_loss(feat, TF))
+
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    dc, fc = oracle.depth_anything_forward(x, leaves, kw["encoder"])
+    lref = total(oracle, dc, fc, teacher, tfeat, mask)
+    lref.backward()
+    ref = {k: v.grad for k, v in leaves.items()}
+
+    m = d.DepthAnythingV2(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    m.precision = "fp32"
+    depth, feat = m(x.cuda())
+    loss = total(d, depth, feat, teacher.cuda(), tfeat.cuda(), mask.cuda())
+    assert abs(float(loss) - float(lref)) <= 1e-3 * abs(float(lref))
+    loss.backward()
+    _compare("train_step_vits", {k: p.grad for k, p in m.named_parameters()}, ref, tol=2e-3)
+
+
+def test_frozen_parameters_and_no_grad_paths():
+    d = dad()
+    kw = synthetic.MODEL_PRESETS["vits"]
+    sd = synthetic.make_state_dict(seed=0, **kw)
+    m = d.DepthAnythingV2(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    m.precision = "fp32"
+    x = synthetic.make_images(1, 56, 56, seed=3).cuda()
+    with torch.no_grad():
+        d0, _ = m(x)
+    assert not d0.requires_grad
+    for p in m.pretrained.parameters():   # frozen encoder: only the head learns
+        p.requires_grad_(False)
+    d1, f1 = m(x)
+    assert torch.allclose(d1.detach(), d0, rtol=0, atol=1e-5 * float(d0.abs().max()))
+    d1.sum().backward()
+    assert all(p.grad is None for p in m.pretrained.parameters())
+    got = [k for k, p in m.depth_head.named_parameters() if p.grad is not None]
+    assert len(got) == len(list(m.depth_head.parameters())) - 4   # refinenet4.resConfUnit1.conv{1,2}.{weight,bias} unused
+    with pytest.raises(RuntimeError):
+        d1.sum().backward()   # tape already consumed
+    m.precision = "bf16"
+    d2, _ = m(x)
+    assert not d2.requires_grad   # tensor-core forward is inference-only
