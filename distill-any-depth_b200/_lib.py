@@ -52,6 +52,7 @@ PROTOTYPES = {
     "dad_distill_loss": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dad_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dad_gemm_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "dad_gemm_splitk": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dad_conv_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dad_conv_nhwc_ex": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dad_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

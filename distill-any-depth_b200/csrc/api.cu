@@ -111,6 +111,15 @@ int dad_gemm_ex(const void* A, const void* W, const float* bias, const float* ga
     return mode == 0 ? dad::gemm_tc(p, ST(stream)) : dad::gemm_simt(p, ST(stream));
 }
 
+int dad_gemm_splitk(const void* A, const void* W, const float* zeros, const float* ones, float* out, int M, int N, int K,
+                    int lda, int ksplit, void* stream) {
+    dad::GemmProblem p;
+    p.A = A; p.M = M; p.K = K; p.lda = lda; p.Wt = W; p.N = N; p.Kp = lda;
+    p.epi.bias = zeros; p.epi.gamma = ones; p.epi.res1 = out; p.epi.out = out; p.epi.ldc = N;
+    p.ksplit = ksplit;
+    return dad::gemm_tc(p, ST(stream));
+}
+
 int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
                   int Co, int taps, int mode, void* stream) {
     dad::GemmProblem p;

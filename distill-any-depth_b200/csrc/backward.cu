@@ -13,6 +13,34 @@ namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16;
 
+// activation tensors are fp32 (verification engine) or bf16 (tensor-core engine): run-time element type, uniform branch
+__device__ __forceinline__ float ldf(const void* p, long long i, int bf) {
+    return bf ? __bfloat162float(reinterpret_cast<const bf16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void stf(void* p, long long i, int bf, float v) {
+    if (bf) reinterpret_cast<bf16*>(p)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(p)[i] = v;
+}
+__device__ __forceinline__ float4 ldf4(const void* p, long long i, int bf) {   // i: element index, multiple of 4
+    if (bf) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p) + i);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+    }
+    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+}
+__device__ __forceinline__ void stf4(void* p, long long i, int bf, float4 v) {
+    if (bf) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a);
+        u.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p) + i) = u;
+    } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) sgemm_kernel(const SGemm g, int ksplit, int kchunk) {
     __shared__ float sA[TK][TM + 4];
     __shared__ float sB[TK][TN + 4];
@@ -111,8 +139,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SGemm g, int ksplit, i
 }
 
 // ---------------------------------------------------------------- column sums (bias / LayerScale gradients)
-__global__ void __launch_bounds__(256) colsum_kernel(const float* X, long long ldx, const float* Y, long long ldy, long long rows,
-                                                     int N, float* out, const float* scale, float* scaled_out) {
+__global__ void __launch_bounds__(256) colsum_kernel(const void* X, int xbf, long long ldx, const void* Y, int ybf, long long ldy,
+                                                     long long rows, int N, float* out, const float* scale, void* scaled_out) {
     __shared__ float red[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + cx;
@@ -120,9 +148,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* X, long long l
     if (n < N) {
         const float sc = scale ? scale[n] : 1.f;
         for (long long r = static_cast<long long>(blockIdx.y) * 8 + ry; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
-            const float x = X[r * ldx + n];
-            s += Y ? x * Y[r * ldy + n] : x;
-            if (scaled_out) scaled_out[r * ldx + n] = x * sc;
+            const float x = ldf(X, r * ldx + n, xbf);
+            s += Y ? x * ldf(Y, r * ldy + n, ybf) : x;
+            if (scaled_out) stf(scaled_out, r * ldx + n, ybf, x * sc);
         }
     }
     red[ry][cx] = s;
@@ -137,7 +165,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* X, long long l
 
 // ---------------------------------------------------------------- LayerNorm backward
 template <int VPT>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* x, const float* w, const float* dy, float* dx, float* dw,
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* x, const float* w, const void* dy, int dybf, float* dx, float* dw,
                                                      float* db, long long rows, int D, int out_period, int in_period,
                                                      int in_offset, float eps) {
     __shared__ float sw[2048];
@@ -158,7 +186,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* x, const float
     for (long long r = gw; r < rows; r += nw) {
         const long long ir = (r / out_period) * in_period + in_offset + r % out_period;
         const float4* src = reinterpret_cast<const float4*>(x + ir * D);
-        const float4* gsrc = reinterpret_cast<const float4*>(dy + r * D);
         float4 v[VPT], gq[VPT];
         float sum = 0.f;
 #pragma unroll
@@ -166,7 +193,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* x, const float
             const int idx = lane + j * 32;
             if (idx * 4 < D) {
                 v[j] = src[idx];
-                gq[j] = gsrc[idx];
+                gq[j] = ldf4(dy, r * D + idx * 4, dybf);
                 sum += v[j].x + v[j].y + v[j].z + v[j].w;
             } else {
                 v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -238,35 +265,113 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* x, const float
 }
 
 // ---------------------------------------------------------------- small elementwise kernels
-__global__ void __launch_bounds__(256) ls_residual_kernel(const float* xold, const float* y, const float* gamma, float* xnew,
+__global__ void __launch_bounds__(256) ls_residual_kernel(const float* xold, const void* y, int bf, const float* gamma, float* xnew,
                                                           long long n, int D) {
     const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-    if (i < n) xnew[i] = xold[i] + y[i] * gamma[i % D];   // x + ls(y), ls(y) = y * gamma (layer_scale.py:27-28)
+    if (i < n) xnew[i] = xold[i] + ldf(y, i, bf) * gamma[i % D];   // x + ls(y), ls(y) = y * gamma (layer_scale.py:27-28)
 }
 
-__global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* pre, float* out, long long n) {
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const void* pre, void* out, int bf, long long n) {
     const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-    if (i < n) { const float x = pre[i]; out[i] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+    if (i < n) { const float x = ldf(pre, i, bf); stf(out, i, bf, 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f))); }
 }
 
-__global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* pre, const float* dout, float* dpre, long long n) {
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const void* pre, const void* dout, void* dpre, int bf, long long n) {
     const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
     if (i < n) {
-        const float x = pre[i];
+        const float x = ldf(pre, i, bf);
         const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
         const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-        dpre[i] = dout[i] * (cdf + x * pdf);
+        stf(dpre, i, bf, ldf(dout, i, bf) * (cdf + x * pdf));
     }
 }
 
-__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* g, const float* y, const float* add, float* out, long long n) {
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const void* g, const void* y, const void* add, void* out, int bf, long long n) {
     const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-    if (i < n) out[i] = (add ? add[i] : 0.f) + (y[i] > 0.f ? g[i] : 0.f);
+    if (i < n) stf(out, i, bf, (add ? ldf(add, i, bf) : 0.f) + (ldf(y, i, bf) > 0.f ? ldf(g, i, bf) : 0.f));
 }
 
-__global__ void __launch_bounds__(256) add_kernel(float* dst, const float* src, long long n) {
+__global__ void __launch_bounds__(256) add_kernel(void* dst, int bf, const float* src, long long n) {
     const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-    if (i < n) dst[i] += src[i];
+    if (i < n) stf(dst, i, bf, ldf(dst, i, bf) + src[i]);
+}
+
+__global__ void __launch_bounds__(256) convert_kernel(const void* src, int sbf, void* dst, int dbf, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i < n) stf(dst, i, dbf, ldf(src, i, sbf));
+}
+
+// out[c][r] = in[r * ld + c] for r < R (0 for R <= r < Rp): K-major operands of the weight-gradient GEMMs
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const bf16* in, long long ld, int R, int C, bf16* out, int Rp) {
+    __shared__ bf16 tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + i * 8, c = c0 + tx;
+        tile[ty + i * 8][tx] = (r < R && c < C) ? in[r * ld + c] : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + i * 8, r = r0 + tx;
+        if (c < C && r < Rp) out[static_cast<long long>(c) * Rp + r] = tile[tx][ty + i * 8];
+    }
+}
+
+// out[(c * taps + tap)][p] = window(X)[p, tap, c], p = output pixel (b, oy, ox); 0 for P <= p < Pp and outside the image
+__global__ void __launch_bounds__(256) im2colT_kernel(const bf16* X, int H, int W, int Ci, int taps, int stride, int Ho, int Wo,
+                                                      long long P, bf16* out, long long Pp) {
+    __shared__ bf16 tile[32][33];
+    const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+    const int c0 = blockIdx.y * 32, tap = blockIdx.z;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int dy = taps == 9 ? tap / 3 - 1 : 0, dx = taps == 9 ? tap % 3 - 1 : 0;
+    const long long hw = static_cast<long long>(Ho) * Wo;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long p = p0 + ty + i * 8;
+        const int c = c0 + tx;
+        bf16 v = __float2bfloat16_rn(0.f);
+        if (p < P && c < Ci) {
+            const int b = static_cast<int>(p / hw);
+            const int r = static_cast<int>(p - b * hw);
+            const int oy = r / Wo, ox = r - oy * Wo;
+            const int y = oy * stride + dy, x = ox * stride + dx;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = X[((static_cast<long long>(b) * H + y) * W + x) * Ci + c];
+        }
+        tile[ty + i * 8][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + i * 8;
+        const long long p = p0 + tx;
+        if (c < Ci && p < Pp) out[(static_cast<long long>(c) * taps + tap) * Pp + p] = tile[tx][ty + i * 8];
+    }
+}
+
+// w [N][K] fp32 -> out [K][Np] bf16 (zero for n >= N): the transposed weight of a data-gradient GEMM
+__global__ void __launch_bounds__(256) pack_linear_T_kernel(const float* w, bf16* out, int N, int K, int Np) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty + i * 8, k = k0 + tx;
+        tile[ty + i * 8][tx] = (n < N && k < K) ? w[static_cast<long long>(n) * K + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = k0 + ty + i * 8, n = n0 + tx;
+        if (k < K && n < Np) out[static_cast<long long>(k) * Np + n] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* p, float v, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 // ---------------------------------------------------------------- attention probabilities
@@ -298,7 +403,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* P, f
 }
 
 // ---------------------------------------------------------------- bilinear adjoint (align_corners=True)
-__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* gout, float* gin, int B, int Hi, int Wi, int Ho, int Wo,
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const void* gout, int bf, float* gin, int B, int Hi, int Wi, int Ho, int Wo,
                                                            int C, float sh, float sw) {
     const int cv = C / 4;
     const long long total = static_cast<long long>(B) * Ho * Wo * cv;
@@ -314,7 +419,7 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* gout, fl
     const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
     const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
     const float ly = fy - y0, hy = 1.f - ly, lx = fx - x0, hx = 1.f - lx;
-    const float4 g = *reinterpret_cast<const float4*>(gout + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C + c * 4);
+    const float4 g = ldf4(gout, ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C + c * 4, bf);
     float* base = gin + static_cast<long long>(b) * Hi * Wi * C + c * 4;
     const float wq[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
     const long long off[4] = {(static_cast<long long>(y0) * Wi + x0) * C, (static_cast<long long>(y0) * Wi + x1) * C,
@@ -328,8 +433,8 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* gout, fl
 }
 
 // ---------------------------------------------------------------- output head adjoint
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float* gdepth, const float* depth, const float* t32, const float* w2,
-                                                       float* dt32, float* dw2, float* db2, long long P) {
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* gdepth, const float* depth, const void* t32, int bf, const float* w2,
+                                                       void* dt32, float* dw2, float* db2, long long P) {
     __shared__ float sacc[33];
     if (threadIdx.x < 33) sacc[threadIdx.x] = 0.f;
     __syncthreads();
@@ -343,14 +448,12 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* gdepth, cons
     for (long long p = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; p < P; p += static_cast<long long>(gridDim.x) * 256) {
         const float g = depth[p] > 0.f ? gdepth[p] : 0.f;   // relu(relu(z)): one mask
         abias += g;
-        const float4* src = reinterpret_cast<const float4*>(t32 + p * 32);
-        float4* dst = reinterpret_cast<float4*>(dt32 + p * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 t = src[j];
+            const float4 t = ldf4(t32, p * 32 + 4 * j, bf);
             aw[4 * j] += g * t.x; aw[4 * j + 1] += g * t.y; aw[4 * j + 2] += g * t.z; aw[4 * j + 3] += g * t.w;
-            dst[j] = make_float4(t.x > 0.f ? g * wv[4 * j] : 0.f, t.y > 0.f ? g * wv[4 * j + 1] : 0.f,
-                                 t.z > 0.f ? g * wv[4 * j + 2] : 0.f, t.w > 0.f ? g * wv[4 * j + 3] : 0.f);
+            stf4(dt32, p * 32 + 4 * j, bf, make_float4(t.x > 0.f ? g * wv[4 * j] : 0.f, t.y > 0.f ? g * wv[4 * j + 1] : 0.f,
+                                                       t.z > 0.f ? g * wv[4 * j + 2] : 0.f, t.w > 0.f ? g * wv[4 * j + 3] : 0.f));
         }
     }
 #pragma unroll
@@ -364,6 +467,20 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* gdepth, cons
     __syncthreads();
     if (threadIdx.x < 32 && dw2) atomicAdd(dw2 + threadIdx.x, sacc[threadIdx.x]);
     if (threadIdx.x == 32 && db2) atomicAdd(db2, sacc[32]);
+}
+
+// training-forward output head on a saved (fp32 or bf16) ReLU'd 32-channel map: relu(dot(row, w) + b)
+__global__ void __launch_bounds__(256) head1x1_any_kernel(const void* in, int bf, const float* w, float bias, float* out, long long P) {
+    const long long p = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (p >= P) return;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 v = ldf4(in, p * 32 + 4 * j, bf);
+        s = fmaf(v.x, w[4 * j], s); s = fmaf(v.y, w[4 * j + 1], s);
+        s = fmaf(v.z, w[4 * j + 2], s); s = fmaf(v.w, w[4 * j + 3], s);
+    }
+    out[p] = fmaxf(s + bias, 0.f);
 }
 
 // ---------------------------------------------------------------- ConvTranspose / strided-conv helpers
@@ -414,14 +531,14 @@ __global__ void __launch_bounds__(256) col2im_s2_kernel(const float* dcol, float
     din[i] = s;
 }
 
-__global__ void __launch_bounds__(256) pack_conv_dgrad_kernel(const float* w, float* out, int Co, int Ci, int taps, int CoP) {
+__global__ void __launch_bounds__(256) pack_conv_dgrad_kernel(const float* w, void* out, int bf, int Co, int Ci, int taps, int CoP) {
     const long long total = static_cast<long long>(Ci) * taps * CoP;
     const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
     if (i >= total) return;
     const int co = static_cast<int>(i % CoP);
     const int t = static_cast<int>((i / CoP) % taps);
     const int ci = static_cast<int>(i / (static_cast<long long>(CoP) * taps));
-    out[i] = co < Co ? w[(static_cast<long long>(co) * Ci + ci) * taps + (taps - 1 - t)] : 0.f;
+    stf(out, i, bf, co < Co ? w[(static_cast<long long>(co) * Ci + ci) * taps + (taps - 1 - t)] : 0.f);
 }
 
 __global__ void __launch_bounds__(256) batch_sum_rows_kernel(const float* G, float* dtab, int B, int T, int D) {
@@ -496,23 +613,23 @@ int sgemm(const SGemm& g, cudaStream_t st) {
     return DAD_OK;
 }
 
-int colsum(const float* X, long long ldx, const float* Y, long long ldy, long long rows, int N, float* out, const float* scale,
-           float* scaled_out, cudaStream_t st) {
+int colsum(const void* X, int xbf, long long ldx, const void* Y, int ybf, long long ldy, long long rows, int N, float* out,
+           const float* scale, void* scaled_out, cudaStream_t st) {
     DAD_REQUIRE(X && rows > 0 && N > 0 && (out || scaled_out), "colsum: bad arguments");
     const dim3 grid(cdiv(N, 32), static_cast<unsigned>(std::min<long long>(cdivl(rows, 64), 1024)));
     ProfScope prof(PROF_ELEM, static_cast<double>(rows) * N * 4 * (1 + (Y ? 1 : 0) + (scaled_out ? 1 : 0)), st);
-    colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, rows, N, out, scale, scaled_out);
+    colsum_kernel<<<grid, 256, 0, st>>>(X, xbf, ldx, Y, ybf, ldy, rows, N, out, scale, scaled_out);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 
-int layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, long long rows, int D,
+int layernorm_bwd(const float* x, const float* w, const void* dy, int dybf, float* dx, float* dw, float* db, long long rows, int D,
                   int out_period, int in_period, int in_offset, float eps, cudaStream_t st) {
     DAD_REQUIRE(x && w && dy && dx && D % 4 == 0 && D <= 2048, "layernorm_bwd: bad arguments (D=%d)", D);
     const unsigned grid = static_cast<unsigned>(std::min<long long>(cdivl(rows, 8), 4LL * num_sms()));
     ProfScope prof(PROF_LN, static_cast<double>(rows) * D * 16, st);
     const int vpt = cdiv(D, 128);
-#define LNB(V) ln_bwd_kernel<V><<<grid, 256, 0, st>>>(x, w, dy, dx, dw, db, rows, D, out_period, in_period, in_offset, eps)
+#define LNB(V) ln_bwd_kernel<V><<<grid, 256, 0, st>>>(x, w, dy, dybf, dx, dw, db, rows, D, out_period, in_period, in_offset, eps)
     if (vpt <= 3) LNB(3);
     else if (vpt <= 6) LNB(6);
     else if (vpt <= 8) LNB(8);
@@ -522,38 +639,89 @@ int layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, fl
     return DAD_OK;
 }
 
-int ls_residual(const float* xold, const float* y, const float* gamma, float* xnew, long long rows, int D, cudaStream_t st) {
+int ls_residual(const float* xold, const void* y, int bf, const float* gamma, float* xnew, long long rows, int D, cudaStream_t st) {
     const long long n = rows * D;
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 12, st);
-    ls_residual_kernel<<<blocks_for(n), 256, 0, st>>>(xold, y, gamma, xnew, n, D);
+    ls_residual_kernel<<<blocks_for(n), 256, 0, st>>>(xold, y, bf, gamma, xnew, n, D);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 
-int gelu_fwd(const float* pre, float* out, long long n, cudaStream_t st) {
+int gelu_fwd(const void* pre, void* out, int bf, long long n, cudaStream_t st) {
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 8, st);
-    gelu_fwd_kernel<<<blocks_for(n), 256, 0, st>>>(pre, out, n);
+    gelu_fwd_kernel<<<blocks_for(n), 256, 0, st>>>(pre, out, bf, n);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 
-int gelu_bwd(const float* pre, const float* dout, float* dpre, long long n, cudaStream_t st) {
+int gelu_bwd(const void* pre, const void* dout, void* dpre, int bf, long long n, cudaStream_t st) {
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 12, st);
-    gelu_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(pre, dout, dpre, n);
+    gelu_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(pre, dout, dpre, bf, n);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 
-int relu_bwd(const float* g, const float* y, const float* add, float* out, long long n, cudaStream_t st) {
+int relu_bwd(const void* g, const void* y, const void* add, void* out, int bf, long long n, cudaStream_t st) {
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * (add ? 16 : 12), st);
-    relu_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(g, y, add, out, n);
+    relu_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(g, y, add, out, bf, n);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 
-int add_inplace(float* dst, const float* src, long long n, cudaStream_t st) {
+int add_inplace(void* dst, int bf, const float* src, long long n, cudaStream_t st) {
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 12, st);
-    add_kernel<<<blocks_for(n), 256, 0, st>>>(dst, src, n);
+    add_kernel<<<blocks_for(n), 256, 0, st>>>(dst, bf, src, n);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int convert(const void* src, int src_bf16, void* dst, int dst_bf16, long long n, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(n) * ((src_bf16 ? 2 : 4) + (dst_bf16 ? 2 : 4)), st);
+    convert_kernel<<<blocks_for(n), 256, 0, st>>>(src, src_bf16, dst, dst_bf16, n);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int fill_f32(float* p, float v, long long n, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(n) * 4, st);
+    fill_kernel<<<blocks_for(n), 256, 0, st>>>(p, v, n);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int transpose_pad(const void* in, long long ld, int R, int C, void* out, int Rp, cudaStream_t st) {
+    DAD_REQUIRE(in && out && R > 0 && C > 0 && Rp >= R, "transpose_pad: bad arguments");
+    const dim3 grid(cdiv(Rp, 32), cdiv(C, 32));
+    DAD_REQUIRE(grid.y <= 65535, "transpose_pad: too many columns");
+    ProfScope prof(PROF_ELEM, (static_cast<double>(R) + Rp) * C * 2, st);
+    transpose_pad_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(in), ld, R, C, reinterpret_cast<bf16*>(out), Rp);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int im2colT(const void* X, int B, int H, int W, int Ci, int taps, int stride, int Ho, int Wo, void* out, long long Pp,
+            cudaStream_t st) {
+    const long long P = static_cast<long long>(B) * Ho * Wo;
+    DAD_REQUIRE(X && out && Pp >= P && (taps == 1 || taps == 9), "im2colT: bad arguments");
+    const dim3 grid(static_cast<unsigned>(cdivl(Pp, 32)), cdiv(Ci, 32), taps);
+    ProfScope prof(PROF_ELEM, static_cast<double>(Pp) * Ci * taps * 4, st);
+    im2colT_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(X), H, W, Ci, taps, stride, Ho, Wo, P,
+                                         reinterpret_cast<bf16*>(out), Pp);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int pack_linear_T(const float* w, void* out, int N, int K, int Np, cudaStream_t st) {
+    const dim3 grid(cdiv(Np, 32), cdiv(K, 32));
+    ProfScope prof(PROF_ELEM, static_cast<double>(N) * K * 6, st);
+    pack_linear_T_kernel<<<grid, 256, 0, st>>>(w, reinterpret_cast<bf16*>(out), N, K, Np);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int head1x1_any(const void* in, int bf, const float* w, float bias, float* out, long long P, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(P) * (32 * (bf ? 2 : 4) + 4), st);
+    head1x1_any_kernel<<<blocks_for(P), 256, 0, st>>>(in, bf, w, bias, out, P);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
@@ -572,22 +740,22 @@ int softmax_bwd_rows(const float* P, float* dP, long long rows, int T, cudaStrea
     return DAD_OK;
 }
 
-int bilinear_bwd(const float* gout, float* gin, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st) {
+int bilinear_bwd(const void* gout, int bf, float* gin, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st) {
     DAD_REQUIRE(C % 4 == 0, "bilinear_bwd: C=%d must be a multiple of 4", C);
     const float sh = Ho > 1 ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.f;
     const float sw = Wo > 1 ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.f;
     const long long total = static_cast<long long>(B) * Ho * Wo * (C / 4);
     ProfScope prof(PROF_ELEM, static_cast<double>(B) * C * 4 * (static_cast<double>(Hi) * Wi + static_cast<double>(Ho) * Wo), st);
-    bilinear_bwd_kernel<<<blocks_for(total), 256, 0, st>>>(gout, gin, B, Hi, Wi, Ho, Wo, C, sh, sw);
+    bilinear_bwd_kernel<<<blocks_for(total), 256, 0, st>>>(gout, bf, gin, B, Hi, Wi, Ho, Wo, C, sh, sw);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 
-int head_bwd(const float* gdepth, const float* depth, const float* t32, const float* w2, float* dt32, float* dw2, float* db2,
+int head_bwd(const float* gdepth, const float* depth, const void* t32, int bf, const float* w2, void* dt32, float* dw2, float* db2,
              long long P, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>(std::min<long long>(cdivl(P, 256), 8LL * num_sms()));
     ProfScope prof(PROF_ELEM, static_cast<double>(P) * (8 + 256), st);
-    head_bwd_kernel<<<grid, 256, 0, st>>>(gdepth, depth, t32, w2, dt32, dw2, db2, P);
+    head_bwd_kernel<<<grid, 256, 0, st>>>(gdepth, depth, t32, bf, w2, dt32, dw2, db2, P);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
@@ -609,10 +777,10 @@ int col2im_s2(const float* dcol, float* din, int B, int H, int W, int C, int Cp,
     return DAD_OK;
 }
 
-int pack_conv_dgrad(const float* w, float* out, int Co, int Ci, int taps, int CoP, cudaStream_t st) {
+int pack_conv_dgrad(const float* w, void* out, int bf, int Co, int Ci, int taps, int CoP, cudaStream_t st) {
     const long long total = static_cast<long long>(Ci) * taps * CoP;
     ProfScope prof(PROF_ELEM, static_cast<double>(total) * 8, st);
-    pack_conv_dgrad_kernel<<<blocks_for(total), 256, 0, st>>>(w, out, Co, Ci, taps, CoP);
+    pack_conv_dgrad_kernel<<<blocks_for(total), 256, 0, st>>>(w, out, bf, Co, Ci, taps, CoP);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

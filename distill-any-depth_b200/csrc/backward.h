@@ -29,33 +29,43 @@ struct SGemm {
 };
 int sgemm(const SGemm& g, cudaStream_t st);
 
-// out[n] += sum_r X[r*ldx + n] * (Y ? Y[r*ldy + n] : 1);  if `scaled_out`: scaled_out[r*ldx + n] = X[r*ldx + n] * scale[n]
-int colsum(const float* X, long long ldx, const float* Y, long long ldy, long long rows, int N, float* out,
-           const float* scale, float* scaled_out, cudaStream_t st);
+// activation tensors carry a run-time element type: *_bf16 / bf = 1 for bf16 (tensor-core engine), 0 for fp32
+// out[n] += sum_r X[r*ldx + n] * (Y ? Y[r*ldy + n] : 1);  if `scaled_out` (type of Y): scaled_out[r*ldx + n] = X[r*ldx + n] * scale[n]
+int colsum(const void* X, int x_bf16, long long ldx, const void* Y, int y_bf16, long long ldy, long long rows, int N, float* out,
+           const float* scale, void* scaled_out, cudaStream_t st);
 // LayerNorm backward, row mapping as layernorm(): dy row r <-> x row ir.  dx[ir] += ..., dw += ..., db += ...
-int layernorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, long long rows, int D,
+int layernorm_bwd(const float* x, const float* w, const void* dy, int dy_bf16, float* dx, float* dw, float* db, long long rows, int D,
                   int out_period, int in_period, int in_offset, float eps, cudaStream_t st);
 // xnew = xold + gamma * y   (LayerScale + residual of the training forward)
-int ls_residual(const float* xold, const float* y, const float* gamma, float* xnew, long long rows, int D, cudaStream_t st);
-int gelu_fwd(const float* pre, float* out, long long n, cudaStream_t st);
-int gelu_bwd(const float* pre, const float* dout, float* dpre, long long n, cudaStream_t st);
+int ls_residual(const float* xold, const void* y, int bf, const float* gamma, float* xnew, long long rows, int D, cudaStream_t st);
+int gelu_fwd(const void* pre, void* out, int bf, long long n, cudaStream_t st);
+int gelu_bwd(const void* pre, const void* dout, void* dpre, int bf, long long n, cudaStream_t st);
 // out = (add ? add : 0) + g * (y > 0)
-int relu_bwd(const float* g, const float* y, const float* add, float* out, long long n, cudaStream_t st);
-int add_inplace(float* dst, const float* src, long long n, cudaStream_t st);
+int relu_bwd(const void* g, const void* y, const void* add, void* out, int bf, long long n, cudaStream_t st);
+int add_inplace(void* dst, int bf, const float* src, long long n, cudaStream_t st);   // dst += src (fp32)
+int convert(const void* src, int src_bf16, void* dst, int dst_bf16, long long n, cudaStream_t st);
+int fill_f32(float* p, float v, long long n, cudaStream_t st);
+// bf16 only: out[c][r] = in[r*ld + c] (r < R; zero for R <= r < Rp) - K-major operands of the weight-gradient GEMMs
+int transpose_pad(const void* in, long long ld, int R, int C, void* out, int Rp, cudaStream_t st);
+// bf16 only: out[(c*taps + tap)][p] = window(X)[p, tap, c] over output pixels p (zero padded to Pp columns)
+int im2colT(const void* X, int B, int H, int W, int Ci, int taps, int stride, int Ho, int Wo, void* out, long long Pp, cudaStream_t st);
+// w [N][K] fp32 -> out [K][Np] bf16
+int pack_linear_T(const float* w, void* out, int N, int K, int Np, cudaStream_t st);
+int head1x1_any(const void* in, int bf, const float* w, float bias, float* out, long long P, cudaStream_t st);
 // row-wise softmax of S [rows, T] in place; and dS = P * (dP - sum_j P*dP) in place of dP
 int softmax_rows(float* S, long long rows, int T, cudaStream_t st);
 int softmax_bwd_rows(const float* P, float* dP, long long rows, int T, cudaStream_t st);
 // adjoint of bilinear_nhwc (align_corners=True): gin [B,Hi,Wi,C] must be zero-filled by the caller
-int bilinear_bwd(const float* gout, float* gin, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st);
+int bilinear_bwd(const void* gout, int bf, float* gin, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st);
 // output head: depth = relu(dot(t32, w2) + b2), t32 = relu(conv + b) saved.  dt32 [P,32]; dw2 [32] / db2 [1] accumulate
-int head_bwd(const float* gdepth, const float* depth, const float* t32, const float* w2, float* dt32, float* dw2,
+int head_bwd(const float* gdepth, const float* depth, const void* t32, int bf, const float* w2, void* dt32, float* dw2,
              float* db2, long long P, cudaStream_t st);
 // ConvTranspose k=s: G[(b,y,x), t*CoP + co] = dOut[b, k*y+ky, k*x+kx, co] (0 for co >= Co)
 int convT_gather(const float* dout, float* G, int B, int H, int W, int k, int Co, int CoP, cudaStream_t st);
 // stride-2 3x3 conv: din[b,y,x,c] = sum over taps of dcol[(b,oy,ox), tap*Cp + c] with y = 2*oy+dy-1, x = 2*ox+dx-1
 int col2im_s2(const float* dcol, float* din, int B, int H, int W, int C, int Cp, cudaStream_t st);
 // dgrad weights of a stride-1 conv: w [Co][Ci][taps] -> out [Ci][taps][CoP], out[ci][t][co] = w[co][ci][taps-1-t]
-int pack_conv_dgrad(const float* w, float* out, int Co, int Ci, int taps, int CoP, cudaStream_t st);
+int pack_conv_dgrad(const float* w, void* out, int bf, int Co, int Ci, int taps, int CoP, cudaStream_t st);
 // dtab[t, d] = sum_b G[(b*T + t), d]
 int batch_sum_rows(const float* G, float* dtab, int B, int T, int D, cudaStream_t st);
 // gradients of pos_table(): cls_token, pos_embed (bicubic adjoint), patch-embed bias; all accumulate (any may be null)

@@ -55,6 +55,8 @@ struct GemmProblem {
     const void* Wt = nullptr; // [N, Kp] K-major; bf16 (tc) or fp32 (simt)
     int N = 0;
     int Kp = 0;               // padded K (row length of Wt)
+    int ksplit = 1;           // gemm_tc, linear, `out += gamma * (acc + bias)` epilogue only: split the K loop over this many
+                              // work items per tile, each reduce-adding its partial product (weight-gradient GEMMs: K = tokens)
     Epilogue epi;
 };
 

@@ -43,6 +43,7 @@ struct TcArgs {
     int tw_log2, th;        // spatial tile (conv): TW = 1 << tw_log2, TH = 128 / TW
     int tiles_x, tiles_y;
     int num_m_tiles, num_n_tiles;
+    int ksplit, kb_per_split;  // split-K (linear + TMA reduce-add epilogue only): work item = (k slice, tile)
     double flops;           // algorithmic 2*M*N*K of this launch (host-side bookkeeping only)
 };
 
@@ -128,6 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
     const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+    const int num_items = num_tiles * g.ksplit;   // ksplit == 1 everywhere except the weight-gradient GEMMs
     const int nkb = g.num_k_blocks;
 
     if (warp == 0) {
@@ -136,7 +138,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0, sa = 0;
             uint32_t phase = 0, pa = 0;
             bool weights_loaded = false;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int ks = item / num_tiles, tile = item - ks * num_tiles;
+                const int kb0 = ks * g.kb_per_split, kb1 = min(nkb, kb0 + g.kb_per_split);
                 const int mt = tile / g.num_n_tiles;
                 const int n0 = (tile - mt * g.num_n_tiles) * BN;
                 int b = 0, y0 = 0, x0 = 0;
@@ -164,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (++sa == NA) { sa = 0; pa ^= 1; }
                     }
                 } else {
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
                     if (g.conv) {
@@ -194,7 +198,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bool weights_ready = false;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int ks = item / num_tiles;
+            const int kb0 = ks * g.kb_per_split, kb1 = min(nkb, kb0 + g.kb_per_split);
             ptx::mbar_wait(&tempty[as], aphase ^ 1);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * BN;
@@ -225,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++sa == NA) { sa = 0; pa ^= 1; }
                 }
             } else {
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&full[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t a_lo = sA_lo + stage * (A_STAGE_BYTES >> 4);
@@ -234,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             ptx::umma_bf16(d_tmem, ptx::make_desc(a_lo + 2 * k, ptx::kDescHiSw128),
-                                           ptx::make_desc(b_lo + 2 * k, ptx::kDescHiSw128), idesc, (kb | k) != 0 ? 1u : 0u);
+                                           ptx::make_desc(b_lo + 2 * k, ptx::kDescHiSw128), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                         ptx::umma_commit(&empty[stage]);
                     }
                     __syncwarp();
@@ -261,7 +267,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tw_mask = (1 << g.tw_log2) - 1;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int tile = item % num_tiles;
             const int mt = tile / g.num_n_tiles;
             const int n0 = (tile - mt * g.num_n_tiles) * BN;
             int cb = 0, cy0 = 0, cx0 = 0;
@@ -488,7 +495,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
                                             Cfg<BN, HALO>::SMEM_BYTES));
         configured = true;
     }
-    const int tiles = a.num_m_tiles * a.num_n_tiles;
+    const int tiles = a.num_m_tiles * a.num_n_tiles * a.ksplit;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     ProfScope prof(PROF_GEMM_TC, a.flops, stream);
     DAD_CHECK_CUDA(launch_pdl(gemm_tc_kernel<BN, KIND, HALO>, dim3(grid), dim3(NUM_THREADS), Cfg<BN, HALO>::SMEM_BYTES, stream,
@@ -531,7 +538,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     DAD_REQUIRE(p.A && p.Wt && p.N > 0, "gemm_tc: null operand or N<=0");
     {
         static const bool no_2cta = getenv("DAD_NO_2CTA") != nullptr;  // A/B switch while the 2-CTA kernel is validated
-        if (!no_2cta && gemm_tc2_eligible(p)) return gemm_tc2(p, stream);
+        if (!no_2cta && p.ksplit <= 1 && gemm_tc2_eligible(p)) return gemm_tc2(p, stream);
         if (!no_2cta && conv_tc2_eligible(p)) return conv_tc2(p, stream);
     }
     DAD_REQUIRE(p.N % 8 == 0, "gemm_tc: N=%d must be a multiple of 8", p.N);
@@ -540,7 +547,9 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     a.epi = p.epi;
     a.N = p.N;
     a.conv = p.conv;
+    a.ksplit = 1;
     int bn = pick_bn(p.N);
+    if (p.ksplit > 1 && bn < 128) bn = 128;   // split-K needs the TMA reduce-add epilogue (wide tiles only)
     if (p.epi.head_out) {
         DAD_REQUIRE(p.N == 32 && p.epi.bias && p.epi.head_w, "gemm_tc: fused head needs N == 32, bias and head_w");
         bn = 32;
@@ -625,6 +634,14 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     if (scat_tma) kind = EK_BIAS_BF16;
     DAD_REQUIRE(!(e.scat_k && p.conv && !scat_tma), "gemm_tc: conv-mode ConvTranspose scatter needs Co %% 64 == 0, bf16 out");
     if (bn < 128) kind = EK_GENERIC;  // the specialised (TMA-store) epilogues exist for the wide tiles only
+    if (p.ksplit > 1) {
+        // split-K: each (k slice, tile) work item reduce-adds its partial product into the fp32 output through TMA
+        DAD_REQUIRE(!p.conv && kind == EK_RES_F32, "gemm_tc: split-K needs a linear problem with the out += gamma * (acc + bias) epilogue");
+        a.kb_per_split = cdiv(a.num_k_blocks, p.ksplit);
+        a.ksplit = cdiv(a.num_k_blocks, a.kb_per_split);
+    } else {
+        a.kb_per_split = a.num_k_blocks;
+    }
     DAD_REQUIRE(!(kind == EK_GENERIC && p.epi.act == ACT_GELU), "gemm_tc: GELU is only fused as bias+GELU->bf16");
     CUtensorMap tmC = tmA;  // placeholder for the generic epilogue (never dereferenced)
     if (kind != EK_GENERIC) {

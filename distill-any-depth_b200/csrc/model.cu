@@ -490,8 +490,7 @@ public:
 namespace {
 
 int train_checks(Model& m, int B, int H, int W, int mode) {
-    if (mode != 1)
-        return set_error(DAD_ERR_UNSUPPORTED, "the training forward / backward runs in the fp32 engine only (mode 1, precision='fp32')");
+    DAD_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (bf16) or 1 (fp32)");
     DAD_REQUIRE(B > 0 && H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0,
                 "input must be [B,3,H,W] with H, W positive multiples of 14 (got B=%d H=%d W=%d)", B, H, W);
     DAD_REQUIRE(static_cast<long long>(B) * (1 + (H / 14) * (W / 14)) < (1LL << 31) / 4, "batch too large for 32-bit row indices");
@@ -505,14 +504,14 @@ int train_workspace(Model& m, int B, int H, int W, int mode, size_t* need) {
     {
         Bump ar(nullptr, 0, true);
         Tape t;
-        Trainer tr(m, B, H, W, true, nullptr);
+        Trainer tr(m, B, H, W, mode, true, nullptr);
         DAD_TRY(tr.forward(nullptr, nullptr, nullptr, ar, t));
         peak = ar.peak;
     }
     {
         Bump ar(nullptr, 0, true);
         Tape t;
-        Trainer tr(m, B, H, W, true, nullptr);
+        Trainer tr(m, B, H, W, mode, true, nullptr);
         DAD_TRY(tr.backward(nullptr, nullptr, ar, t));
         if (ar.peak > peak) peak = ar.peak;
     }
@@ -525,7 +524,8 @@ int train_ready(Model& m, int B, int H, int W, int mode, void* ws, size_t ws_byt
     DAD_TRY(train_workspace(m, B, H, W, mode, &need));
     if (ws_bytes < need) return set_error(DAD_ERR_WORKSPACE, "training workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     const auto pit = m.pos_tables.find(std::make_pair(H, W));
-    DAD_REQUIRE(m.packed[1] && pit != m.pos_tables.end() && pit->second != nullptr, "call dad_model_prepare(mode, H, W) first");
+    DAD_REQUIRE(m.packed[1] && m.packed[mode] && pit != m.pos_tables.end() && pit->second != nullptr,
+                "call dad_model_prepare(mode, H, W) first (training in mode 0 also needs the fp32 pack: prepare both modes)");
     DAD_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
     return DAD_OK;
 }
@@ -599,7 +599,7 @@ int dad_forward_train(dad_model* m, const float* x, int B, int H, int W, int mod
     DAD_TRY(dad::train_ready(mm, B, H, W, mode, workspace, workspace_bytes));
     dad::Bump ar(workspace, workspace_bytes, false);
     dad::Tape t;
-    dad::Trainer tr(mm, B, H, W, false, reinterpret_cast<cudaStream_t>(stream));
+    dad::Trainer tr(mm, B, H, W, mode, false, reinterpret_cast<cudaStream_t>(stream));
     return tr.forward(x, depth_out, feat_out, ar, t);
 }
 
@@ -610,7 +610,7 @@ int dad_backward(dad_model* m, int B, int H, int W, int mode, const float* grad_
     DAD_TRY(dad::train_ready(mm, B, H, W, mode, workspace, workspace_bytes));
     dad::Bump ar(workspace, workspace_bytes, false);
     dad::Tape t;
-    dad::Trainer tr(mm, B, H, W, false, reinterpret_cast<cudaStream_t>(stream));
+    dad::Trainer tr(mm, B, H, W, mode, false, reinterpret_cast<cudaStream_t>(stream));
     return tr.backward(grad_depth, grad_feat, ar, t);
 }
 

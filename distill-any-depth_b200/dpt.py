@@ -150,6 +150,9 @@ class _NativeDepthModel(nn.Module):
         self._ws = None
         self._prepared = set()
         self.precision = "bf16"  # "bf16" (tensor cores) or "fp32" (verification mode)
+        # precision "bf16": False = inference forward (outputs detached); True = differentiable forward with a bf16
+        # activation tape and the tensor-core backward.  precision "fp32" is always differentiable under grad mode.
+        self.bf16_backward = False
 
     # -- key mapping: our state-dict key -> student-layout key understood by the library
     def _student_key(self, k):
@@ -212,14 +215,14 @@ class _NativeDepthModel(nn.Module):
         if self.precision not in _MODES:
             raise ValueError("precision must be 'bf16' or 'fp32'")
         mode = _MODES[self.precision]
-        if mode == 1 and captures is None and torch.is_grad_enabled():
+        if (mode == 1 or self.bf16_backward) and captures is None and torch.is_grad_enabled():
             live = [(k, p) for k, p in self.named_parameters()
                     if p.requires_grad and not any(u in k for u in self._UNUSED)]
             if live:
-                return _TrainForward.apply(self, x, tuple(k for k, _ in live), *[p for _, p in live])
+                return _TrainForward.apply(self, x, mode, tuple(k for k, _ in live), *[p for _, p in live])
         return self._run_native(x, mode, captures)
 
-    def _train_begin(self, x):
+    def _train_begin(self, x, mode):
         """dad_forward_train: same outputs as the inference forward, activations kept on a tape tensor."""
         B, _, H, W = x.shape
         lib = _lib.load()
@@ -227,10 +230,11 @@ class _NativeDepthModel(nn.Module):
             self._ensure_handle()
             self._sync_weights(x.device)
             st = _lib.stream_ptr()
-            if (1, H, W) not in self._prepared:
-                _lib.check(lib.dad_model_prepare(self._handle, 1, H, W, st), "dad_model_prepare")
-                self._prepared.add((1, H, W))
-            need = int(lib.dad_train_workspace_bytes(self._handle, B, H, W, 1))
+            for md in {mode, 1}:   # the bf16 backward still runs a few small contractions on the fp32 pack
+                if (md, H, W) not in self._prepared:
+                    _lib.check(lib.dad_model_prepare(self._handle, md, H, W, st), "dad_model_prepare")
+                    self._prepared.add((md, H, W))
+            need = int(lib.dad_train_workspace_bytes(self._handle, B, H, W, mode))
             if need == 0:
                 _lib.check(-1, "dad_train_workspace_bytes")
             tape = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
@@ -241,12 +245,12 @@ class _NativeDepthModel(nn.Module):
             D = ENCODERS[self._desc["encoder"]]["embed_dim"]
             depth = torch.empty(B, 1, H, W, dtype=torch.float32, device=x.device)
             feat = torch.empty(B, (H // 14) * (W // 14), D, dtype=torch.float32, device=x.device)
-            _lib.check(lib.dad_forward_train(self._handle, _lib.ptr(xin), B, H, W, 1, _lib.ptr(depth), _lib.ptr(feat),
+            _lib.check(lib.dad_forward_train(self._handle, _lib.ptr(xin), B, H, W, mode, _lib.ptr(depth), _lib.ptr(feat),
                                              ctypes.c_void_p(tape.data_ptr() + off), tape.numel() - off, st),
                        "dad_forward_train")
         return depth, feat, tape
 
-    def _train_backward(self, tape, shape, names, gdepth, gfeat):
+    def _train_backward(self, tape, shape, mode, names, gdepth, gfeat):
         """dad_backward: returns one fp32 gradient tensor per name (accumulated by the library from zero)."""
         B, H, W = shape
         lib = _lib.load()
@@ -265,7 +269,7 @@ class _NativeDepthModel(nn.Module):
                 off = (-tape.data_ptr()) % 1024
                 gd = gdepth.float().contiguous()
                 gf = None if gfeat is None else gfeat.float().contiguous()
-                _lib.check(lib.dad_backward(self._handle, B, H, W, 1, _lib.ptr(gd), _lib.ptr(gf),
+                _lib.check(lib.dad_backward(self._handle, B, H, W, mode, _lib.ptr(gd), _lib.ptr(gf),
                                             ctypes.c_void_p(tape.data_ptr() + off), tape.numel() - off, st), "dad_backward")
             finally:
                 for sk in registered:
@@ -309,12 +313,12 @@ class _NativeDepthModel(nn.Module):
 
 
 class _TrainForward(torch.autograd.Function):
-    """Differentiable fp32 forward: forward = dad_forward_train (tape), backward = dad_backward."""
+    """Differentiable forward: forward = dad_forward_train (activation tape), backward = dad_backward."""
 
     @staticmethod
-    def forward(ctx, model, x, names, *params):
-        depth, feat, tape = model._train_begin(x)
-        ctx.model, ctx.tape, ctx.names = model, tape, names
+    def forward(ctx, model, x, mode, names, *params):
+        depth, feat, tape = model._train_begin(x, mode)
+        ctx.model, ctx.tape, ctx.names, ctx.mode = model, tape, names, mode
         ctx.shape = (x.shape[0], x.shape[2], x.shape[3])
         ctx.versions = tuple(p._version for p in params)
         ctx.params = params
@@ -328,9 +332,9 @@ class _TrainForward(torch.autograd.Function):
             raise RuntimeError("a parameter was modified between the native forward and its backward")
         if gdepth is None:
             gdepth = torch.zeros(ctx.shape[0], 1, ctx.shape[1], ctx.shape[2], device=ctx.tape.device)
-        grads = ctx.model._train_backward(ctx.tape, ctx.shape, ctx.names, gdepth, gfeat)
+        grads = ctx.model._train_backward(ctx.tape, ctx.shape, ctx.mode, ctx.names, gdepth, gfeat)
         ctx.tape = None
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
 class DepthAnythingV2(_NativeDepthModel):

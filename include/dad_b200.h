@@ -176,6 +176,11 @@ int dad_gemm(const void* A, const void* W, const float* bias, float* out, int M,
  * or bf16 (out_bf16 / res_bf16); act: 0 none, 1 GELU(erf), 2 ReLU.  res may alias out (in-place residual). */
 int dad_gemm_ex(const void* A, const void* W, const float* bias, const float* gamma, const void* res, int res_bf16,
                 void* out, int out_bf16, int act, int M, int N, int K, int mode, void* stream);
+/* Weight-gradient GEMM of the bf16 backward: out[M,N] (fp32) += A[M,K] W[N,K]^T with both bf16 operands K-major with row
+ * pitch `lda` elements (zero beyond K); the K loop is split over `ksplit` work items per tile whose fp32 partial tiles
+ * are reduce-added through TMA.  zeros / ones: device vectors of N floats (the epilogue's bias / scale). */
+int dad_gemm_splitk(const void* A, const void* W, const float* zeros, const float* ones, float* out, int M, int N, int K,
+                    int lda, int ksplit, void* stream);
 /* conv3x3 / 1x1 (stride 1, zero padding) on NHWC input [B,H,W,C] with packed weights [Co, taps*Cp]. */
 int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
                   int Co, int taps, int mode, void* stream);
