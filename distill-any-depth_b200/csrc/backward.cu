@@ -607,6 +607,7 @@ int sgemm(const SGemm& g, cudaStream_t st) {
     }
     DAD_REQUIRE(static_cast<long long>(batch) * ksplit <= 65535 && cdiv(g.N, TN) <= 65535, "sgemm: grid too large");
     const dim3 grid(cdiv(g.M, TM), cdiv(g.N, TN), batch * ksplit);
+    debug_label("sgemm");
     ProfScope prof(PROF_GEMM_SIMT, 2.0 * g.M * g.N * static_cast<double>(g.K) * batch, st);
     sgemm_kernel<<<grid, 256, 0, st>>>(g, ksplit, kchunk);
     DAD_CHECK_LAUNCH();
@@ -617,6 +618,7 @@ int colsum(const void* X, int xbf, long long ldx, const void* Y, int ybf, long l
            const float* scale, void* scaled_out, cudaStream_t st) {
     DAD_REQUIRE(X && rows > 0 && N > 0 && (out || scaled_out), "colsum: bad arguments");
     const dim3 grid(cdiv(N, 32), static_cast<unsigned>(std::min<long long>(cdivl(rows, 64), 1024)));
+    debug_label("colsum");
     ProfScope prof(PROF_ELEM, static_cast<double>(rows) * N * 4 * (1 + (Y ? 1 : 0) + (scaled_out ? 1 : 0)), st);
     colsum_kernel<<<grid, 256, 0, st>>>(X, xbf, ldx, Y, ybf, ldy, rows, N, out, scale, scaled_out);
     DAD_CHECK_LAUNCH();
@@ -627,6 +629,7 @@ int layernorm_bwd(const float* x, const float* w, const void* dy, int dybf, floa
                   int out_period, int in_period, int in_offset, float eps, cudaStream_t st) {
     DAD_REQUIRE(x && w && dy && dx && D % 4 == 0 && D <= 2048, "layernorm_bwd: bad arguments (D=%d)", D);
     const unsigned grid = static_cast<unsigned>(std::min<long long>(cdivl(rows, 8), 4LL * num_sms()));
+    debug_label("layernorm_bwd");
     ProfScope prof(PROF_LN, static_cast<double>(rows) * D * 16, st);
     const int vpt = cdiv(D, 128);
 #define LNB(V) ln_bwd_kernel<V><<<grid, 256, 0, st>>>(x, w, dy, dybf, dx, dw, db, rows, D, out_period, in_period, in_offset, eps)
@@ -641,6 +644,7 @@ int layernorm_bwd(const float* x, const float* w, const void* dy, int dybf, floa
 
 int ls_residual(const float* xold, const void* y, int bf, const float* gamma, float* xnew, long long rows, int D, cudaStream_t st) {
     const long long n = rows * D;
+    debug_label("ls_residual");
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 12, st);
     ls_residual_kernel<<<blocks_for(n), 256, 0, st>>>(xold, y, bf, gamma, xnew, n, D);
     DAD_CHECK_LAUNCH();
@@ -648,6 +652,7 @@ int ls_residual(const float* xold, const void* y, int bf, const float* gamma, fl
 }
 
 int gelu_fwd(const void* pre, void* out, int bf, long long n, cudaStream_t st) {
+    debug_label("gelu_fwd");
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 8, st);
     gelu_fwd_kernel<<<blocks_for(n), 256, 0, st>>>(pre, out, bf, n);
     DAD_CHECK_LAUNCH();
@@ -655,6 +660,7 @@ int gelu_fwd(const void* pre, void* out, int bf, long long n, cudaStream_t st) {
 }
 
 int gelu_bwd(const void* pre, const void* dout, void* dpre, int bf, long long n, cudaStream_t st) {
+    debug_label("gelu_bwd");
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 12, st);
     gelu_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(pre, dout, dpre, bf, n);
     DAD_CHECK_LAUNCH();
@@ -662,6 +668,7 @@ int gelu_bwd(const void* pre, const void* dout, void* dpre, int bf, long long n,
 }
 
 int relu_bwd(const void* g, const void* y, const void* add, void* out, int bf, long long n, cudaStream_t st) {
+    debug_label("relu_bwd");
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * (add ? 16 : 12), st);
     relu_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(g, y, add, out, bf, n);
     DAD_CHECK_LAUNCH();
@@ -669,6 +676,7 @@ int relu_bwd(const void* g, const void* y, const void* add, void* out, int bf, l
 }
 
 int add_inplace(void* dst, int bf, const float* src, long long n, cudaStream_t st) {
+    debug_label("add_inplace");
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 12, st);
     add_kernel<<<blocks_for(n), 256, 0, st>>>(dst, bf, src, n);
     DAD_CHECK_LAUNCH();
@@ -676,6 +684,7 @@ int add_inplace(void* dst, int bf, const float* src, long long n, cudaStream_t s
 }
 
 int convert(const void* src, int src_bf16, void* dst, int dst_bf16, long long n, cudaStream_t st) {
+    debug_label("convert");
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * ((src_bf16 ? 2 : 4) + (dst_bf16 ? 2 : 4)), st);
     convert_kernel<<<blocks_for(n), 256, 0, st>>>(src, src_bf16, dst, dst_bf16, n);
     DAD_CHECK_LAUNCH();
@@ -683,6 +692,7 @@ int convert(const void* src, int src_bf16, void* dst, int dst_bf16, long long n,
 }
 
 int fill_f32(float* p, float v, long long n, cudaStream_t st) {
+    debug_label("fill_f32");
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 4, st);
     fill_kernel<<<blocks_for(n), 256, 0, st>>>(p, v, n);
     DAD_CHECK_LAUNCH();
@@ -693,6 +703,7 @@ int transpose_pad(const void* in, long long ld, int R, int C, void* out, int Rp,
     DAD_REQUIRE(in && out && R > 0 && C > 0 && Rp >= R, "transpose_pad: bad arguments");
     const dim3 grid(cdiv(Rp, 32), cdiv(C, 32));
     DAD_REQUIRE(grid.y <= 65535, "transpose_pad: too many columns");
+    debug_label("transpose_pad");
     ProfScope prof(PROF_ELEM, (static_cast<double>(R) + Rp) * C * 2, st);
     transpose_pad_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(in), ld, R, C, reinterpret_cast<bf16*>(out), Rp);
     DAD_CHECK_LAUNCH();
@@ -704,6 +715,7 @@ int im2colT(const void* X, int B, int H, int W, int Ci, int taps, int stride, in
     const long long P = static_cast<long long>(B) * Ho * Wo;
     DAD_REQUIRE(X && out && Pp >= P && (taps == 1 || taps == 9), "im2colT: bad arguments");
     const dim3 grid(static_cast<unsigned>(cdivl(Pp, 32)), cdiv(Ci, 32), taps);
+    debug_label("im2colT");
     ProfScope prof(PROF_ELEM, static_cast<double>(Pp) * Ci * taps * 4, st);
     im2colT_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(X), H, W, Ci, taps, stride, Ho, Wo, P,
                                          reinterpret_cast<bf16*>(out), Pp);
@@ -713,6 +725,7 @@ int im2colT(const void* X, int B, int H, int W, int Ci, int taps, int stride, in
 
 int pack_linear_T(const float* w, void* out, int N, int K, int Np, cudaStream_t st) {
     const dim3 grid(cdiv(Np, 32), cdiv(K, 32));
+    debug_label("pack_linear_T");
     ProfScope prof(PROF_ELEM, static_cast<double>(N) * K * 6, st);
     pack_linear_T_kernel<<<grid, 256, 0, st>>>(w, reinterpret_cast<bf16*>(out), N, K, Np);
     DAD_CHECK_LAUNCH();
@@ -720,6 +733,7 @@ int pack_linear_T(const float* w, void* out, int N, int K, int Np, cudaStream_t 
 }
 
 int head1x1_any(const void* in, int bf, const float* w, float bias, float* out, long long P, cudaStream_t st) {
+    debug_label("head1x1_any");
     ProfScope prof(PROF_ELEM, static_cast<double>(P) * (32 * (bf ? 2 : 4) + 4), st);
     head1x1_any_kernel<<<blocks_for(P), 256, 0, st>>>(in, bf, w, bias, out, P);
     DAD_CHECK_LAUNCH();
@@ -727,6 +741,7 @@ int head1x1_any(const void* in, int bf, const float* w, float bias, float* out, 
 }
 
 int softmax_rows(float* S, long long rows, int T, cudaStream_t st) {
+    debug_label("softmax_rows");
     ProfScope prof(PROF_ELEM, static_cast<double>(rows) * T * 8, st);
     softmax_rows_kernel<<<blocks_for(rows * 32), 256, 0, st>>>(S, rows, T);
     DAD_CHECK_LAUNCH();
@@ -734,6 +749,7 @@ int softmax_rows(float* S, long long rows, int T, cudaStream_t st) {
 }
 
 int softmax_bwd_rows(const float* P, float* dP, long long rows, int T, cudaStream_t st) {
+    debug_label("softmax_bwd_rows");
     ProfScope prof(PROF_ELEM, static_cast<double>(rows) * T * 12, st);
     softmax_bwd_rows_kernel<<<blocks_for(rows * 32), 256, 0, st>>>(P, dP, rows, T);
     DAD_CHECK_LAUNCH();
@@ -745,6 +761,7 @@ int bilinear_bwd(const void* gout, int bf, float* gin, int B, int Hi, int Wi, in
     const float sh = Ho > 1 ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.f;
     const float sw = Wo > 1 ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.f;
     const long long total = static_cast<long long>(B) * Ho * Wo * (C / 4);
+    debug_label("bilinear_bwd");
     ProfScope prof(PROF_ELEM, static_cast<double>(B) * C * 4 * (static_cast<double>(Hi) * Wi + static_cast<double>(Ho) * Wo), st);
     bilinear_bwd_kernel<<<blocks_for(total), 256, 0, st>>>(gout, bf, gin, B, Hi, Wi, Ho, Wo, C, sh, sw);
     DAD_CHECK_LAUNCH();
@@ -754,6 +771,7 @@ int bilinear_bwd(const void* gout, int bf, float* gin, int B, int Hi, int Wi, in
 int head_bwd(const float* gdepth, const float* depth, const void* t32, int bf, const float* w2, void* dt32, float* dw2, float* db2,
              long long P, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>(std::min<long long>(cdivl(P, 256), 8LL * num_sms()));
+    debug_label("head_bwd");
     ProfScope prof(PROF_ELEM, static_cast<double>(P) * (8 + 256), st);
     head_bwd_kernel<<<grid, 256, 0, st>>>(gdepth, depth, t32, bf, w2, dt32, dw2, db2, P);
     DAD_CHECK_LAUNCH();
@@ -762,6 +780,7 @@ int head_bwd(const float* gdepth, const float* depth, const void* t32, int bf, c
 
 int convT_gather(const float* dout, float* G, int B, int H, int W, int k, int Co, int CoP, cudaStream_t st) {
     const long long total = static_cast<long long>(B) * H * W * k * k * CoP;
+    debug_label("convT_gather");
     ProfScope prof(PROF_ELEM, static_cast<double>(total) * 8, st);
     convT_gather_kernel<<<blocks_for(total), 256, 0, st>>>(dout, G, B, H, W, k, Co, CoP);
     DAD_CHECK_LAUNCH();
@@ -771,6 +790,7 @@ int convT_gather(const float* dout, float* G, int B, int H, int W, int k, int Co
 int col2im_s2(const float* dcol, float* din, int B, int H, int W, int C, int Cp, cudaStream_t st) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = static_cast<long long>(B) * H * W * C;
+    debug_label("col2im_s2");
     ProfScope prof(PROF_ELEM, static_cast<double>(total) * 4 + static_cast<double>(B) * Ho * Wo * 9 * Cp * 4, st);
     col2im_s2_kernel<<<blocks_for(total), 256, 0, st>>>(dcol, din, B, H, W, C, Cp, Ho, Wo);
     DAD_CHECK_LAUNCH();
@@ -779,6 +799,7 @@ int col2im_s2(const float* dcol, float* din, int B, int H, int W, int C, int Cp,
 
 int pack_conv_dgrad(const float* w, void* out, int bf, int Co, int Ci, int taps, int CoP, cudaStream_t st) {
     const long long total = static_cast<long long>(Ci) * taps * CoP;
+    debug_label("pack_conv_dgrad");
     ProfScope prof(PROF_ELEM, static_cast<double>(total) * 8, st);
     pack_conv_dgrad_kernel<<<blocks_for(total), 256, 0, st>>>(w, out, bf, Co, Ci, taps, CoP);
     DAD_CHECK_LAUNCH();
@@ -787,6 +808,7 @@ int pack_conv_dgrad(const float* w, void* out, int bf, int Co, int Ci, int taps,
 
 int batch_sum_rows(const float* G, float* dtab, int B, int T, int D, cudaStream_t st) {
     const long long n = static_cast<long long>(T) * D;
+    debug_label("batch_sum_rows");
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 4 * (B + 1), st);
     batch_sum_rows_kernel<<<blocks_for(n), 256, 0, st>>>(G, dtab, B, T, D);
     DAD_CHECK_LAUNCH();
@@ -798,6 +820,7 @@ int pos_table_bwd(const float* dtab, float* dpos, float* dcls, float* dpbias, in
     const int ph = H / 14, pw = W / 14;
     const int identity = (ph * pw == S * S && H == W) ? 1 : 0;
     const double sfy = (static_cast<double>(ph) + 0.1) / S, sfx = (static_cast<double>(pw) + 0.1) / S;
+    debug_label("pos_table_bwd");
     ProfScope prof(PROF_ELEM, static_cast<double>(1 + ph * pw) * D * 8, st);
     pos_table_bwd_kernel<<<1 + ph * pw, 256, 0, st>>>(dtab, dpos, dcls, dpbias, D, S, ph, pw, identity,
                                                       static_cast<float>(1.0 / sfy), static_cast<float>(1.0 / sfx));

@@ -75,6 +75,12 @@ def main():
         ours = sorted((float((g32[k] - o32[k]).norm() / (o32[k].norm() + 1e-30)), k) for k in o32 if o32[k] is not None)
         print("our fp32 engine vs torch fp32 (GPU): median l2 %.3e, worst %.3e (%s)" % (ours[len(ours) // 2][0], ours[-1][0], ours[-1][1]))
     # timings
+    if os.environ.get("DAD_DEBUG_TIME"):
+        m.precision = "bf16"
+        print("=== per-launch timing of one bf16 train step", file=sys.stderr, flush=True)
+        grads_of(m, x, wd, wf)
+        torch.cuda.synchronize()
+        return
     import ctypes
     lib = _lib.load()
     names = ["gemm_tc", "gemm_simt", "attention", "layernorm", "elementwise", "loss"]

@@ -146,3 +146,76 @@ def test_frozen_parameters_and_no_grad_paths():
     m.precision = "bf16"
     d2, _ = m(x)
     assert not d2.requires_grad   # tensor-core forward is inference-only
+
+
+# ----------------------------------------------------------------------------------------------- bf16 (tensor-core) training path
+def _grads(m, x, wd, wf):
+    for p in m.parameters():
+        p.grad = None
+    depth, feat = m(x)
+    _objective(depth, feat, wd, wf).backward()
+    return depth.detach(), feat.detach(), {k: p.grad for k, p in m.named_parameters()}
+
+
+@pytest.mark.parametrize("preset,B,H,W", [("vits", 2, 70, 98), ("vitb", 2, 224, 224)])
+def test_bf16_backward_matches_fp32_engine_at_bf16_tolerance(preset, B, H, W):
+    """precision='bf16' + bf16_backward: bf16 activation tape, tcgen05 data / weight gradient GEMMs (split-K, TMA reduce-add).
+    Yardstick (measured, tests/gpu_bwd_probe.py): torch.autocast(bf16) of the reference graph deviates from its own fp32
+    gradients by 2.6e-2 (median over parameters) / 6.8e-2 (worst) in relative L2; ours 2.7e-2 / 6.3e-2 .. 9e-2.
+    Gate: every parameter's gradient has cosine >= 0.99 and relative L2 error <= 0.15 against the fp32 engine (itself
+    pinned to autograd above), median <= 5e-2; depth within the north-star 2e-2."""
+    d = dad()
+    kw = synthetic.MODEL_PRESETS[preset]
+    sd = synthetic.make_state_dict(seed=0, **kw)
+    x = synthetic.make_images(B, H, W, seed=77).cuda()
+    g = torch.Generator().manual_seed(5)
+    D = sd["pretrained.cls_token"].shape[-1]
+    wd = torch.randn(B, 1, H, W, generator=g).cuda()
+    wf = (torch.randn(B, (H // 14) * (W // 14), D, generator=g) * 0.05).cuda()
+    m = d.DepthAnythingV2(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    m.precision = "fp32"
+    d32, f32, g32 = _grads(m, x, wd, wf)
+    m.precision = "bf16"
+    m.bf16_backward = True
+    d16, f16, g16 = _grads(m, x, wd, wf)
+    den = d32.abs().clamp(min=0.1 * float(d32.abs().max()))
+    assert float(((d16 - d32).abs() / den).max()) <= 2e-2
+    l2s, bad = [], []
+    for k, r in g32.items():
+        if r is None:
+            assert g16[k] is None
+            continue
+        a = g16[k]
+        assert a is not None and torch.isfinite(a).all(), k
+        l2 = float((a - r).norm() / (r.norm() + 1e-30))
+        cos = float((a * r).sum() / (a.norm() * r.norm() + 1e-30))
+        l2s.append(l2)
+        if not (l2 <= 0.15 and cos >= 0.99):
+            bad.append((k, l2, cos))
+    l2s.sort()
+    _log(f"bf16_{preset}_{B}x{H}x{W}", dict(median_l2=l2s[len(l2s) // 2], worst_l2=l2s[-1], n_bad=len(bad), bad=bad[:20]))
+    assert not bad, bad[:8]
+    assert l2s[len(l2s) // 2] <= 5e-2
+
+
+def test_split_k_weight_gradient_gemm():
+    """dad_gemm_splitk: out += A W^T with the K loop split over work items that reduce-add fp32 partial tiles through TMA."""
+    from distill_any_depth_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    z, o = torch.zeros(8192, device="cuda"), torch.ones(8192, device="cuda")
+    for (M, N, K, ks) in [(768, 768, 1570, 4), (32, 576, 20000, 16), (3072, 768, 1570, 2), (96, 384, 333, 3), (128, 128, 64, 2)]:
+        lda = (K + 63) // 64 * 64
+        A = torch.zeros(M, lda)
+        A[:, :K] = torch.randn(M, K, generator=g)
+        Wt = torch.zeros(N, lda)
+        Wt[:, :K] = torch.randn(N, K, generator=g)
+        Ab, Wb = A.cuda().bfloat16().contiguous(), Wt.cuda().bfloat16().contiguous()
+        out0 = torch.randn(M, N, generator=g).cuda()
+        out = out0.clone()
+        _lib.check(lib.dad_gemm_splitk(_lib.ptr(Ab), _lib.ptr(Wb), _lib.ptr(z), _lib.ptr(o), _lib.ptr(out), M, N, K, lda, ks,
+                                       _lib.stream_ptr()), "dad_gemm_splitk")
+        ref = out0.double() + Ab.double() @ Wb.double().t()
+        assert float((out.double() - ref).abs().max() / ref.abs().max()) <= 2e-5, (M, N, K, ks)
