@@ -301,53 +301,83 @@ __global__ void __launch_bounds__(256) convert_kernel(const void* src, int sbf, 
     if (i < n) stf(dst, i, dbf, ldf(src, i, sbf));
 }
 
-// out[c][r] = in[r * ld + c] for r < R (0 for R <= r < Rp): K-major operands of the weight-gradient GEMMs
-__global__ void __launch_bounds__(256) transpose_pad_kernel(const bf16* in, long long ld, int R, int C, bf16* out, int Rp) {
-    __shared__ bf16 tile[32][33];
-    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+// ---- bf16 tile transposes (64 x 64 tiles, 4-byte accesses on both sides) -------------------------------------------
+// T64 stages a [64 rows][64 cols] tile; lanes read column PAIRS of one source row and write row PAIRS of one output row.
+struct T64 {
+    bf16 t[64][66];
+};
+__device__ __forceinline__ void t64_store_rows(T64& s, int row, int lane, __nv_bfloat162 v) {
+    s.t[row][2 * lane] = __low2bfloat16(v);
+    s.t[row][2 * lane + 1] = __high2bfloat16(v);
+}
+// out_row: pointer to output row c at element offset r0; writes elements r0 + 2*lane, +1 when < rlimit (rlimit even)
+__device__ __forceinline__ void t64_write_col(const T64& s, int c, int lane, bf16* out_row, int rlimit_local) {
+    if (2 * lane < rlimit_local) {
+        __nv_bfloat162 v;
+        v.x = s.t[2 * lane][c];
+        v.y = s.t[2 * lane + 1][c];
+        *reinterpret_cast<__nv_bfloat162*>(out_row + 2 * lane) = v;
+    }
+}
+
+// out[z][c][r] = in[z][r * ld + c] for r < R (0 for R <= r < Rp); z = blockIdx.z with element strides zin / zout.
+// R, Rp, ld even; C even.  K-major operands of the weight-gradient GEMMs and the attention-backward transposes.
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const bf16* in, long long ld, int R, int C, bf16* out, int Rp,
+                                                            long long zin, long long zout) {
+    __shared__ T64 s;
+    in += blockIdx.z * zin;
+    out += blockIdx.z * zout;
+    const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = r0 + ty + i * 8, c = c0 + tx;
-        tile[ty + i * 8][tx] = (r < R && c < C) ? in[r * ld + c] : __float2bfloat16_rn(0.f);
+    for (int i = 0; i < 8; ++i) {
+        const int rr = w + i * 8, r = r0 + rr, c = c0 + 2 * lane;
+        __nv_bfloat162 v = zero2;
+        if (r < R && c < C) v = *reinterpret_cast<const __nv_bfloat162*>(in + r * ld + c);
+        t64_store_rows(s, rr, lane, v);
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + i * 8, r = r0 + tx;
-        if (c < C && r < Rp) out[static_cast<long long>(c) * Rp + r] = tile[tx][ty + i * 8];
+    for (int i = 0; i < 8; ++i) {
+        const int cc = w + i * 8, c = c0 + cc;
+        if (c < C) t64_write_col(s, cc, lane, out + static_cast<long long>(c) * Rp + r0, Rp - r0);
     }
 }
 
 // out[(c * taps + tap)][p] = window(X)[p, tap, c], p = output pixel (b, oy, ox); 0 for P <= p < Pp and outside the image
 __global__ void __launch_bounds__(256) im2colT_kernel(const bf16* X, int H, int W, int Ci, int taps, int stride, int Ho, int Wo,
                                                       long long P, bf16* out, long long Pp) {
-    __shared__ bf16 tile[32][33];
-    const long long p0 = static_cast<long long>(blockIdx.x) * 32;
-    const int c0 = blockIdx.y * 32, tap = blockIdx.z;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __shared__ T64 s;
+    const long long p0 = static_cast<long long>(blockIdx.x) * 64;
+    const int c0 = blockIdx.y * 64, tap = blockIdx.z;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int dy = taps == 9 ? tap / 3 - 1 : 0, dx = taps == 9 ? tap % 3 - 1 : 0;
     const long long hw = static_cast<long long>(Ho) * Wo;
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const long long p = p0 + ty + i * 8;
-        const int c = c0 + tx;
-        bf16 v = __float2bfloat16_rn(0.f);
+    for (int i = 0; i < 8; ++i) {
+        const int rr = w + i * 8;
+        const long long p = p0 + rr;
+        const int c = c0 + 2 * lane;
+        __nv_bfloat162 v = zero2;
         if (p < P && c < Ci) {
             const int b = static_cast<int>(p / hw);
             const int r = static_cast<int>(p - b * hw);
             const int oy = r / Wo, ox = r - oy * Wo;
             const int y = oy * stride + dy, x = ox * stride + dx;
-            if (y >= 0 && y < H && x >= 0 && x < W) v = X[((static_cast<long long>(b) * H + y) * W + x) * Ci + c];
+            if (y >= 0 && y < H && x >= 0 && x < W)
+                v = *reinterpret_cast<const __nv_bfloat162*>(X + ((static_cast<long long>(b) * H + y) * W + x) * Ci + c);
         }
-        tile[ty + i * 8][tx] = v;
+        t64_store_rows(s, rr, lane, v);
     }
     __syncthreads();
+    const long long rem = Pp - p0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + i * 8;
-        const long long p = p0 + tx;
-        if (c < Ci && p < Pp) out[(static_cast<long long>(c) * taps + tap) * Pp + p] = tile[tx][ty + i * 8];
+    for (int i = 0; i < 8; ++i) {
+        const int cc = w + i * 8, c = c0 + cc;
+        if (c < Ci)
+            t64_write_col(s, cc, lane, out + (static_cast<long long>(c) * taps + tap) * Pp + p0, rem > 64 ? 64 : static_cast<int>(rem));
     }
 }
 
@@ -369,17 +399,89 @@ __global__ void __launch_bounds__(256) pack_linear_T_kernel(const float* w, bf16
     }
 }
 
+// P = softmax(S) row-wise, S fp32 [rows][ld] -> P bf16 [rows][ld] (columns >= T zeroed)
+__global__ void __launch_bounds__(256) softmax_rows_bf16_kernel(const float* S, bf16* P, long long rows, int T, int ld) {
+    const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* row = S + r * ld;
+    bf16* out = P + r * ld;
+    float m = -INFINITY;
+    for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = 0.f;
+    for (int j = lane; j < T; j += 32) l += expf(row[j] - m);
+    for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float inv = 1.f / l;
+    for (int j = lane; j < ld; j += 32) out[j] = __float2bfloat16_rn(j < T ? expf(row[j] - m) * inv : 0.f);
+}
+
+// dS = P * (dP - sum_j P dP) row-wise: P bf16, dP fp32 -> dS bf16 (columns >= T zeroed)
+__global__ void __launch_bounds__(256) softmax_bwd_bf16_kernel(const bf16* P, const float* dP, bf16* dS, long long rows, int T, int ld) {
+    const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const bf16* p = P + r * ld;
+    const float* d = dP + r * ld;
+    bf16* o = dS + r * ld;
+    float s = 0.f;
+    for (int j = lane; j < T; j += 32) s = fmaf(__bfloat162float(p[j]), d[j], s);
+    for (int o2 = 16; o2; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+    for (int j = lane; j < ld; j += 32) o[j] = __float2bfloat16_rn(j < T ? __bfloat162float(p[j]) * (d[j] - s) : 0.f);
+}
+
+// per problem z: src fp32 [T][ld] -> dstN bf16 [T][ld] (same layout; columns >= T zeroed) and / or dstT bf16 [T][ld] (transposed)
+__global__ void __launch_bounds__(256) cvt_tiles_kernel(const float* src, bf16* dstN, bf16* dstT, int T, int ld) {
+    __shared__ float tile[32][33];
+    const long long zo = static_cast<long long>(blockIdx.z) * T * ld;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + i * 8, c = c0 + tx;
+        const float v = (r < T && c < T) ? src[zo + static_cast<long long>(r) * ld + c] : 0.f;
+        tile[ty + i * 8][tx] = v;
+        if (dstN && r < T && c < ld) dstN[zo + static_cast<long long>(r) * ld + c] = __float2bfloat16_rn(v);
+    }
+    if (!dstT) return;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + i * 8, r = r0 + tx;   // dstT[c][r] = src[r][c]
+        if (c < T && r < ld) dstT[zo + static_cast<long long>(c) * ld + r] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+    }
+}
+
+// per (image b, head h): dst[(b*heads + h)][d][t] = src[(b*T + t) * lds + h*64 + d], t < T (zero for T <= t < ld), d < 64
+__global__ void __launch_bounds__(256) head_transpose_kernel(const bf16* src, long long lds, bf16* dst, int T, int heads, int ld) {
+    __shared__ bf16 tile[32][33];
+    const int z = blockIdx.z, b = z / heads, h = z - b * heads;
+    const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + ty + i * 8;
+        tile[ty + i * 8][tx] = t < T ? src[(static_cast<long long>(b) * T + t) * lds + h * 64 + d0 + tx] : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int d = d0 + ty + i * 8, t = t0 + tx;
+        if (t < ld) dst[(static_cast<long long>(z) * 64 + d) * ld + t] = tile[tx][ty + i * 8];
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_kernel(float* p, float v, long long n) {
     const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
     if (i < n) p[i] = v;
 }
 
 // ---------------------------------------------------------------- attention probabilities
-__global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long rows, int T) {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long rows, int T, int ld) {
     const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
-    float* row = S + r * T;
+    float* row = S + r * ld;
     float m = -INFINITY;
     for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -390,12 +492,12 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long r
     for (int j = lane; j < T; j += 32) row[j] *= inv;
 }
 
-__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* P, float* dP, long long rows, int T) {
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* P, float* dP, long long rows, int T, int ld) {
     const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
-    const float* p = P + r * T;
-    float* d = dP + r * T;
+    const float* p = P + r * ld;
+    float* d = dP + r * ld;
     float s = 0.f;
     for (int j = lane; j < T; j += 32) s = fmaf(p[j], d[j], s);
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -699,13 +801,55 @@ int fill_f32(float* p, float v, long long n, cudaStream_t st) {
     return DAD_OK;
 }
 
+int softmax_rows_bf16(const float* S, void* P, long long rows, int T, int ld, cudaStream_t st) {
+    debug_label("softmax_rows_bf16");
+    ProfScope prof(PROF_ELEM, static_cast<double>(rows) * ld * 6, st);
+    softmax_rows_bf16_kernel<<<blocks_for(rows * 32), 256, 0, st>>>(S, reinterpret_cast<bf16*>(P), rows, T, ld);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int softmax_bwd_bf16(const void* P, const float* dP, void* dS, long long rows, int T, int ld, cudaStream_t st) {
+    debug_label("softmax_bwd_bf16");
+    ProfScope prof(PROF_ELEM, static_cast<double>(rows) * ld * 8, st);
+    softmax_bwd_bf16_kernel<<<blocks_for(rows * 32), 256, 0, st>>>(reinterpret_cast<const bf16*>(P), dP, reinterpret_cast<bf16*>(dS), rows, T, ld);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int cvt_tiles(const float* src, void* dstN, void* dstT, int Z, int T, int ld, cudaStream_t st) {
+    DAD_REQUIRE(src && (dstN || dstT) && Z > 0 && Z <= 65535 && ld >= T, "cvt_tiles: bad arguments");
+    const dim3 grid(cdiv(ld, 32), cdiv(ld, 32), Z);
+    debug_label("cvt_tiles");
+    ProfScope prof(PROF_ELEM, static_cast<double>(Z) * T * ld * (4 + (dstN ? 2 : 0) + (dstT ? 2 : 0)), st);
+    cvt_tiles_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<bf16*>(dstN), reinterpret_cast<bf16*>(dstT), T, ld);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int head_transpose(const void* src, long long lds, void* dst, int B, int T, int heads, int ld, cudaStream_t st) {
+    DAD_REQUIRE(src && dst && B * heads <= 65535 && ld >= T, "head_transpose: bad arguments");
+    const dim3 grid(cdiv(ld, 32), 2, B * heads);
+    debug_label("head_transpose");
+    ProfScope prof(PROF_ELEM, static_cast<double>(B) * heads * 64 * (T + ld) * 2, st);
+    head_transpose_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(src), lds, reinterpret_cast<bf16*>(dst), T, heads, ld);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
 int transpose_pad(const void* in, long long ld, int R, int C, void* out, int Rp, cudaStream_t st) {
-    DAD_REQUIRE(in && out && R > 0 && C > 0 && Rp >= R, "transpose_pad: bad arguments");
-    const dim3 grid(cdiv(Rp, 32), cdiv(C, 32));
+    return transpose_pad_batched(in, ld, R, C, out, Rp, 1, 0, 0, st);
+}
+
+int transpose_pad_batched(const void* in, long long ld, int R, int C, void* out, int Rp, int Z, long long zin, long long zout,
+                          cudaStream_t st) {
+    DAD_REQUIRE(in && out && R > 0 && C > 0 && Rp >= R && Z > 0 && Z <= 65535, "transpose_pad: bad arguments");
+    DAD_REQUIRE(ld % 2 == 0 && C % 2 == 0 && Rp % 2 == 0 && zin % 2 == 0 && zout % 2 == 0, "transpose_pad: odd extents");
+    const dim3 grid(cdiv(Rp, 64), cdiv(C, 64), Z);
     DAD_REQUIRE(grid.y <= 65535, "transpose_pad: too many columns");
     debug_label("transpose_pad");
-    ProfScope prof(PROF_ELEM, (static_cast<double>(R) + Rp) * C * 2, st);
-    transpose_pad_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(in), ld, R, C, reinterpret_cast<bf16*>(out), Rp);
+    ProfScope prof(PROF_ELEM, (static_cast<double>(R) + Rp) * C * 2 * Z, st);
+    transpose_pad_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(in), ld, R, C, reinterpret_cast<bf16*>(out), Rp, zin, zout);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
@@ -713,8 +857,8 @@ int transpose_pad(const void* in, long long ld, int R, int C, void* out, int Rp,
 int im2colT(const void* X, int B, int H, int W, int Ci, int taps, int stride, int Ho, int Wo, void* out, long long Pp,
             cudaStream_t st) {
     const long long P = static_cast<long long>(B) * Ho * Wo;
-    DAD_REQUIRE(X && out && Pp >= P && (taps == 1 || taps == 9), "im2colT: bad arguments");
-    const dim3 grid(static_cast<unsigned>(cdivl(Pp, 32)), cdiv(Ci, 32), taps);
+    DAD_REQUIRE(X && out && Pp >= P && (taps == 1 || taps == 9) && Ci % 2 == 0 && Pp % 2 == 0, "im2colT: bad arguments");
+    const dim3 grid(static_cast<unsigned>(cdivl(Pp, 64)), cdiv(Ci, 64), taps);
     debug_label("im2colT");
     ProfScope prof(PROF_ELEM, static_cast<double>(Pp) * Ci * taps * 4, st);
     im2colT_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(X), H, W, Ci, taps, stride, Ho, Wo, P,
@@ -740,18 +884,18 @@ int head1x1_any(const void* in, int bf, const float* w, float bias, float* out, 
     return DAD_OK;
 }
 
-int softmax_rows(float* S, long long rows, int T, cudaStream_t st) {
+int softmax_rows(float* S, long long rows, int T, int ld, cudaStream_t st) {
     debug_label("softmax_rows");
     ProfScope prof(PROF_ELEM, static_cast<double>(rows) * T * 8, st);
-    softmax_rows_kernel<<<blocks_for(rows * 32), 256, 0, st>>>(S, rows, T);
+    softmax_rows_kernel<<<blocks_for(rows * 32), 256, 0, st>>>(S, rows, T, ld);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 
-int softmax_bwd_rows(const float* P, float* dP, long long rows, int T, cudaStream_t st) {
+int softmax_bwd_rows(const float* P, float* dP, long long rows, int T, int ld, cudaStream_t st) {
     debug_label("softmax_bwd_rows");
     ProfScope prof(PROF_ELEM, static_cast<double>(rows) * T * 12, st);
-    softmax_bwd_rows_kernel<<<blocks_for(rows * 32), 256, 0, st>>>(P, dP, rows, T);
+    softmax_bwd_rows_kernel<<<blocks_for(rows * 32), 256, 0, st>>>(P, dP, rows, T, ld);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

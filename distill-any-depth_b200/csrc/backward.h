@@ -47,14 +47,24 @@ int convert(const void* src, int src_bf16, void* dst, int dst_bf16, long long n,
 int fill_f32(float* p, float v, long long n, cudaStream_t st);
 // bf16 only: out[c][r] = in[r*ld + c] (r < R; zero for R <= r < Rp) - K-major operands of the weight-gradient GEMMs
 int transpose_pad(const void* in, long long ld, int R, int C, void* out, int Rp, cudaStream_t st);
+// the same for Z problems (element strides zin / zout between them)
+int transpose_pad_batched(const void* in, long long ld, int R, int C, void* out, int Rp, int Z, long long zin, long long zout,
+                          cudaStream_t st);
 // bf16 only: out[(c*taps + tap)][p] = window(X)[p, tap, c] over output pixels p (zero padded to Pp columns)
 int im2colT(const void* X, int B, int H, int W, int Ci, int taps, int stride, int Ho, int Wo, void* out, long long Pp, cudaStream_t st);
 // w [N][K] fp32 -> out [K][Np] bf16
 int pack_linear_T(const float* w, void* out, int N, int K, int Np, cudaStream_t st);
 int head1x1_any(const void* in, int bf, const float* w, float bias, float* out, long long P, cudaStream_t st);
 // row-wise softmax of S [rows, T] in place; and dS = P * (dP - sum_j P*dP) in place of dP
-int softmax_rows(float* S, long long rows, int T, cudaStream_t st);
-int softmax_bwd_rows(const float* P, float* dP, long long rows, int T, cudaStream_t st);
+int softmax_rows(float* S, long long rows, int T, int ld, cudaStream_t st);
+int softmax_bwd_rows(const float* P, float* dP, long long rows, int T, int ld, cudaStream_t st);
+// bf16 engine: P = softmax(S) (fp32 -> bf16), dS = P * (dP - sum P dP) (bf16, fp32 -> bf16); pad columns [T, ld) zeroed
+int softmax_rows_bf16(const float* S, void* P, long long rows, int T, int ld, cudaStream_t st);
+int softmax_bwd_bf16(const void* P, const float* dP, void* dS, long long rows, int T, int ld, cudaStream_t st);
+// Z problems of [T][ld] fp32 -> bf16 copy in the same layout (dstN) and / or transposed (dstT); pad columns zeroed
+int cvt_tiles(const float* src, void* dstN, void* dstT, int Z, int T, int ld, cudaStream_t st);
+// bf16: dst[(b*heads + h)][d][t] = src[(b*T + t)*lds + h*64 + d] (64 x ld per problem, zero for t >= T)
+int head_transpose(const void* src, long long lds, void* dst, int B, int T, int heads, int ld, cudaStream_t st);
 // adjoint of bilinear_nhwc (align_corners=True): gin [B,Hi,Wi,C] must be zero-filled by the caller
 int bilinear_bwd(const void* gout, int bf, float* gin, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st);
 // output head: depth = relu(dot(t32, w2) + b2), t32 = relu(conv + b) saved.  dt32 [P,32]; dw2 [32] / db2 [1] accumulate

@@ -57,6 +57,16 @@ struct GemmProblem {
     int Kp = 0;               // padded K (row length of Wt)
     int ksplit = 1;           // gemm_tc, linear, `out += gamma * (acc + bias)` epilogue only: split the K loop over this many
                               // work items per tile, each reduce-adding its partial product (weight-gradient GEMMs: K = tokens)
+    // gemm_tc, linear, generic epilogue only: a BATCH of independent problems z = b * batch_h + h (attention backward: one per
+    // image and head).  M / N / K / Kp are per problem; operand element strides per head / image; Wt has `w_rows` valid rows
+    // (<= N; rows beyond are zero-filled, so N can be padded).  Output element (row, col) of problem (b, h) goes to
+    // out[(b * c_row_b + h * c_row_h + row) * ldc + h * c_col_h + col].
+    int batch_h = 0, batch_b = 0;
+    long long a_sh = 0, a_sb = 0, w_sh = 0, w_sb = 0;
+    int w_rows = 0;
+    long long ldw = 0;        // batched only: elements between rows of Wt (0 = Kp)
+    long long c_row_b = 0, c_row_h = 0;
+    int c_col_h = 0;
     Epilogue epi;
 };
 

@@ -44,6 +44,8 @@ struct TcArgs {
     int tiles_x, tiles_y;
     int num_m_tiles, num_n_tiles;
     int ksplit, kb_per_split;  // split-K (linear + TMA reduce-add epilogue only): work item = (k slice, tile)
+    int batch_h, mt_per_batch, rows_per_batch, c_col_h;   // batched linear problems (batch_h > 0): m tile -> (image, head, local tile)
+    long long c_row_b, c_row_h;
     double flops;           // algorithmic 2*M*N*K of this launch (host-side bookkeeping only)
 };
 
@@ -178,6 +180,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (g.taps == 9) { dy = tap / 3; dx = tap - dy * 3; }
                         ptx::tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], cc * BK,
                                          x0 * g.stride + dx - g.pad, y0 * g.stride + dy - g.pad, b);
+                    } else if (g.batch_h) {
+                        const int z = mt / g.mt_per_batch, zb = z / g.batch_h;
+                        ptx::tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, (mt - z * g.mt_per_batch) * BM,
+                                         z - zb * g.batch_h, zb);
+                        ptx::tma_load_4d(sB + stage * C::B_STAGE_BYTES, &tmB, &full[stage], kb * BK, n0, z - zb * g.batch_h, zb);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
                     } else {
                         ptx::tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, mt * BM);
                     }
@@ -287,9 +296,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     grow = (static_cast<long long>(cb) * g.H + y) * g.W + x;
                     return (y < g.H) && (x < g.W);
                 }
+                if (g.batch_h) {
+                    const int z = mt / g.mt_per_batch, zb = z / g.batch_h;
+                    const int lr = (mt - z * g.mt_per_batch) * BM + r;
+                    grow = zb * g.c_row_b + (z - zb * g.batch_h) * g.c_row_h + lr;
+                    return lr < g.rows_per_batch;
+                }
                 grow = static_cast<long long>(mt) * BM + r;
                 return grow < g.M;
             };
+            int col_shift = 0;   // batched problems: per-head column offset of the output
+            if (g.batch_h) {
+                const int z = mt / g.mt_per_batch;
+                col_shift = (z - (z / g.batch_h) * g.batch_h) * g.c_col_h;
+            }
             ptx::mbar_wait(&tfull[as], aphase);
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
@@ -362,7 +382,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 ptx::tma_store_4d(&tmC, tile_stg, col0, cx0, cy0, cb);
                             }
                         } else if constexpr (F32) {
-                            ptx::tma_reduce_add_2d(&tmC, tile_stg, col0, mt * BM);
+                            int row0 = mt * BM;
+                            if (g.batch_h) {   // batched problems: rows of problem (b, h) start at b * c_row_b + h * c_row_h
+                                const int z = mt / g.mt_per_batch, zb = z / g.batch_h;
+                                row0 = static_cast<int>(zb * g.c_row_b + (z - zb * g.batch_h) * g.c_row_h) + (mt - z * g.mt_per_batch) * BM;
+                            }
+                            ptx::tma_reduce_add_2d(&tmC, tile_stg, col0, row0);
                         } else {
                             ptx::tma_store_2d(&tmC, tile_stg, col0, mt * BM);
                         }
@@ -440,7 +465,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int c = c_lo; c < c_hi; ++c) {
                     const int col = n0 + c * 16 + cg;
                     EpiCols cols;
-                    if (col < g.N) epilogue_load_cols<KIND>(g.epi, col, cols);  // in flight while TMEM is read
+                    if (col < g.N) epilogue_load_cols<KIND>(g.epi, col + col_shift, cols);  // in flight while TMEM is read
                     uint32_t v[16];
                     ptx::tmem_ld_32x16(t_row + c * 16, v);
                     ptx::tmem_ld_wait();
@@ -453,7 +478,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         EpiPre pre[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i)  // issue the residual / table loads of the 4 passes first
-                            if (ok[i]) epilogue_prefetch<KIND>(g.epi, g.N, grow4[i], grow4[i], col, pre[i], sbase4[i]);
+                            if (ok[i]) epilogue_prefetch<KIND>(g.epi, g.N, grow4[i], grow4[i], col + col_shift, pre[i], sbase4[i]);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             if (ok[i]) {
@@ -536,9 +561,10 @@ int pick_bn(int N) {
 
 int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     DAD_REQUIRE(p.A && p.Wt && p.N > 0, "gemm_tc: null operand or N<=0");
+    if (p.ksplit > 1 || p.batch_h > 0) debug_label(p.batch_h > 0 ? "gemm_tc batched" : "gemm_tc split-K");
     {
         static const bool no_2cta = getenv("DAD_NO_2CTA") != nullptr;  // A/B switch while the 2-CTA kernel is validated
-        if (!no_2cta && p.ksplit <= 1 && gemm_tc2_eligible(p)) return gemm_tc2(p, stream);
+        if (!no_2cta && p.ksplit <= 1 && p.batch_h == 0 && gemm_tc2_eligible(p)) return gemm_tc2(p, stream);
         if (!no_2cta && conv_tc2_eligible(p)) return conv_tc2(p, stream);
     }
     DAD_REQUIRE(p.N % 8 == 0, "gemm_tc: N=%d must be a multiple of 8", p.N);
@@ -547,6 +573,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     a.epi = p.epi;
     a.N = p.N;
     a.conv = p.conv;
+    a.batch_h = 0;
     a.ksplit = 1;
     int bn = pick_bn(p.N);
     if (p.ksplit > 1 && bn < 128) bn = 128;   // split-K needs the TMA reduce-add epilogue (wide tiles only)
@@ -612,12 +639,38 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         a.flops = 2.0 * p.M * p.N * static_cast<double>(p.K);
         a.num_k_blocks = cdiv(p.K, BK);
         a.num_m_tiles = cdiv(p.M, BM);
+        if (p.batch_h > 0) {
+            DAD_REQUIRE(p.batch_b > 0 && p.ksplit <= 1 && p.w_rows > 0 && p.w_rows <= p.N && p.a_sh % 8 == 0 && p.a_sb % 8 == 0 &&
+                            p.w_sh % 8 == 0 && p.w_sb % 8 == 0 && !p.epi.scat_k && !p.epi.rowtab && !p.epi.res2 && !p.epi.head_out,
+                        "gemm_tc: bad batched problem");
+            // with a residual the only supported form is out += gamma * (acc + bias) through the TMA reduce-add epilogue: rows
+            // past a problem's M are zero (A is zero-filled there), so tiles may overhang into the next problem's rows
+            DAD_REQUIRE((!p.epi.bias && !p.epi.res1) || (epilogue_kind(p.epi) == EK_RES_F32 && p.c_col_h == 0 && pick_bn(p.N) >= 128),
+                        "gemm_tc: batched problems take either no bias / residual or the reduce-add epilogue with N %% 128 == 0");
+            const int nz = p.batch_h * p.batch_b;
+            a.batch_h = p.batch_h;
+            a.mt_per_batch = cdiv(p.M, BM);
+            a.rows_per_batch = p.M;
+            a.num_m_tiles = a.mt_per_batch * nz;
+            a.c_row_b = p.c_row_b; a.c_row_h = p.c_row_h; a.c_col_h = p.c_col_h;
+            a.flops *= nz;
+            const cuuint64_t dims[4] = {(cuuint64_t)p.K, (cuuint64_t)p.M, (cuuint64_t)p.batch_h, (cuuint64_t)p.batch_b};
+            const cuuint64_t strides[3] = {(cuuint64_t)p.lda * 2, (cuuint64_t)p.a_sh * 2, (cuuint64_t)p.a_sb * 2};
+            const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)BM, 1, 1};
+            DAD_TRY(make_tmap(&tmA, 0, p.A, 4, dims, strides, box));
+        } else {
         const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
         const cuuint64_t strides[1] = {(cuuint64_t)p.lda * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
         DAD_TRY(make_tmap_bf16(&tmA, p.A, 2, dims, strides, box));
+        }
     }
-    {
+    if (a.batch_h) {
+        const cuuint64_t dims[4] = {(cuuint64_t)p.K, (cuuint64_t)p.w_rows, (cuuint64_t)p.batch_h, (cuuint64_t)p.batch_b};
+        const cuuint64_t strides[3] = {(cuuint64_t)(p.ldw ? p.ldw : p.Kp) * 2, (cuuint64_t)p.w_sh * 2, (cuuint64_t)p.w_sb * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bn, 1, 1};
+        DAD_TRY(make_tmap(&tmB, 0, p.Wt, 4, dims, strides, box));
+    } else {
         const cuuint64_t dims[2] = {(cuuint64_t)p.Kp, (cuuint64_t)p.N};
         const cuuint64_t strides[1] = {(cuuint64_t)p.Kp * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
@@ -633,7 +686,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
                           bn >= 128;
     if (scat_tma) kind = EK_BIAS_BF16;
     DAD_REQUIRE(!(e.scat_k && p.conv && !scat_tma), "gemm_tc: conv-mode ConvTranspose scatter needs Co %% 64 == 0, bf16 out");
-    if (bn < 128) kind = EK_GENERIC;  // the specialised (TMA-store) epilogues exist for the wide tiles only
+    if (bn < 128 || (a.batch_h && kind != EK_RES_F32)) kind = EK_GENERIC;  // the specialised (TMA-store) epilogues exist for the wide tiles only
     if (p.ksplit > 1) {
         // split-K: each (k slice, tile) work item reduce-adds its partial product into the fp32 output through TMA
         DAD_REQUIRE(!p.conv && kind == EK_RES_F32, "gemm_tc: split-K needs a linear problem with the out += gamma * (acc + bias) epilogue");
@@ -663,7 +716,8 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
             const cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)tw, (cuuint32_t)a.th, 1};
             DAD_TRY(make_tmap(&tmC, f32 ? 1 : 0, p.epi.out, 4, dims, strides, box));
         } else {
-            const cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.M};
+            const cuuint64_t out_rows = a.batch_h ? (cuuint64_t)(p.batch_b * p.c_row_b) : (cuuint64_t)p.M;
+            const cuuint64_t dims[2] = {(cuuint64_t)p.N, out_rows};
             const cuuint64_t strides[1] = {(cuuint64_t)p.epi.ldc * es};
             const cuuint32_t box[2] = {(cuuint32_t)cw, (cuuint32_t)BM};
             DAD_TRY(make_tmap(&tmC, f32 ? 1 : 0, p.epi.out, 2, dims, strides, box));

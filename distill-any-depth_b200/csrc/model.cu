@@ -74,6 +74,7 @@ public:
     std::map<std::pair<int, int>, float*> pos_tables;   // (H, W) -> [1 + ph*pw, D]
     std::unordered_map<std::string, std::pair<float*, long long>> captures;
     std::unordered_map<std::string, std::pair<float*, long long>> grads;   // caller-owned fp32 gradient accumulators
+    bool attn_bwd_fp32 = getenv("DAD_ATTN_BWD_FP32") != nullptr;   // A/B switch: bf16 training with the fp32 attention backward
 
     // packed matrices
     Mat patch;

@@ -75,6 +75,7 @@ struct Trainer {
     void* a(Bump& ar, size_t n) const { return ar.bytes(n * es); }   // n elements of the activation type
     const float* zeros = nullptr;   // [8192] 0 / 1 vectors for the TMA epilogues of the backward GEMMs (mode 0)
     const float* ones = nullptr;
+    const float* eighths = nullptr;
 
     float* G(const std::string& name) const {
         auto it = m.grads.find(name);
@@ -276,6 +277,7 @@ struct Trainer {
             GemmProblem p;
             p.A = dY; p.M = static_cast<int>(rows); p.K = Nout; p.lda = ldy; p.Wt = WT; p.N = Kin; p.Kp = Np;
             p.epi.bias = zeros; p.epi.out = dX; p.epi.out_bf16 = 1; p.epi.ldc = Kin;
+            debug_label("gemm_tc dgrad");
             DAD_TRY(gemm_tc(p, st));
         }
         ar.used = mk;
@@ -349,7 +351,73 @@ struct Trainer {
         return d;
     }
 
+    // one batched tcgen05 launch: per (image, head) out = A W^T over K-major bf16 operands (see GemmProblem::batch_h)
+    int batched_tc(const void* A, long long lda, long long a_sh, long long a_sb, const void* Wt, long long ldw, long long w_sh,
+                   long long w_sb, int w_rows, int Mrows, int N, int K, void* out, int out_bf16, long long ldc, long long c_row_b,
+                   long long c_row_h, int c_col_h, const float* scale) {
+        GemmProblem p;
+        p.A = A; p.M = Mrows; p.K = K; p.lda = lda; p.a_sh = a_sh; p.a_sb = a_sb;
+        p.Wt = Wt; p.N = N; p.Kp = rup(K, 8); p.ldw = ldw; p.w_sh = w_sh; p.w_sb = w_sb; p.w_rows = w_rows;
+        p.batch_h = heads; p.batch_b = B;
+        p.c_row_b = c_row_b; p.c_row_h = c_row_h; p.c_col_h = c_col_h;
+        p.epi.out = out; p.epi.out_bf16 = out_bf16; p.epi.ldc = ldc; p.epi.gamma = scale;
+        return gemm_tc(p, st);
+    }
+
+    // bf16 engine: the five contractions of the attention backward as batched tcgen05 GEMMs (one problem per image and
+    // head) over K-major operands.  S and dP are materialised in fp32 ([Z][T][Tp], Tp = T rounded up to 128) by the TMA
+    // reduce-add epilogue onto zero-filled buffers; the row-wise softmax kernels turn them into bf16 P / dS, which the
+    // remaining three GEMMs read directly or through 64 x 64 tile transposes.
+    int attention_bwd_tc(const BlockTape& bt, const void* datt, void* dqkv, Bump& ar) {
+        const size_t mk = ar.used;
+        const int Tp = rup(T, 128), Z = B * heads;
+        const long long tt = static_cast<long long>(T) * Tp, sq = static_cast<long long>(Tp) * Tp, ld = 3LL * Dm;
+        float* S = ar.f(static_cast<size_t>(Z) * tt);
+        float* dPf = ar.f(static_cast<size_t>(Z) * tt);
+        void* Pn = ar.bytes(static_cast<size_t>(Z) * tt * 2);    // P  [z][i][j]
+        void* Pt = ar.bytes(static_cast<size_t>(Z) * sq * 2);    // P  [z][j][i]
+        void* dS = ar.bytes(static_cast<size_t>(Z) * tt * 2);    // dS [z][i][j]
+        void* dSt = ar.bytes(static_cast<size_t>(Z) * sq * 2);   // dS [z][j][i]
+        void* Qt = ar.bytes(static_cast<size_t>(Z) * 64 * Tp * 2);
+        void* Kt = ar.bytes(static_cast<size_t>(Z) * 64 * Tp * 2);
+        void* dOt = ar.bytes(static_cast<size_t>(Z) * 64 * Tp * 2);
+        if (!dry) {
+            DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
+            const bf16* q = reinterpret_cast<const bf16*>(bt.qkv);
+            bf16* dq = reinterpret_cast<bf16*>(dqkv);
+            const long long zrows = static_cast<long long>(Z) * T;
+            auto scores = [&](const void* A, long long lda, long long a_sb, const void* Wt, float* out) -> int {
+                DAD_CHECK_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(Z) * tt * 4, st));
+                GemmProblem p;
+                p.A = A; p.M = T; p.K = 64; p.lda = lda; p.a_sh = 64; p.a_sb = a_sb;
+                p.Wt = Wt; p.N = Tp; p.Kp = 64; p.ldw = ld; p.w_sh = 64; p.w_sb = T * ld; p.w_rows = T;
+                p.batch_h = heads; p.batch_b = B; p.c_row_b = static_cast<long long>(heads) * T; p.c_row_h = T;
+                p.epi.bias = zeros; p.epi.gamma = ones; p.epi.res1 = out; p.epi.out = out; p.epi.ldc = Tp;
+                return gemm_tc(p, st);
+            };
+            DAD_TRY(scores(q, ld, T * ld, q + Dm, S));                                           // S  = Q' K^T
+            DAD_TRY(scores(datt, Dm, static_cast<long long>(T) * Dm, q + 2 * Dm, dPf));          // dP = dO V^T
+            DAD_TRY(softmax_rows_bf16(S, Pn, zrows, T, Tp, st));
+            DAD_TRY(transpose_pad_batched(Pn, Tp, T, Tp, Pt, Tp, Z, tt, sq, st));
+            DAD_TRY(head_transpose(datt, Dm, dOt, B, T, heads, Tp, st));
+            DAD_TRY(head_transpose(q, ld, Qt, B, T, heads, Tp, st));
+            DAD_TRY(head_transpose(q + Dm, ld, Kt, B, T, heads, Tp, st));
+            // dV[j, d] = sum_i P[i, j] dO[i, d]
+            DAD_TRY(batched_tc(Pt, Tp, sq, heads * sq, dOt, Tp, 64LL * Tp, heads * 64LL * Tp, 64, T, 64, T, dq + 2 * Dm, 1, ld, T, 0, 64,
+                               nullptr));
+            DAD_TRY(softmax_bwd_bf16(Pn, dPf, dS, zrows, T, Tp, st));
+            DAD_TRY(transpose_pad_batched(dS, Tp, T, Tp, dSt, Tp, Z, tt, sq, st));
+            // dq = 0.125 * dS K  (the packed q rows carry 64^-0.5), dK = dS^T Q'
+            DAD_TRY(batched_tc(dS, Tp, tt, heads * tt, Kt, Tp, 64LL * Tp, heads * 64LL * Tp, 64, T, 64, T, dq, 1, ld, T, 0, 64, eighths));
+            DAD_TRY(batched_tc(dSt, Tp, sq, heads * sq, Qt, Tp, 64LL * Tp, heads * 64LL * Tp, 64, T, 64, T, dq + Dm, 1, ld, T, 0, 64,
+                               nullptr));
+        }
+        ar.used = mk;
+        return DAD_OK;
+    }
+
     int attention_bwd(const BlockTape& bt, const void* datt_any, void* dqkv_any, Bump& ar) {
+        if (bf && !m.attn_bwd_fp32) return attention_bwd_tc(bt, datt_any, dqkv_any, ar);
         const size_t mk = ar.used;
         const long long tt = static_cast<long long>(T) * T;
         const float* qkv = as_f32(bt.qkv, M * 3 * Dm, ar);
@@ -366,7 +434,7 @@ struct Trainer {
             s.C = Pm; s.scm = T; s.scn = 1; s.c1 = heads * tt; s.c2 = tt;
             s.M = T; s.N = T; s.K = 64; s.nb1 = B; s.nb2 = heads;
             DAD_TRY(sgemm(s, st));
-            DAD_TRY(softmax_rows(Pm, static_cast<long long>(B) * heads * T, T, st));
+            DAD_TRY(softmax_rows(Pm, static_cast<long long>(B) * heads * T, T, T, st));
             SGemm p;  // dP = dO V^T
             p.A = datt; p.sam = Dm; p.sak = 1; p.a1 = static_cast<long long>(T) * Dm; p.a2 = 64;
             p.B = qkv + 2 * Dm; p.sbk = 1; p.sbn = ld; p.b1 = T * ld; p.b2 = 64;
@@ -379,7 +447,7 @@ struct Trainer {
             v.C = dqkv + 2 * Dm; v.scm = ld; v.scn = 1; v.c1 = T * ld; v.c2 = 64;
             v.M = T; v.N = 64; v.K = T; v.nb1 = B; v.nb2 = heads;
             DAD_TRY(sgemm(v, st));
-            DAD_TRY(softmax_bwd_rows(Pm, dP, static_cast<long long>(B) * heads * T, T, st));   // dP <- dS
+            DAD_TRY(softmax_bwd_rows(Pm, dP, static_cast<long long>(B) * heads * T, T, T, st));   // dP <- dS
             SGemm q;  // dq = 0.125 * dS K   (the packed q rows carry 64^-0.5: q' = q / 8)
             q.A = dP; q.sam = T; q.sak = 1; q.a1 = heads * tt; q.a2 = tt;
             q.B = qkv + Dm; q.sbk = ld; q.sbn = 1; q.b1 = T * ld; q.b2 = 64;
@@ -449,13 +517,14 @@ struct Trainer {
         const int F2 = F / 2, H1 = 2 * t.hs[0], W1 = 2 * t.wsz[0];
         const long long P = static_cast<long long>(B) * H * W, P1 = static_cast<long long>(B) * H1 * W1;
         if (bf) {
-            float* v = ar.f(2 * 8192);
+            float* v = ar.f(3 * 8192);
             if (!dry) {
                 DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
                 DAD_TRY(fill_f32(v, 0.f, 8192, st));
                 DAD_TRY(fill_f32(v + 8192, 1.f, 8192, st));
+                DAD_TRY(fill_f32(v + 2 * 8192, 0.125f, 8192, st));
             }
-            zeros = v; ones = v ? v + 8192 : nullptr;
+            zeros = v; ones = v ? v + 8192 : nullptr; eighths = v ? v + 2 * 8192 : nullptr;
         }
 
         // ---- output head
