@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--graph", type=int, default=1, choices=[0, 1],
                     help="1 (default): capture one step (forward + losses [+ all-reduce]) in a CUDA graph after warm-up and "
                          "replay it in the timed loops; 0: launch every kernel from the host each step")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "train"],
                     help="c3 (default, the metric's config): ViT-L 518^2 B=32 bf16 fwd + SSI + HDN-DR; the others are "
                          "BASELINE.json's remaining GPU configs, for DESIGN.md's table (not bench lines): c2 ViT-B 392^2 "
                          "B=16 + SSI/grad; c4 distillation step teacher ViT-L + student ViT-B 392^2 B=16/GPU, 5 losses; "
@@ -52,6 +52,8 @@ def parse():
         a.encoder, a.size, a.batch = "vitb", 392, 16
     elif a.workload == "c5":
         a.encoder, a.size, a.batch = "vitl", 1036, max(1, 8 // max(a.gpus, 1))
+    elif a.workload == "train":   # student update (forward + SSI / gradient loss + backward), C2's model and shape
+        a.encoder, a.size, a.batch = "vitb", 392, 16
     return a
 
 
@@ -181,6 +183,67 @@ class ClockSampler(threading.Thread):
                     samples=len(s))
 
 
+# ---------------------------------------------------------------------------------- training step (not a bench line)
+def run_train(a):
+    """Student update of the reference loop (tools/train_distillation.py:1509-1575) for BASELINE configs[1]'s model and
+    shape: forward + SSI + gradient-preservation loss + backward into .grad of all parameters, single GPU.  For
+    DESIGN.md's table; the headline metric stays the forward + loss workload."""
+    import ctypes
+    import torch
+    import distill_any_depth_b200 as d
+    from distill_any_depth_b200 import synthetic, _lib
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    B, H = a.batch, a.size
+    kw = synthetic.MODEL_PRESETS[a.encoder]
+    model = d.DepthAnythingV2(**kw)
+    model.load_state_dict(synthetic.make_state_dict(seed=1, **kw), strict=True)
+    model = model.to(dev).train()
+    model.precision = a.precision
+    model.bf16_backward = True
+    x = synthetic.make_images(B, H, H, seed=1234).to(dev)
+    _, gt, _ = synthetic.make_depth_pair(B, H, H, seed=7)
+    gt = gt.to(dev)
+    full = torch.ones_like(gt, dtype=torch.bool)
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        depth, _ = model(x)
+        loss = d.SSILoss()(depth, gt, full) + 0.2 * d.gradient_preservation_loss(depth)
+        loss.backward()
+        return loss.detach()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = lib.dad_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    launches = lib.dad_launch_count() - l0
+    lib.dad_profile_enable(1)
+    step()
+    torch.cuda.synchronize()
+    breakdown = {}
+    for ci, name in enumerate(PROF_CLASSES):
+        t, w, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        lib.dad_profile_get(ci, ctypes.byref(t), ctypes.byref(w), ctypes.byref(n))
+        if n.value:
+            breakdown[name] = dict(ms_per_step=t.value, launches_per_step=n.value, work_per_step=w.value)
+    lib.dad_profile_enable(0)
+    print(json.dumps(dict(metric="images/sec, student training step (forward + SSI/gradient loss + backward)", value=B / ms * 1e3,
+                          unit="images/s", n_gpus=1, steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms,
+                          higher_is_better=True, dtype=a.precision, data="synthetic",
+                          config=dict(workload=f"DepthAnythingV2 {a.encoder} {H}x{H} batch {B} {a.precision} train step "
+                                               f"(SURVEY 8f N1; not the headline metric)"),
+                          loss=float(loss), gpu_launches=int(launches), kernel_breakdown=breakdown)))
+
+
 # ---------------------------------------------------------------------------------- B200 arm
 def run_b200(a):
     import ctypes
@@ -194,6 +257,9 @@ def run_b200(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py (impl b200) needs a GPU; there is no CPU fallback"
+    if a.workload == "train":
+        return run_train(a)
+    torch.set_grad_enabled(False)   # inference benchmark: never take the differentiable (activation-tape) forward
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

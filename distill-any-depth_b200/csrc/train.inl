@@ -663,7 +663,9 @@ struct Trainer {
             ar.used = mk;
         }
         // ---- patch embedding / positional table (fp32 engine: N = 588 columns, tiny)
-        if (float* dW = dry ? reinterpret_cast<float*>(this) : G(p + "patch_embed.proj.weight")) {
+        float* dWpe = G(p + "patch_embed.proj.weight");
+        if (dWpe || dry) {   // (the dry run sizes the scratch for the all-parameters case)
+            float* dW = dWpe;
             const size_t mk = ar.used;
             const float* ape_f = as_f32(t.ape, M * PATCH_KP, ar);
             if (!dry) {

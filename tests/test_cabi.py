@@ -77,3 +77,31 @@ def test_workspace_sizing_is_consistent(lib):
         assert int(h.dad_loss_workspace_bytes(16, 7)) > int(h.dad_loss_workspace_bytes(16, 1)) > 0
     finally:
         h.dad_model_destroy(handle)
+
+
+def test_training_workspace_sizing_and_argument_checks(lib):
+    """dad_train_workspace_bytes is a dry run of the tape + backward-scratch layout (no GPU needed): both engines size,
+    the bf16 tape is smaller than the fp32 one, and it exceeds the inference workspace."""
+    h = lib.load()
+    d = lib.ModelDesc()
+    d.embed_dim, d.depth, d.num_heads = 384, 12, 6
+    d.taps = (ctypes.c_int * 4)(2, 5, 8, 11)
+    d.features = 64
+    d.out_channels = (ctypes.c_int * 4)(48, 96, 192, 384)
+    handle = ctypes.c_void_p()
+    assert h.dad_model_create(ctypes.byref(d), ctypes.byref(handle)) == 0
+    try:
+        t = lambda B, H, W, m: int(h.dad_train_workspace_bytes(handle, B, H, W, m))
+        f = lambda B, H, W, m: int(h.dad_forward_workspace_bytes(handle, B, H, W, m))
+        assert t(2, 70, 98, 1) > f(2, 70, 98, 1) > 0
+        assert 0 < t(2, 70, 98, 0)
+        assert t(4, 392, 392, 0) < t(4, 392, 392, 1)
+        assert t(1, 392, 392, 1) < t(2, 392, 392, 1) < t(4, 392, 392, 1)
+        assert t(1, 75, 70, 1) == 0 and b"multiples of 14" in h.dad_last_error()
+        assert t(1, 70, 70, 2) == 0
+        # gradient registration needs a known parameter of the right size; backward without prepared weights is refused
+        assert h.dad_model_set_grad(handle, b"pretrained.nope", ctypes.c_void_p(16), 4) == lib.DAD_ERR_INVALID
+        assert h.dad_backward(handle, 1, 70, 70, 1, None, None, ctypes.c_void_p(1024), 1 << 40, None) == lib.DAD_ERR_INVALID
+        assert b"dad_model_prepare" in h.dad_last_error()
+    finally:
+        h.dad_model_destroy(handle)
