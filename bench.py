@@ -456,9 +456,20 @@ def run_b200(a):
         else:
             rec.update(bound="hbm", achieved_gbs=per_s / 1e9, frac=per_s / 1e9 / pk_["hbm"])
 
-    if rank != 0:
+    def finish_ranks():
+        # Multi-rank exit: rendezvous, then leave WITHOUT tearing NCCL / the captured graphs down.  destroy_process_group()
+        # (and interpreter finalisation with graph-captured NCCL kernels alive) was observed to hang on a 2-GPU box after the
+        # JSON line had been printed; every rank has finished its work at the barrier, so a hard exit with code 0 is safe.
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            time.sleep(0.5)   # let the peers' last NCCL kernels drain before this rank's buffers go away
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish_ranks()
         return
     pk = peaks()
     imgs = B * world * a.steps
@@ -499,8 +510,7 @@ def run_b200(a):
     if world == 1 and not a.no_cpu_baseline and a.workload == "c3":
         line["cpu_baseline"] = cpu_baseline(a)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish_ranks()
 
 
 def main():
