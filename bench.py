@@ -260,6 +260,11 @@ def run_b200(a):
     if a.workload == "train":
         return run_train(a)
     torch.set_grad_enabled(False)   # inference benchmark: never take the differentiable (activation-tape) forward
+    # stdout must carry exactly ONE JSON line: NCCL prints its version banner to the process's stdout (fd 1), so fd 1 is
+    # pointed at stderr for the rest of the run and the JSON line is written to a saved duplicate of the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -509,7 +514,7 @@ def run_b200(a):
                 gpu_launches=int(launches), clocks=sampler.result(), roofline=roofline, kernel_breakdown=prof)
     if world == 1 and not a.no_cpu_baseline and a.workload == "c3":
         line["cpu_baseline"] = cpu_baseline(a)
-    print(json.dumps(line), flush=True)
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     finish_ranks()
 
 
