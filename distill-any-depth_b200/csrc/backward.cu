@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(256) head1x1_any_kernel(const void* in, int bf
 }
 
 // ---------------------------------------------------------------- ConvTranspose / strided-conv helpers
-__global__ void __launch_bounds__(256) convT_gather_kernel(const float* dout, float* G, int B, int H, int W, int k, int Co,
+__global__ void __launch_bounds__(256) convT_gather_kernel(const void* dout, void* G, int bf, int B, int H, int W, int k, int Co,
                                                            int CoP) {
     const long long total = static_cast<long long>(B) * H * W * k * k * CoP;
     const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
@@ -601,11 +601,11 @@ __global__ void __launch_bounds__(256) convT_gather_kernel(const float* dout, fl
     const int b = static_cast<int>(q / H);
     const int ky = t / k, kx = t - ky * k;
     float v = 0.f;
-    if (co < Co) v = dout[((static_cast<long long>(b) * (k * H) + k * y + ky) * (k * W) + k * x + kx) * Co + co];
-    G[i] = v;
+    if (co < Co) v = ldf(dout, ((static_cast<long long>(b) * (k * H) + k * y + ky) * (k * W) + k * x + kx) * Co + co, bf);
+    stf(G, i, bf, v);
 }
 
-__global__ void __launch_bounds__(256) col2im_s2_kernel(const float* dcol, float* din, int B, int H, int W, int C, int Cp, int Ho,
+__global__ void __launch_bounds__(256) col2im_s2_kernel(const void* dcol, void* din, int bf, int B, int H, int W, int C, int Cp, int Ho,
                                                         int Wo) {
     const long long total = static_cast<long long>(B) * H * W * C;
     const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
@@ -627,10 +627,10 @@ __global__ void __launch_bounds__(256) col2im_s2_kernel(const float* dcol, float
             if (tx < 0 || (tx & 1)) continue;
             const int ox = tx >> 1;
             if (ox >= Wo) continue;
-            s += dcol[((static_cast<long long>(b) * Ho + oy) * Wo + ox) * 9 * Cp + (dy * 3 + dx) * Cp + c];
+            s += ldf(dcol, ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * 9 * Cp + (dy * 3 + dx) * Cp + c, bf);
         }
     }
-    din[i] = s;
+    stf(din, i, bf, s);
 }
 
 __global__ void __launch_bounds__(256) pack_conv_dgrad_kernel(const float* w, void* out, int bf, int Co, int Ci, int taps, int CoP) {
@@ -641,6 +641,17 @@ __global__ void __launch_bounds__(256) pack_conv_dgrad_kernel(const float* w, vo
     const int t = static_cast<int>((i / CoP) % taps);
     const int ci = static_cast<int>(i / (static_cast<long long>(CoP) * taps));
     stf(out, i, bf, co < Co ? w[(static_cast<long long>(co) * Ci + ci) * taps + (taps - 1 - t)] : 0.f);
+}
+
+// ConvTranspose weight gradient: tmp [(t * CoP + co)][Ci] (GEMM output) -> dW[ci][co][t] += tmp
+__global__ void __launch_bounds__(256) convT_wgrad_permute_kernel(const float* tmp, float* dW, int Ci, int Co, int CoP, int kk) {
+    const long long total = static_cast<long long>(Ci) * Co * kk;
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int t = static_cast<int>(i % kk);
+    const int co = static_cast<int>((i / kk) % Co);
+    const int ci = static_cast<int>(i / (static_cast<long long>(kk) * Co));
+    dW[i] += tmp[(static_cast<long long>(t) * CoP + co) * Ci + ci];
 }
 
 __global__ void __launch_bounds__(256) batch_sum_rows_kernel(const float* G, float* dtab, int B, int T, int D) {
@@ -922,21 +933,30 @@ int head_bwd(const float* gdepth, const float* depth, const void* t32, int bf, c
     return DAD_OK;
 }
 
-int convT_gather(const float* dout, float* G, int B, int H, int W, int k, int Co, int CoP, cudaStream_t st) {
-    const long long total = static_cast<long long>(B) * H * W * k * k * CoP;
-    debug_label("convT_gather");
-    ProfScope prof(PROF_ELEM, static_cast<double>(total) * 8, st);
-    convT_gather_kernel<<<blocks_for(total), 256, 0, st>>>(dout, G, B, H, W, k, Co, CoP);
+int convT_wgrad_permute(const float* tmp, float* dW, int Ci, int Co, int CoP, int kk, cudaStream_t st) {
+    const long long total = static_cast<long long>(Ci) * Co * kk;
+    debug_label("convT_wgrad_permute");
+    ProfScope prof(PROF_ELEM, static_cast<double>(total) * 12, st);
+    convT_wgrad_permute_kernel<<<blocks_for(total), 256, 0, st>>>(tmp, dW, Ci, Co, CoP, kk);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 
-int col2im_s2(const float* dcol, float* din, int B, int H, int W, int C, int Cp, cudaStream_t st) {
+int convT_gather(const void* dout, void* G, int bf, int B, int H, int W, int k, int Co, int CoP, cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * H * W * k * k * CoP;
+    debug_label("convT_gather");
+    ProfScope prof(PROF_ELEM, static_cast<double>(total) * 8, st);
+    convT_gather_kernel<<<blocks_for(total), 256, 0, st>>>(dout, G, bf, B, H, W, k, Co, CoP);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int col2im_s2(const void* dcol, void* din, int bf, int B, int H, int W, int C, int Cp, cudaStream_t st) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = static_cast<long long>(B) * H * W * C;
     debug_label("col2im_s2");
     ProfScope prof(PROF_ELEM, static_cast<double>(total) * 4 + static_cast<double>(B) * Ho * Wo * 9 * Cp * 4, st);
-    col2im_s2_kernel<<<blocks_for(total), 256, 0, st>>>(dcol, din, B, H, W, C, Cp, Ho, Wo);
+    col2im_s2_kernel<<<blocks_for(total), 256, 0, st>>>(dcol, din, bf, B, H, W, C, Cp, Ho, Wo);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

@@ -71,9 +71,11 @@ int bilinear_bwd(const void* gout, int bf, float* gin, int B, int Hi, int Wi, in
 int head_bwd(const float* gdepth, const float* depth, const void* t32, int bf, const float* w2, void* dt32, float* dw2,
              float* db2, long long P, cudaStream_t st);
 // ConvTranspose k=s: G[(b,y,x), t*CoP + co] = dOut[b, k*y+ky, k*x+kx, co] (0 for co >= Co)
-int convT_gather(const float* dout, float* G, int B, int H, int W, int k, int Co, int CoP, cudaStream_t st);
+int convT_gather(const void* dout, void* G, int bf, int B, int H, int W, int k, int Co, int CoP, cudaStream_t st);
+// ConvTranspose weight gradient: tmp [(t*CoP + co)][Ci] (GEMM output) -> dW[ci][co][t] += tmp
+int convT_wgrad_permute(const float* tmp, float* dW, int Ci, int Co, int CoP, int kk, cudaStream_t st);
 // stride-2 3x3 conv: din[b,y,x,c] = sum over taps of dcol[(b,oy,ox), tap*Cp + c] with y = 2*oy+dy-1, x = 2*ox+dx-1
-int col2im_s2(const float* dcol, float* din, int B, int H, int W, int C, int Cp, cudaStream_t st);
+int col2im_s2(const void* dcol, void* din, int bf, int B, int H, int W, int C, int Cp, cudaStream_t st);
 // dgrad weights of a stride-1 conv: w [Co][Ci][taps] -> out [Ci][taps][CoP], out[ci][t][co] = w[co][ci][taps-1-t]
 int pack_conv_dgrad(const float* w, void* out, int bf, int Co, int Ci, int taps, int CoP, cudaStream_t st);
 // dtab[t, d] = sum_b G[(b*T + t), d]

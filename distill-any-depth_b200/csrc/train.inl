@@ -227,7 +227,7 @@ struct Trainer {
     }
     // out[Mo, No] (fp32) += At[Mo, K] Bt[No, K]^T on the tensor cores, split over K, partial tiles reduce-added through TMA
     int tc_accumulate(const void* At, const void* Bt, int Mo, int No, long long K, int Kp, float* out) {
-        DAD_REQUIRE(No <= 8192, "backward: weight-gradient width %d exceeds the epilogue vectors", No);
+        DAD_REQUIRE(No <= 16384, "backward: weight-gradient width %d exceeds the epilogue vectors", No);
         GemmProblem p;
         p.A = At; p.M = Mo; p.K = static_cast<int>(K); p.lda = Kp; p.Wt = Bt; p.N = No; p.Kp = Kp;
         p.epi.bias = zeros; p.epi.gamma = ones; p.epi.res1 = out; p.epi.out = out; p.epi.ldc = No;
@@ -517,14 +517,15 @@ struct Trainer {
         const int F2 = F / 2, H1 = 2 * t.hs[0], W1 = 2 * t.wsz[0];
         const long long P = static_cast<long long>(B) * H * W, P1 = static_cast<long long>(B) * H1 * W1;
         if (bf) {
-            float* v = ar.f(3 * 8192);
+            constexpr int VN = 16384;
+            float* v = ar.f(3 * VN);
             if (!dry) {
                 DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
-                DAD_TRY(fill_f32(v, 0.f, 8192, st));
-                DAD_TRY(fill_f32(v + 8192, 1.f, 8192, st));
-                DAD_TRY(fill_f32(v + 2 * 8192, 0.125f, 8192, st));
+                DAD_TRY(fill_f32(v, 0.f, VN, st));
+                DAD_TRY(fill_f32(v + VN, 1.f, VN, st));
+                DAD_TRY(fill_f32(v + 2 * VN, 0.125f, VN, st));
             }
-            zeros = v; ones = v ? v + 8192 : nullptr; eighths = v ? v + 2 * 8192 : nullptr;
+            zeros = v; ones = v ? v + VN : nullptr; eighths = v ? v + 2 * VN : nullptr;
         }
 
         // ---- output head
@@ -561,7 +562,47 @@ struct Trainer {
             void* drj = a(ar, pxj * oc[j]);
             DAD_TRY(conv_dgrad(dlat[j], hj, wj, F, oc[j], 9, m.P(s + "layer" + std::to_string(j + 1) + "_rn.weight"), drj, ar));
             void* dpj = drj;
-            if (j != 2) {
+            if (j != 2 && bf) {
+                // bf16 engine: the same contractions through the tensor-core helpers
+                dpj = a(ar, Mp * oc[j]);
+                DAD_TRY(bias_grad(drj, oc[j], pxj, oc[j], G(h + "resize_layers." + js + ".bias")));
+                const size_t mk = ar.used;
+                if (j == 3) {
+                    const int Cp = cdiv(oc[3], 64) * 64, CoP8 = rup(oc[3], 8);
+                    DAD_TRY(conv_wgrad(t.pj[3], drj, ph, pw, oc[3], oc[3], 9, 2, hj, wj, G(h + "resize_layers.3.weight"), ar));
+                    void* WT = ar.bytes(static_cast<size_t>(9) * Cp * CoP8 * 2);
+                    void* dcol = a(ar, pxj * 9 * Cp);
+                    if (!dry) {
+                        DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
+                        // dcol[pxj, 9*Cp] = drj[pxj, Co] W[Co, 9*Cp]  (the packed fp32 matrix of the forward), then col2im
+                        DAD_TRY(pack_linear_T(reinterpret_cast<const float*>(m.resize3.w[1]), WT, oc[3], 9 * Cp, CoP8, st));
+                        GemmProblem p;
+                        p.A = drj; p.M = static_cast<int>(pxj); p.K = oc[3]; p.lda = oc[3]; p.Wt = WT; p.N = 9 * Cp; p.Kp = CoP8;
+                        p.epi.bias = zeros; p.epi.out = dcol; p.epi.out_bf16 = 1; p.epi.ldc = 9 * Cp;
+                        DAD_TRY(gemm_tc(p, st));
+                        DAD_TRY(col2im_s2(dcol, dpj, 1, B, ph, pw, oc[3], Cp, st));
+                    }
+                } else {
+                    const int k = j == 0 ? 4 : 2, kk = k * k, CoP = j == 0 ? m.CoP0 : m.CoP1;
+                    const Mat& mt = j == 0 ? m.resize0 : m.resize1;
+                    void* Gm = a(ar, Mp * kk * CoP);
+                    float* tmpw = ar.f(static_cast<size_t>(kk) * CoP * oc[j]);
+                    if (!dry) {
+                        DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
+                        DAD_TRY(convT_gather(drj, Gm, 1, B, ph, pw, k, oc[j], CoP, st));
+                    }
+                    float* dW = G(h + "resize_layers." + js + ".weight");
+                    if (dW || dry) {
+                        if (!dry) DAD_CHECK_CUDA(cudaMemsetAsync(tmpw, 0, static_cast<size_t>(kk) * CoP * oc[j] * 4, st));
+                        DAD_TRY(wgrad_linear(Gm, static_cast<long long>(kk) * CoP, t.pj[j], oc[j], Mp, kk * CoP, oc[j], tmpw, ar));
+                        if (!dry) DAD_TRY(convT_wgrad_permute(tmpw, dW, oc[j], oc[j], CoP, kk, st));
+                    }
+                    // dpj[Mp, Ci] = Gm[Mp, kk*CoP] Wm[kk*CoP, Ci]  (the packed fp32 ConvTranspose matrix of the forward)
+                    DAD_TRY(dgrad_linear(Gm, static_cast<long long>(kk) * CoP, Mp, kk * CoP, reinterpret_cast<const float*>(mt.w[1]), oc[j],
+                                         dpj, ar));
+                }
+                ar.used = mk;
+            } else if (j != 2) {
                 // ConvTranspose (j = 0, 1) / stride-2 conv (j = 3): small GEMMs, fp32 engine in both modes
                 dpj = a(ar, Mp * oc[j]);
                 const size_t mk = ar.used;
@@ -584,7 +625,7 @@ struct Trainer {
                         SGemm d; d.A = drj_f; d.sam = oc[3]; d.sak = 1; d.B = reinterpret_cast<const float*>(m.resize3.w[1]); d.sbk = 9 * Cp;
                         d.sbn = 1; d.C = dcol; d.scm = 9 * Cp; d.scn = 1; d.M = static_cast<int>(pxj); d.N = 9 * Cp; d.K = oc[3];
                         DAD_TRY(sgemm(d, st));
-                        DAD_TRY(col2im_s2(dcol, dpj_f, B, ph, pw, oc[3], Cp, st));
+                        DAD_TRY(col2im_s2(dcol, dpj_f, 0, B, ph, pw, oc[3], Cp, st));
                     }
                 } else {
                     const int k = j == 0 ? 4 : 2, kk = k * k, CoP = j == 0 ? m.CoP0 : m.CoP1;
@@ -592,7 +633,7 @@ struct Trainer {
                     float* Gm = ar.f(Mp * kk * CoP);
                     if (!dry) {
                         DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
-                        DAD_TRY(convT_gather(drj_f, Gm, B, ph, pw, k, oc[j], CoP, st));
+                        DAD_TRY(convT_gather(drj_f, Gm, 0, B, ph, pw, k, oc[j], CoP, st));
                         if (float* dW = G(h + "resize_layers." + js + ".weight")) {
                             SGemm g; g.A = Gm; g.sam = 1; g.sak = static_cast<long long>(kk) * CoP; g.B = pj_f; g.sbk = oc[j]; g.sbn = 1;
                             g.C = dW; g.M = kk * CoP; g.N = oc[j]; g.K = static_cast<int>(Mp); g.accumulate = 1;
