@@ -36,3 +36,62 @@ def finish_losses(partials, group=None):
             v = 1.0 - v
         out[n] = v.to(torch.float32)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- data-parallel training
+# The reference trains in a single process, so its gradient is that of the FULL-batch losses.  Every loss is
+# numerator / (denominator + eps) with a denominator that does not depend on the parameters (valid-pixel / element counts),
+# so the full-batch gradient is sum_r (den_r + eps) / (den_total + eps) * grad(loss_r): scale each local loss by its shard
+# weight before backward(), then SUM-all-reduce the gradients - exactly the single-process gradient, with two small
+# collectives per step (the denominators, then one flat gradient buffer).
+def shard_loss_weights(partials, group=None):
+    """partials as for finish_losses (per-rank (numerator, denominator)); -> {name: fp32 scalar} shard weights
+    (den_local + eps) / (den_total + eps) (1.0 when not distributed)."""
+    names = sorted(partials)
+    den = torch.stack([partials[n][1].to(torch.float64)[1] for n in names])
+    tot = den.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    out = {}
+    for i, n in enumerate(names):
+        eps = LOSS_EPS[partials[n][0]]
+        out[n] = ((den[i] + eps) / (tot[i] + eps)).to(torch.float32)
+    return out
+
+
+def allreduce_gradients(parameters, group=None, average=False, bucket_bytes=256 << 20):
+    """SUM (or mean) all-reduce of the .grad of `parameters` through flat fp32 buckets (one collective per bucket;
+    NVSwitch reduces in the fabric, so buckets are sized for launch latency, not link count).  Parameters whose .grad is
+    None on this rank are treated as zeros when any bucket-mate has a gradient; returns the number of collectives."""
+    params = [p for p in parameters if p.requires_grad]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or not params:
+        return 0
+    world = dist.get_world_size(group)
+    n_coll, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal n_coll, bucket, size
+        if not bucket:
+            return
+        for p in bucket:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p, dtype=torch.float32)
+        flat = torch.cat([p.grad.reshape(-1).to(torch.float32) for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= world
+        off = 0
+        for p in bucket:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+        n_coll += 1
+        bucket, size = [], 0
+
+    for p in params:
+        bucket.append(p)
+        size += p.numel() * 4
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return n_coll

@@ -61,7 +61,8 @@ def _compare(name, grads, ref, tol=1e-3):
     assert not bad, f"{len(bad)} parameter gradients off: {bad[:8]}"
 
 
-@pytest.mark.parametrize("preset,B,H,W,seed", [("vits", 2, 70, 98, 0), ("vits", 1, 518, 518, 1), ("vitb", 2, 56, 56, 3)])
+@pytest.mark.parametrize("preset,B,H,W,seed", [("vits", 2, 70, 98, 0), ("vits", 1, 518, 518, 1), ("vitb", 2, 56, 56, 3),
+                                               ("vitl", 1, 56, 70, 1)])
 def test_parameter_gradients_match_autograd(preset, B, H, W, seed):
     d = dad()
     kw = synthetic.MODEL_PRESETS[preset]
@@ -219,3 +220,49 @@ def test_split_k_weight_gradient_gemm():
                                        _lib.stream_ptr()), "dad_gemm_splitk")
         ref = out0.double() + Ab.double() @ Wb.double().t()
         assert float((out.double() - ref).abs().max() / ref.abs().max()) <= 2e-5, (M, N, K, ks)
+
+
+def test_two_forwards_share_one_backward_and_teacher_class_trains_too():
+    """The reference step runs the student twice before one backward (tools/train_distillation.py:1509-1514): two activation
+    tapes coexist and their gradients add.  The teacher-layout class (DepthAnything, keys backbone.blocks.0.N.*) takes the same
+    path."""
+    d = dad()
+    from distill_any_depth_b200.dam import student_to_teacher_keys
+    kw = synthetic.MODEL_PRESETS["vits"]
+    sd = synthetic.make_state_dict(seed=0, **kw)
+    x1 = synthetic.make_images(1, 56, 56, seed=1).cuda()
+    x2 = synthetic.make_images(2, 56, 70, seed=2).cuda()
+    m = d.DepthAnythingV2(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    m.precision = "fp32"
+
+    def grads_after(fn):
+        for p in m.parameters():
+            p.grad = None
+        fn()
+        return {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    g1 = grads_after(lambda: m(x1)[0].sum().backward())
+    g2 = grads_after(lambda: (m(x2)[0] * 0.5).sum().backward())
+
+    def both():
+        a, _ = m(x1)
+        b, _ = m(x2)
+        (a.sum() + (b * 0.5).sum()).backward()
+    g12 = grads_after(both)
+    for k in g1:
+        ref = g1[k] + g2[k]
+        assert float((g12[k] - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-9, k
+
+    t = d.DepthAnything(**kw)
+    t.load_state_dict(student_to_teacher_keys(sd), strict=True)
+    t = t.cuda()
+    t.precision = "fp32"
+    t(x1)[0].sum().backward()
+    tg = {k: p.grad for k, p in t.named_parameters() if p.grad is not None}
+    assert len(tg) == len(g1)
+    k_t = "backbone.blocks.0.3.attn.qkv.weight"
+    assert float((tg[k_t] - g1["pretrained.blocks.3.attn.qkv.weight"]).abs().max()) <= 1e-4 * float(g1["pretrained.blocks.3.attn.qkv.weight"].abs().max())
+    assert float((tg["depth_head.scratch.output_conv1.weight"] - g1["depth_head.scratch.output_conv1.weight"]).abs().max()) <= \
+        1e-4 * float(g1["depth_head.scratch.output_conv1.weight"].abs().max())

@@ -198,3 +198,53 @@ def test_checkpoint_io_round_trips_both_key_layouts(tmp_path):
         bad["pretrained.blocks.0.attn.extra"] = torch.zeros(1)
         save_file({k: v.contiguous() for k, v in bad.items()}, str(tmp_path / "bad.safetensors"))
         ck.load_checkpoint(d.DepthAnythingV2(**kw), str(tmp_path / "bad.safetensors"), strict=True)
+
+
+def _train_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from distill_any_depth_b200.dist import shard_loss_weights, allreduce_gradients, shard_batch
+    net, x, gt, mask = _toy_problem()
+    sl = lambda t: shard_batch(t, rank, world)
+    pred = net(sl(x))
+    ssi = oracle.SSILoss()(pred, sl(gt), sl(mask))
+    grad = oracle.gradient_preservation_loss(pred)
+    t64 = lambda a, b: torch.tensor([float(a), float(b)], dtype=torch.float64)
+    w = shard_loss_weights({"ssi": ("ssi", t64(0, sl(mask).sum())), "grad": ("grad", t64(0, pred.numel()))})
+    (w["ssi"] * ssi + 0.2 * w["grad"] * grad).backward()
+    n = allreduce_gradients(net.parameters(), bucket_bytes=64)   # tiny buckets: several collectives
+    if rank == 0:
+        q.put(([p.grad.clone() for p in net.parameters()], n))
+    dist.destroy_process_group()
+
+
+def _toy_problem():
+    g = torch.Generator().manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 1, 3, padding=1))
+    for p in net.parameters():
+        p.data = torch.randn(p.shape, generator=g) * 0.3
+    x = torch.randn(5, 3, 24, 32, generator=g)      # 5 images over 2 ranks: uneven shards (3 + 2)
+    gt = torch.rand(5, 1, 24, 32, generator=g) + 0.1
+    mask = torch.rand(5, 1, 24, 32, generator=g) > 0.3   # per-shard valid counts differ
+    return net, x, gt, mask
+
+
+def test_two_rank_training_gradient_equals_single_process_full_batch():
+    """N1 x 8e: shard-weighted local losses + SUM all-reduce of the gradients == the gradient of the full-batch loss."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, n_coll = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert n_coll >= 2
+    net, x, gt, mask = _toy_problem()
+    pred = net(x)
+    (oracle.SSILoss()(pred, gt, mask) + 0.2 * oracle.gradient_preservation_loss(pred)).backward()
+    for a, p in zip(got, net.parameters()):
+        assert float((a - p.grad).abs().max()) <= 1e-5 * float(p.grad.abs().max()) + 1e-8
