@@ -255,14 +255,23 @@ def test_two_forwards_share_one_backward_and_teacher_class_trains_too():
         ref = g1[k] + g2[k]
         assert float((g12[k] - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-9, k
 
-    t = d.DepthAnything(**kw)
-    t.load_state_dict(student_to_teacher_keys(sd), strict=True)
+    # teacher-layout class (ViT-L only, as upstream): same gradients as the student class on the same weights
+    kwl = synthetic.MODEL_PRESETS["vitl"]
+    sdl = synthetic.make_state_dict(seed=1, **kwl)
+    ms = d.DepthAnythingV2(**kwl)
+    ms.load_state_dict(sdl, strict=True)
+    ms = ms.cuda()
+    ms.precision = "fp32"
+    ms(x1)[0].sum().backward()
+    gs = {k: p.grad for k, p in ms.named_parameters() if p.grad is not None}
+    t = d.DepthAnything(**kwl)
+    t.load_state_dict(student_to_teacher_keys(sdl), strict=True)
     t = t.cuda()
     t.precision = "fp32"
     t(x1)[0].sum().backward()
     tg = {k: p.grad for k, p in t.named_parameters() if p.grad is not None}
-    assert len(tg) == len(g1)
-    k_t = "backbone.blocks.0.3.attn.qkv.weight"
-    assert float((tg[k_t] - g1["pretrained.blocks.3.attn.qkv.weight"]).abs().max()) <= 1e-4 * float(g1["pretrained.blocks.3.attn.qkv.weight"].abs().max())
-    assert float((tg["depth_head.scratch.output_conv1.weight"] - g1["depth_head.scratch.output_conv1.weight"]).abs().max()) <= \
-        1e-4 * float(g1["depth_head.scratch.output_conv1.weight"].abs().max())
+    assert len(tg) == len(gs)
+    for kt, ks in (("backbone.blocks.0.3.attn.qkv.weight", "pretrained.blocks.3.attn.qkv.weight"),
+                   ("backbone.pos_embed", "pretrained.pos_embed"),
+                   ("depth_head.scratch.output_conv1.weight", "depth_head.scratch.output_conv1.weight")):
+        assert float((tg[kt] - gs[ks]).abs().max()) <= 1e-4 * float(gs[ks].abs().max()) + 1e-9, kt
