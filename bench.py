@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--graph", type=int, default=1, choices=[0, 1],
                     help="1 (default): capture one step (forward + losses [+ all-reduce]) in a CUDA graph after warm-up and "
                          "replay it in the timed loops; 0: launch every kernel from the host each step")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "train"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "train", "train4"],
                     help="c3 (default, the metric's config): ViT-L 518^2 B=32 bf16 fwd + SSI + HDN-DR; the others are "
                          "BASELINE.json's remaining GPU configs, for DESIGN.md's table (not bench lines): c2 ViT-B 392^2 "
                          "B=16 + SSI/grad; c4 distillation step teacher ViT-L + student ViT-B 392^2 B=16/GPU, 5 losses; "
@@ -52,7 +52,7 @@ def parse():
         a.encoder, a.size, a.batch = "vitb", 392, 16
     elif a.workload == "c5":
         a.encoder, a.size, a.batch = "vitl", 1036, max(1, 8 // max(a.gpus, 1))
-    elif a.workload == "train":   # student update (forward + SSI / gradient loss + backward), C2's model and shape
+    elif a.workload in ("train", "train4"):   # student update (forward + SSI / gradient loss + backward), C2's model and shape
         a.encoder, a.size, a.batch = "vitb", 392, 16
     return a
 
@@ -206,7 +206,20 @@ def run_train(a):
     gt = gt.to(dev)
     full = torch.ones_like(gt, dtype=torch.bool)
 
+    teacher = None
+    if a.workload == "train4":   # the reference's whole update (:1503-1575): ViT-L teacher, two student forwards, five losses
+        from distill_any_depth_b200.dam import student_to_teacher_keys
+        tkw = synthetic.MODEL_PRESETS["vitl"]
+        teacher = d.DepthAnything(**tkw)
+        teacher.load_state_dict(student_to_teacher_keys(synthetic.make_state_dict(seed=2, head_bias=0.6, **tkw)), strict=True)
+        teacher = teacher.to(dev).eval()
+        teacher.precision = a.precision
+        x2 = synthetic.make_images(B, H, H, seed=4321).to(dev)
+        opt = torch.optim.SGD(model.parameters(), lr=1e-6)
+
     def step():
+        if teacher is not None:
+            return d.distillation_train_step(model, teacher, x, x2, optimizer=opt)["batch_loss"]
         for p in model.parameters():
             p.grad = None
         depth, _ = model(x)
@@ -239,7 +252,10 @@ def run_train(a):
     print(json.dumps(dict(metric="images/sec, student training step (forward + SSI/gradient loss + backward)", value=B / ms * 1e3,
                           unit="images/s", n_gpus=1, steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms,
                           higher_is_better=True, dtype=a.precision, data="synthetic",
-                          config=dict(workload=f"DepthAnythingV2 {a.encoder} {H}x{H} batch {B} {a.precision} train step "
+                          config=dict(workload=(f"distillation update: ViT-L teacher forward + 2x {a.encoder} student forward + 5 losses + "
+                                                f"backward + SGD step, {H}x{H} batch {B} {a.precision} (BASELINE configs[3] per-GPU shard, "
+                                                f"training half; not the headline metric)") if teacher is not None else
+                                               f"DepthAnythingV2 {a.encoder} {H}x{H} batch {B} {a.precision} train step "
                                                f"(SURVEY 8f N1; not the headline metric)"),
                           loss=float(loss), gpu_launches=int(launches), kernel_breakdown=breakdown)))
 
@@ -257,7 +273,7 @@ def run_b200(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py (impl b200) needs a GPU; there is no CPU fallback"
-    if a.workload == "train":
+    if a.workload in ("train", "train4"):
         return run_train(a)
     torch.set_grad_enabled(False)   # inference benchmark: never take the differentiable (activation-tape) forward
     # stdout must carry exactly ONE JSON line: NCCL prints its version banner to the process's stdout (fd 1), so fd 1 is

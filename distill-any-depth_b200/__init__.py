@@ -12,4 +12,4 @@ from . import dist  # noqa: F401
 from . import checkpoint  # noqa: F401
 from . import preprocess  # noqa: F401
 from .graph import capture  # noqa: F401
-from .step import distillation_step_losses  # noqa: F401
+from .step import distillation_step_losses, distillation_train_step  # noqa: F401

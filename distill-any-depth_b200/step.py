@@ -5,7 +5,9 @@ nothing synchronises the host.  Under ``torch.distributed`` (one process per GPU
 each loss is finished from its (numerator, denominator) partials by ONE all-reduce (``dist.finish_losses``),
 so the value equals the single-process full-batch loss.
 
-The backward / optimiser half (``:1561-1573``) is outside this path.
+``distillation_train_step`` is the whole step including the backward / optimiser half (``:1556-1575``, SURVEY.md 8f
+N1): the student forwards are differentiable (``precision="fp32"``, or ``"bf16"`` with ``bf16_backward=True``), the
+losses are the public autograd-aware functions, and ``batch_loss.backward()`` fills ``.grad`` of the student.
 """
 import torch
 
@@ -55,3 +57,44 @@ def distillation_step_losses(student_model, teacher_model, global_image, local_i
             batch = batch + lam["hdn"] * out["hdn_loss"]
         out["batch_loss"] = batch
     return out
+
+
+def distillation_train_step(student_model, teacher_model, global_image, local_image, optimizer=None, normalization="hybrid",
+                            lambdas=None, use_hdn_loss=True, hdn_level=3, grad_clip=None):
+    """One update of the reference loop (``tools/train_distillation.py:1503-1575``), single process: teacher forward without
+    gradients, the two student forwards with gradients, the five losses, ``batch_loss.backward()`` and - when an
+    ``optimizer`` is given - ``optimizer.step()`` / ``zero_grad()``.  Returns the dict of detached loss scalars.
+    (Data-parallel: scale the local losses with ``dist.shard_loss_weights`` and call ``dist.allreduce_gradients`` before
+    the optimiser step; see dist.py.)"""
+    lam = dict(DEFAULT_LAMBDAS)
+    lam.update(lambdas or {})
+    if not torch.is_grad_enabled():
+        raise RuntimeError("distillation_train_step needs grad mode")
+    if getattr(student_model, "precision", "fp32") == "bf16" and not getattr(student_model, "bf16_backward", True):
+        raise RuntimeError("the student runs the inference-only bf16 forward: set student.bf16_backward = True "
+                           "(or student.precision = 'fp32')")
+    with torch.no_grad():
+        teacher_local_disp, teacher_local_features = teacher_model(local_image)
+    student_global_disp, _ = student_model(global_image)
+    student_local_disp, student_local_features = student_model(local_image)
+    out = {}
+    out["sc_loss"] = losses.distillation_loss(student_local_disp, teacher_local_disp, normalization)
+    out["lg_loss"] = losses.distillation_loss(student_global_disp, student_local_disp, normalization)
+    out["feat_loss"] = losses.feature_distillation_loss(student_local_features, teacher_local_features)
+    out["grad_loss"] = losses.gradient_preservation_loss(student_local_disp)
+    batch = (lam["sc"] * out["sc_loss"] + lam["lg"] * out["lg_loss"] + lam["feat"] * out["feat_loss"]
+             + lam["grad"] * out["grad_loss"])
+    if use_hdn_loss:
+        ctx = losses.get_contexts_dr(hdn_level, teacher_local_disp, None)
+        out["hdn_loss"] = losses.compute_hdn_loss(losses.SSILoss(), student_local_disp, teacher_local_disp, ctx)
+        batch = batch + lam["hdn"] * out["hdn_loss"]
+    else:
+        out["hdn_loss"] = torch.zeros((), device=local_image.device)
+    out["batch_loss"] = batch
+    batch.backward()
+    if optimizer is not None:
+        if grad_clip is not None:
+            torch.nn.utils.clip_grad_norm_(student_model.parameters(), grad_clip)
+        optimizer.step()
+        optimizer.zero_grad(set_to_none=True)
+    return {k: v.detach() for k, v in out.items()}

@@ -275,3 +275,57 @@ def test_two_forwards_share_one_backward_and_teacher_class_trains_too():
                    ("backbone.pos_embed", "pretrained.pos_embed"),
                    ("depth_head.scratch.output_conv1.weight", "depth_head.scratch.output_conv1.weight")):
         assert float((tg[kt] - gs[ks]).abs().max()) <= 1e-4 * float(gs[ks].abs().max()) + 1e-9, kt
+
+
+def test_distillation_train_step_matches_the_reference_loop():
+    """tools/train_distillation.py:1503-1575 as one call: ViT-L teacher (no grad), ViT-S student run twice, SC / LG / feature /
+    gradient / HDN-DR losses with the default lambdas, backward, SGD step; loss values, gradients and the updated weights
+    against the same composition on the CPU oracle."""
+    d = dad()
+    from distill_any_depth_b200.dam import student_to_teacher_keys
+    kws, kwl = synthetic.MODEL_PRESETS["vits"], synthetic.MODEL_PRESETS["vitl"]
+    sds = synthetic.make_state_dict(seed=0, **kws)
+    sdl = synthetic.make_state_dict(seed=2, head_bias=0.6, **kwl)
+    xg = synthetic.make_images(2, 56, 70, seed=11)
+    xl = synthetic.make_images(2, 56, 70, seed=12)
+    lam = dict(sc=0.5, lg=0.5, feat=1.0, grad=0.2, hdn=0.8)
+
+    # ---- oracle
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sds.items()}
+    with torch.no_grad():
+        td, tf = oracle.depth_anything_forward(xl, sdl, "vitl")
+    sgd_, _ = oracle.depth_anything_forward(xg, leaves, "vits")
+    sld, slf = oracle.depth_anything_forward(xl, leaves, "vits")
+    ref = dict(sc_loss=oracle.distillation_loss(sld, td, "hybrid"), lg_loss=oracle.distillation_loss(sgd_, sld, "hybrid"),
+               feat_loss=oracle.feature_distillation_loss(slf, tf), grad_loss=oracle.gradient_preservation_loss(sld),
+               hdn_loss=oracle.compute_hdn_loss(oracle.SSILoss(), sld, td, oracle.get_contexts_dr(3, td, None)))
+    total = (lam["sc"] * ref["sc_loss"] + lam["lg"] * ref["lg_loss"] + lam["feat"] * ref["feat_loss"] + lam["grad"] * ref["grad_loss"]
+             + lam["hdn"] * ref["hdn_loss"])
+    total.backward()
+    gref = {k: v.grad for k, v in leaves.items()}
+
+    # ---- native
+    student = d.DepthAnythingV2(**kws)
+    student.load_state_dict(sds, strict=True)
+    student = student.cuda().train()
+    student.precision = "fp32"
+    teacher = d.DepthAnything(**kwl)
+    teacher.load_state_dict(student_to_teacher_keys(sdl), strict=True)
+    teacher = teacher.cuda().eval()
+    teacher.precision = "fp32"
+    out = d.distillation_train_step(student, teacher, xg.cuda(), xl.cuda(), optimizer=None, lambdas=lam)
+    for k, v in ref.items():
+        assert abs(float(out[k]) - float(v)) <= 1e-3 * max(abs(float(v)), 1e-6), (k, float(out[k]), float(v))
+    assert abs(float(out["batch_loss"]) - float(total)) <= 1e-3 * abs(float(total))
+    _compare("distill_train_step", {k: p.grad for k, p in student.named_parameters()}, gref, tol=5e-3)
+    assert all(p.grad is None for p in teacher.parameters())
+    # optimiser half: one SGD step moves the weights by -lr * grad and the next forward sees them
+    g0 = student.depth_head.scratch.output_conv1.weight.grad.clone()
+    w0 = student.depth_head.scratch.output_conv1.weight.detach().clone()
+    opt = torch.optim.SGD(student.parameters(), lr=1e-3)
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    assert torch.allclose(student.depth_head.scratch.output_conv1.weight.detach(), w0 - 1e-3 * g0, rtol=0, atol=1e-7)
+    out2 = d.distillation_train_step(student, teacher, xg.cuda(), xl.cuda(), optimizer=opt, lambdas=lam)
+    assert float(out2["batch_loss"]) != float(out["batch_loss"])
+    assert all(p.grad is None for p in student.parameters())
