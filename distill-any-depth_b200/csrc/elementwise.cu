@@ -243,6 +243,38 @@ __global__ void __launch_bounds__(256) pos_table_kernel(const float* pos, const 
     }
 }
 
+// ---------------------------------------------------------------- readout concat (use_clstoken, dpt.py:153-156)
+// out[(b, i), 0:D] = tok[(b, i), :]; out[(b, i), D:2D] = cls[b, :]   (torch.cat((x, cls.unsqueeze(1).expand_as(x)), -1))
+// VEC elements (16 bytes) per thread.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) concat_cls_kernel(const T* __restrict__ tok, const T* __restrict__ cls,
+                                                         T* __restrict__ out, long long rows, int np, int D) {
+    const int dv = D / VEC;  // vectors per half row
+    const long long total = rows * 2 * dv;
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * 256) {
+        const long long r = i / (2 * dv);
+        const int c = static_cast<int>(i - r * 2 * dv);
+        const uint4* src = c < dv ? reinterpret_cast<const uint4*>(tok + r * D) + c
+                                  : reinterpret_cast<const uint4*>(cls + (r / np) * D) + (c - dv);
+        reinterpret_cast<uint4*>(out + r * 2 * D)[c] = *src;
+    }
+}
+
+// ---------------------------------------------------------------- SwiGLU gate (ViT-g, swiglu_ffn.py:30-34)
+// x12 [rows, 2*Hd] -> out [rows, Hd] = silu(x12[:, :Hd]) * x12[:, Hd:]; fp32 maths, ATen's silu = x / (1 + exp(-x))
+template <typename T>
+__global__ void __launch_bounds__(256) swiglu_kernel(const T* __restrict__ x12, T* __restrict__ out, long long rows, int Hd) {
+    const long long total = rows * Hd;
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * 256) {
+        const long long r = i / Hd;
+        const int c = static_cast<int>(i - r * Hd);
+        const float a = to_f(x12[r * 2 * Hd + c]), g = to_f(x12[r * 2 * Hd + Hd + c]);
+        out[i] = from_f<T>(a / (1.f + expf(-a)) * g);
+    }
+}
+
 // ---------------------------------------------------------------- weight packing
 template <typename T>
 __global__ void __launch_bounds__(256) pack_linear_kernel(const float* w, T* out, int N, int K, int Kp, int scale_rows,
@@ -368,6 +400,29 @@ int im2col_s2(const void* in, void* A, int is_bf16, int B, int H, int W, int C, 
 int head1x1(const float* in, const float* w, float bias, float* out, long long P, cudaStream_t st) {
     ProfScope prof(PROF_ELEM, static_cast<double>(P) * 33 * 4, st);
     head1x1_kernel<<<static_cast<unsigned>(cdivl(P, 256)), 256, 0, st>>>(in, w, bias, out, P);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int concat_cls(const void* tok, const void* cls, void* out, int is_bf16, int B, int np, int D, cudaStream_t st) {
+    DAD_REQUIRE(D % 8 == 0, "concat_cls: D=%d must be a multiple of 8", D);
+    const long long rows = static_cast<long long>(B) * np;
+    const size_t es = is_bf16 ? 2 : 4;
+    ProfScope prof(PROF_ELEM, static_cast<double>(rows) * D * es * 3 + static_cast<double>(B) * D * es, st);
+    if (is_bf16)
+        concat_cls_kernel<bf16, 8><<<grid_for(rows * 2 * (D / 8)), 256, 0, st>>>(
+            reinterpret_cast<const bf16*>(tok), reinterpret_cast<const bf16*>(cls), reinterpret_cast<bf16*>(out), rows, np, D);
+    else
+        concat_cls_kernel<float, 4><<<grid_for(rows * 2 * (D / 4)), 256, 0, st>>>(
+            reinterpret_cast<const float*>(tok), reinterpret_cast<const float*>(cls), reinterpret_cast<float*>(out), rows, np, D);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int swiglu(const void* x12, void* out, int is_bf16, long long rows, int Hd, cudaStream_t st) {
+    ProfScope prof(PROF_ELEM, static_cast<double>(rows) * Hd * 3 * (is_bf16 ? 2 : 4), st);
+    DISPATCH_T(is_bf16, (swiglu_kernel<T><<<grid_for(rows * Hd), 256, 0, st>>>(reinterpret_cast<const T*>(x12),
+                                                                               reinterpret_cast<T*>(out), rows, Hd)));
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

@@ -11,6 +11,10 @@ int layernorm(const float* in, const float* w, const float* b, void* out, int is
 int bilinear_nhwc(const void* in, void* out, int is_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st);
 int im2col_s2(const void* in, void* A, int is_bf16, int B, int H, int W, int C, int Cp, cudaStream_t st);
 int head1x1(const float* in, const float* w, float bias, float* out, long long P, cudaStream_t st);
+// use_clstoken readout input: out [B*np, 2D] = [tok | cls[b]]  (dpt.py:153-156)
+int concat_cls(const void* tok, const void* cls, void* out, int is_bf16, int B, int np, int D, cudaStream_t st);
+// ViT-g SwiGLU gate: out [rows, Hd] = silu(x12[:, :Hd]) * x12[:, Hd:]  (swiglu_ffn.py:30-34)
+int swiglu(const void* x12, void* out, int is_bf16, long long rows, int Hd, cudaStream_t st);
 int pos_table(const float* pos, const float* cls, const float* pbias, float* tab, int D, int H, int W, cudaStream_t st);
 int pack_linear(const float* w, void* out, int is_bf16, int N, int K, int Kp, int scale_rows, float scale, cudaStream_t st);
 int pack_conv(const float* w, void* out, int is_bf16, int Co, int Ci, int taps, int Cp, cudaStream_t st);

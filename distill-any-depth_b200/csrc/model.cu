@@ -80,10 +80,19 @@ public:
     Mat patch;
     std::vector<Mat> qkv, proj, fc1, fc2;
     Mat projects[4], resize0, resize1, resize3, layer_rn[4];
+    // optional parts, switched on by the PRESENCE of their parameters (no ABI field): the use_clstoken readout
+    // (depth_head.readout_projects.{j}.0.*, dpt.py:116-122) and the ViT-g SwiGLU FFN (blocks.N.mlp.w12 / w3, swiglu_ffn.py)
+    Mat readout_proj[4];
+    std::vector<Mat> w12, w3;
     Mat rcu[4][2][2], out_conv[4], output_conv1, output_conv2_0;
     int CoP0 = 0, CoP1 = 0;
 
     int D() const { return desc.embed_dim; }
+    bool has_readout() const { return master.count("depth_head.readout_projects.0.0.weight") != 0; }
+    int swiglu_hidden() const {   // 0 = plain Mlp
+        auto it = master.find("pretrained.blocks.0.mlp.w12.weight");
+        return it == master.end() ? 0 : static_cast<int>(it->second.second / (2LL * desc.embed_dim));
+    }
 
     const float* P(const std::string& name) const {
         auto it = master.find(name);
@@ -159,25 +168,45 @@ public:
         DAD_TRY(need(p + "norm.bias", Dm));
         DAD_TRY(pack_lin(patch, mode, p + "patch_embed.proj.weight", Dm, PATCH_K, PATCH_KP, 0, st));
         qkv.resize(L); proj.resize(L); fc1.resize(L); fc2.resize(L);
+        // FFN flavour from the parameters present: Mlp (fc1 / fc2) or SwiGLUFFNFused (w12 / w3)
+        const int ffn_hidden = swiglu_hidden();
+        const bool swiglu_ffn = ffn_hidden > 0;
+        if (swiglu_ffn) {
+            DAD_REQUIRE(ffn_hidden % 8 == 0, "SwiGLU hidden width %d must be a multiple of 8", ffn_hidden);
+            w12.resize(L); w3.resize(L);
+        }
         if (!bqkv_scaled) DAD_TRY(alloc(reinterpret_cast<void**>(&bqkv_scaled), static_cast<size_t>(L) * 3 * Dm * 4));
         for (int i = 0; i < L; ++i) {
             const std::string b = p + "blocks." + std::to_string(i) + ".";
             for (const char* v : {"norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias", "ls1.gamma", "ls2.gamma",
-                                  "attn.proj.bias", "mlp.fc2.bias"})
+                                  "attn.proj.bias"})
                 DAD_TRY(need(b + v, Dm));
             DAD_TRY(need(b + "attn.qkv.bias", 3LL * Dm));
-            DAD_TRY(need(b + "mlp.fc1.bias", 4LL * Dm));
             DAD_TRY(pack_lin(qkv[i], mode, b + "attn.qkv.weight", 3 * Dm, Dm, Dm, Dm, st));  // q rows * 1/8
             DAD_TRY(copy_scale(P(b + "attn.qkv.bias"), bqkv_scaled + static_cast<long long>(i) * 3 * Dm, 3LL * Dm, Dm,
                                0.125f, st));
             DAD_TRY(pack_lin(proj[i], mode, b + "attn.proj.weight", Dm, Dm, Dm, 0, st));
-            DAD_TRY(pack_lin(fc1[i], mode, b + "mlp.fc1.weight", 4 * Dm, Dm, Dm, 0, st));
-            DAD_TRY(pack_lin(fc2[i], mode, b + "mlp.fc2.weight", Dm, 4 * Dm, 4 * Dm, 0, st));
+            if (swiglu_ffn) {   // x12 = w12(x); w3(silu(x1) * x2)
+                DAD_TRY(need(b + "mlp.w12.bias", 2LL * ffn_hidden));
+                DAD_TRY(need(b + "mlp.w3.bias", Dm));
+                DAD_TRY(pack_lin(w12[i], mode, b + "mlp.w12.weight", 2 * ffn_hidden, Dm, Dm, 0, st));
+                DAD_TRY(pack_lin(w3[i], mode, b + "mlp.w3.weight", Dm, ffn_hidden, ffn_hidden, 0, st));
+            } else {
+                DAD_TRY(need(b + "mlp.fc1.bias", 4LL * Dm));
+                DAD_TRY(need(b + "mlp.fc2.bias", Dm));
+                DAD_TRY(pack_lin(fc1[i], mode, b + "mlp.fc1.weight", 4 * Dm, Dm, Dm, 0, st));
+                DAD_TRY(pack_lin(fc2[i], mode, b + "mlp.fc2.weight", Dm, 4 * Dm, 4 * Dm, 0, st));
+            }
         }
         const std::string h = "depth_head.";
         for (int j = 0; j < 4; ++j) {
             DAD_TRY(pack_lin(projects[j], mode, h + "projects." + std::to_string(j) + ".weight", oc[j], Dm, Dm, 0, st));
             DAD_TRY(need(h + "projects." + std::to_string(j) + ".bias", oc[j]));
+        }
+        for (int j = 0; has_readout() && j < 4; ++j) {   // Linear(2D -> D) + GELU on cat(patch tokens, cls)
+            const std::string r = h + "readout_projects." + std::to_string(j) + ".0.";
+            DAD_TRY(pack_lin(readout_proj[j], mode, r + "weight", Dm, 2 * Dm, 2 * Dm, 0, st));
+            DAD_TRY(need(r + "bias", Dm));
         }
         DAD_TRY(pack_ct(resize0, mode, h + "resize_layers.0.weight", oc[0], 4, CoP0, st));
         DAD_TRY(pack_ct(resize1, mode, h + "resize_layers.1.weight", oc[1], 2, CoP1, st));
@@ -361,9 +390,16 @@ public:
         void* ln = ar.take(M * Dm * es);
         void* qkvb = ar.take(M * 3 * Dm * es);
         void* att = ar.take(M * Dm * es);
-        void* hid = ar.take(M * 4 * Dm * es);
+        // optional parts (read from the parameter set, so the workspace query works before dad_model_prepare as well)
+        const bool readout = has_readout(), swiglu_ffn = swiglu_hidden() > 0;
+        const int Hd = swiglu_hidden();
+        void* hid = ar.take(M * (swiglu_ffn ? 2 * Hd : 4 * Dm) * es);
+        void* gated = swiglu_ffn ? ar.take(M * Hd * es) : nullptr;
         void* tapbuf[4];
         for (int j = 0; j < 4; ++j) tapbuf[j] = ar.take(Mp * Dm * es);
+        void* tapraw = readout ? ar.take(Mp * Dm * es) : nullptr;       // normalised patch tokens before the readout
+        void* clsbuf = readout ? ar.take(static_cast<size_t>(B) * Dm * es) : nullptr;
+        void* catbuf = readout ? ar.take(Mp * 2 * Dm * es) : nullptr;   // [patch | cls] rows
         DAD_REQUIRE(!ar.overflow, "forward: workspace arena overflow (encoder)");
         if (!dry) {
             debug_label("patch_im2col");
@@ -384,17 +420,37 @@ public:
                 DAD_TRY(linear(mode, att, M, Dm, proj[i], ep, dry, st));
                 debug_label(("block " + std::to_string(i) + " ln2").c_str());
                 DAD_TRY(layernorm(xres, P(b + "norm2.weight"), P(b + "norm2.bias"), ln, bf, nullptr, M, Dm, 1, 1, 0, LN_EPS, st));
-                Epilogue e1; e1.bias = P(b + "mlp.fc1.bias"); e1.act = ACT_GELU; e1.out = hid; e1.out_bf16 = bf;
-                DAD_TRY(linear(mode, ln, M, Dm, fc1[i], e1, dry, st));
-                Epilogue e2; e2.bias = P(b + "mlp.fc2.bias"); e2.gamma = P(b + "ls2.gamma"); e2.res1 = xres; e2.out = xres;
-                DAD_TRY(linear(mode, hid, M, 4 * Dm, fc2[i], e2, dry, st));
+                if (swiglu_ffn) {
+                    Epilogue e1; e1.bias = P(b + "mlp.w12.bias"); e1.out = hid; e1.out_bf16 = bf;
+                    DAD_TRY(linear(mode, ln, M, Dm, w12[i], e1, dry, st));
+                    debug_label("swiglu gate");
+                    DAD_TRY(swiglu(hid, gated, bf, M, Hd, st));
+                    Epilogue e2; e2.bias = P(b + "mlp.w3.bias"); e2.gamma = P(b + "ls2.gamma"); e2.res1 = xres; e2.out = xres;
+                    DAD_TRY(linear(mode, gated, M, Hd, w3[i], e2, dry, st));
+                } else {
+                    Epilogue e1; e1.bias = P(b + "mlp.fc1.bias"); e1.act = ACT_GELU; e1.out = hid; e1.out_bf16 = bf;
+                    DAD_TRY(linear(mode, ln, M, Dm, fc1[i], e1, dry, st));
+                    Epilogue e2; e2.bias = P(b + "mlp.fc2.bias"); e2.gamma = P(b + "ls2.gamma"); e2.res1 = xres; e2.out = xres;
+                    DAD_TRY(linear(mode, hid, M, 4 * Dm, fc2[i], e2, dry, st));
+                }
                 if (i == 0) DAD_TRY(capture("block0", xres, false, M * Dm, st));
                 if (i == L - 1) DAD_TRY(capture("block_last", xres, false, M * Dm, st));
                 if (tj < 4 && i == desc.taps[tj]) {
                     // final LayerNorm on the tapped residual, cls row dropped (dinov2.py:310-312)
                     debug_label("tap layernorm");
-                    DAD_TRY(layernorm(xres, P(p + "norm.weight"), P(p + "norm.bias"), tapbuf[tj], bf,
+                    DAD_TRY(layernorm(xres, P(p + "norm.weight"), P(p + "norm.bias"), readout ? tapraw : tapbuf[tj], bf,
                                       (tj == 3) ? feat_out : nullptr, Mp, Dm, np, T, 1, LN_EPS, st));
+                    if (readout) {
+                        // dpt.py:153-156: x = GELU(Linear(cat(x, cls.expand_as(x)))); features[3][0] (feat_out) stays the
+                        // plain normalised patch tokens
+                        const std::string r = "depth_head.readout_projects." + std::to_string(tj) + ".0.";
+                        debug_label("readout: cls layernorm + concat + project");
+                        DAD_TRY(layernorm(xres, P(p + "norm.weight"), P(p + "norm.bias"), clsbuf, bf, nullptr, B, Dm, 1, T, 0,
+                                          LN_EPS, st));
+                        DAD_TRY(concat_cls(tapraw, clsbuf, catbuf, bf, B, np, Dm, st));
+                        Epilogue er; er.bias = P(r + "bias"); er.act = ACT_GELU; er.out = tapbuf[tj]; er.out_bf16 = bf;
+                        DAD_TRY(linear(mode, catbuf, Mp, 2 * Dm, readout_proj[tj], er, dry, st));
+                    }
                     ++tj;
                 }
             }
@@ -495,7 +551,9 @@ int train_checks(Model& m, int B, int H, int W, int mode) {
     DAD_REQUIRE(B > 0 && H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0,
                 "input must be [B,3,H,W] with H, W positive multiples of 14 (got B=%d H=%d W=%d)", B, H, W);
     DAD_REQUIRE(static_cast<long long>(B) * (1 + (H / 14) * (W / 14)) < (1LL << 31) / 4, "batch too large for 32-bit row indices");
-    (void)m;
+    if (m.has_readout() || m.swiglu_hidden() > 0)
+        return set_error(DAD_ERR_UNSUPPORTED, "training (dad_forward_train / dad_backward) covers the Mlp encoder without the "
+                                              "use_clstoken readout; ViT-g / SwiGLU and use_clstoken are forward-only");
     return DAD_OK;
 }
 

@@ -10,6 +10,9 @@ Training: in ``precision = "fp32"`` the outputs are differenti
 parameters - ``loss.backward()`` (tools/train_distillation.py:1556-1575) runs ``dad_backward`` behind a
 ``torch.autograd.Function`` and fills ``.grad`` of every parameter the reference's autograd would reach.  In
 ``precision = "bf16"`` the forward is inference-only and its outputs are detached.
+
+Options: ``encoder="vitg"`` (SwiGLU FFN, dinov2.py:381-395) and ``use_clstoken=True`` (readout
+projection, dpt.py:116-122, 153-156) run forward-only; ``use_bn=True`` raises ``NotImplementedError``.
 """
 import ctypes
 import math
@@ -26,6 +29,8 @@ ENCODERS = {  # dinov2.py:339-378
     "vits": dict(embed_dim=384, depth=12, num_heads=6),
     "vitb": dict(embed_dim=768, depth=12, num_heads=12),
     "vitl": dict(embed_dim=1024, depth=24, num_heads=16),
+    # vit_giant2 (dinov2.py:381-395) with ffn_layer="swiglufused" (dinov2.py:410): forward-only here
+    "vitg": dict(embed_dim=1536, depth=40, num_heads=24, ffn="swiglu"),
 }
 INTERMEDIATE_LAYER_IDX = {  # dpt.py:198-203
     "vits": [2, 5, 8, 11], "vitb": [2, 5, 8, 11], "vitl": [4, 11, 17, 23], "vitg": [9, 19, 29, 39],
@@ -50,7 +55,12 @@ class _LayerScale(_Params):
         self.gamma = nn.Parameter(init_values * torch.ones(dim))
 
 
-def _make_block(dim, init_values):
+def swiglu_hidden(dim, mlp_ratio=4):
+    """SwiGLUFFNFused's hidden width (swiglu_ffn.py:55-56): 2/3 of mlp_ratio * dim, rounded up to a multiple of 8."""
+    return (int(int(dim * mlp_ratio) * 2 / 3) + 7) // 8 * 8
+
+
+def _make_block(dim, init_values, ffn="mlp"):
     b = _Params()
     b.norm1 = nn.LayerNorm(dim, eps=1e-6)
     b.attn = _Params()
@@ -59,8 +69,13 @@ def _make_block(dim, init_values):
     b.ls1 = _LayerScale(dim, init_values)
     b.norm2 = nn.LayerNorm(dim, eps=1e-6)
     b.mlp = _Params()
-    b.mlp.fc1 = nn.Linear(dim, 4 * dim, bias=True)
-    b.mlp.fc2 = nn.Linear(4 * dim, dim, bias=True)
+    if ffn == "swiglu":  # SwiGLUFFN (swiglu_ffn.py:13-34): w3(silu(x1) * x2) with x1, x2 = w12(x).chunk(2)
+        hid = swiglu_hidden(dim)
+        b.mlp.w12 = nn.Linear(dim, 2 * hid, bias=True)
+        b.mlp.w3 = nn.Linear(hid, dim, bias=True)
+    else:
+        b.mlp.fc1 = nn.Linear(dim, 4 * dim, bias=True)
+        b.mlp.fc2 = nn.Linear(4 * dim, dim, bias=True)
     b.ls2 = _LayerScale(dim, init_values)
     return b
 
@@ -71,8 +86,6 @@ class DinoV2Params(_Params):
     def __init__(self, encoder, init_values=1.0, chunked=False, mask_token=True):
         super().__init__()
         if encoder not in ENCODERS:
-            if encoder == "vitg":
-                raise NotImplementedError("vitg / SwiGLU is outside the hot path (SURVEY.md 8a)")
             raise KeyError(encoder)  # as model_zoo[model_name] in dinov2.py:406
         cfg = ENCODERS[encoder]
         D = cfg["embed_dim"]
@@ -88,7 +101,7 @@ class DinoV2Params(_Params):
         self.pos_embed = nn.Parameter(torch.zeros(1, 37 * 37 + 1, D))
         if mask_token:
             self.mask_token = nn.Parameter(torch.zeros(1, D))
-        blocks = [_make_block(D, init_values) for _ in range(cfg["depth"])]
+        blocks = [_make_block(D, init_values, cfg.get("ffn", "mlp")) for _ in range(cfg["depth"])]
         # teacher layout (ViT_DINO.py:592): one BlockChunk holding all blocks -> keys blocks.0.N.*
         self.blocks = nn.ModuleList([nn.ModuleList(blocks)]) if chunked else nn.ModuleList(blocks)
         self.norm = nn.LayerNorm(D, eps=1e-6)
@@ -108,8 +121,6 @@ class DPTHead(_Params):
         super().__init__()
         if use_bn:
             raise NotImplementedError("use_bn=True is outside the hot path (no caller enables it)")
-        if use_clstoken:
-            raise NotImplementedError("use_clstoken=True is outside the hot path (no caller enables it)")
         oc = list(out_channels)
         self.use_clstoken = use_clstoken
         self.projects = nn.ModuleList([nn.Conv2d(in_channels, c, 1) for c in oc])
@@ -118,6 +129,9 @@ class DPTHead(_Params):
             nn.ConvTranspose2d(oc[1], oc[1], kernel_size=2, stride=2),
             nn.Identity(),
             nn.Conv2d(oc[3], oc[3], kernel_size=3, stride=2, padding=1)])
+        if use_clstoken:  # dpt.py:116-122; forward-only here
+            self.readout_projects = nn.ModuleList(
+                [nn.Sequential(nn.Linear(2 * in_channels, in_channels), nn.GELU()) for _ in oc])
         sc = _Params()
         for i in range(4):
             setattr(sc, f"layer{i + 1}_rn", nn.Conv2d(oc[i], features, 3, padding=1, bias=False))
@@ -218,6 +232,9 @@ class _NativeDepthModel(nn.Module):
         if (mode == 1 or self.bf16_backward) and captures is None and torch.is_grad_enabled():
             live = [(k, p) for k, p in self.named_parameters()
                     if p.requires_grad and not any(u in k for u in self._UNUSED)]
+            if live and (self._desc["encoder"] == "vitg" or self.depth_head.use_clstoken):
+                raise NotImplementedError("ViT-g / SwiGLU and the use_clstoken readout are forward-only here: run under "
+                                          "torch.no_grad() (the training backward covers the Mlp encoder, SURVEY.md 8f N1)")
             if live:
                 return _TrainForward.apply(self, x, mode, tuple(k for k, _ in live), *[p for _, p in live])
         return self._run_native(x, mode, captures)

@@ -14,16 +14,18 @@ ENCODERS = {
     "vits": dict(embed_dim=384, depth=12, num_heads=6, taps=[2, 5, 8, 11]),
     "vitb": dict(embed_dim=768, depth=12, num_heads=12, taps=[2, 5, 8, 11]),
     "vitl": dict(embed_dim=1024, depth=24, num_heads=16, taps=[4, 11, 17, 23]),
+    "vitg": dict(embed_dim=1536, depth=40, num_heads=24, taps=[9, 19, 29, 39], ffn_hidden=4096),  # SwiGLU, dinov2.py:381-395
 }
 MODEL_PRESETS = {  # tools/train_distillation.py:713-730, :802-808; BASELINE.json configs
     "vits": dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384]),
     "vitb": dict(encoder="vitb", features=128, out_channels=[96, 192, 384, 768]),
     "vitl": dict(encoder="vitl", features=256, out_channels=[256, 512, 1024, 1024]),
+    "vitg": dict(encoder="vitg", features=384, out_channels=[1536, 1536, 1536, 1536]),  # Depth-Anything-V2 giant config
 }
 
 
-def param_shapes(encoder, features, out_channels):
-    """Ordered {key: shape} of the student state dict."""
+def param_shapes(encoder, features, out_channels, use_clstoken=False):
+    """Ordered {key: shape} of the student state dict (``use_clstoken`` appends the readout projections, dpt.py:116-122)."""
     cfg = ENCODERS[encoder]
     D, L = cfg["embed_dim"], cfg["depth"]
     s = {}
@@ -40,8 +42,13 @@ def param_shapes(encoder, features, out_channels):
         s[b + "attn.proj.weight"] = (D, D); s[b + "attn.proj.bias"] = (D,)
         s[b + "ls1.gamma"] = (D,)
         s[b + "norm2.weight"] = (D,); s[b + "norm2.bias"] = (D,)
-        s[b + "mlp.fc1.weight"] = (4 * D, D); s[b + "mlp.fc1.bias"] = (4 * D,)
-        s[b + "mlp.fc2.weight"] = (D, 4 * D); s[b + "mlp.fc2.bias"] = (D,)
+        if "ffn_hidden" in cfg:  # SwiGLUFFNFused (swiglu_ffn.py:44-63)
+            Hd = cfg["ffn_hidden"]
+            s[b + "mlp.w12.weight"] = (2 * Hd, D); s[b + "mlp.w12.bias"] = (2 * Hd,)
+            s[b + "mlp.w3.weight"] = (D, Hd); s[b + "mlp.w3.bias"] = (D,)
+        else:
+            s[b + "mlp.fc1.weight"] = (4 * D, D); s[b + "mlp.fc1.bias"] = (4 * D,)
+            s[b + "mlp.fc2.weight"] = (D, 4 * D); s[b + "mlp.fc2.bias"] = (D,)
         s[b + "ls2.gamma"] = (D,)
     s[p + "norm.weight"] = (D,); s[p + "norm.bias"] = (D,)
     h = "depth_head."
@@ -64,17 +71,20 @@ def param_shapes(encoder, features, out_channels):
     s[sc + "output_conv1.weight"] = (Fe // 2, Fe, 3, 3); s[sc + "output_conv1.bias"] = (Fe // 2,)
     s[sc + "output_conv2.0.weight"] = (32, Fe // 2, 3, 3); s[sc + "output_conv2.0.bias"] = (32,)
     s[sc + "output_conv2.2.weight"] = (1, 32, 1, 1); s[sc + "output_conv2.2.bias"] = (1,)
+    if use_clstoken:  # appended last so the other tensors keep the values they have without the option
+        for i in range(4):
+            s[h + f"readout_projects.{i}.0.weight"] = (D, 2 * D); s[h + f"readout_projects.{i}.0.bias"] = (D,)
     return s
 
 
 def make_state_dict(encoder="vits", features=64, out_channels=(48, 96, 192, 384), seed=0,
-                    head_bias=0.25, head_gain=6.0):
+                    head_bias=0.25, head_gain=6.0, use_clstoken=False):
     """Random-init weights: Linear N(0, 0.02) (dinov2.py:331-336), conv
     U(+-1/sqrt(fan_in)) (PyTorch default), small random biases so every bias path
     is exercised, LayerNorm/LayerScale around 1, final bias ``head_bias`` > 0."""
     rng = np.random.Generator(np.random.PCG64(seed))
     sd = {}
-    for k, shp in param_shapes(encoder, features, out_channels).items():
+    for k, shp in param_shapes(encoder, features, out_channels, use_clstoken).items():
         n = int(np.prod(shp))
         leaf = k.rsplit(".", 1)[-1]
         if k.endswith("gamma"):
@@ -87,6 +97,9 @@ def make_state_dict(encoder="vits", features=64, out_channels=(48, 96, 192, 384)
             v = 0.02 * rng.standard_normal(n, dtype=np.float32)
         elif leaf in ("cls_token", "pos_embed", "mask_token"):
             v = 0.02 * rng.standard_normal(n, dtype=np.float32)
+        elif leaf == "weight" and len(shp) == 2:  # head Linear layers (readout): PyTorch default U(+-1/sqrt(fan_in))
+            bound = 1.0 / math.sqrt(shp[1])
+            v = rng.uniform(-bound, bound, n).astype(np.float32)
         elif leaf == "weight":  # convs
             fan_in = shp[1] * shp[2] * shp[3]
             bound = 1.0 / math.sqrt(max(fan_in, 1))

@@ -17,6 +17,7 @@ VIT_CONFIGS = {
     "vits": dict(embed_dim=384, depth=12, num_heads=6, taps=[2, 5, 8, 11]),
     "vitb": dict(embed_dim=768, depth=12, num_heads=12, taps=[2, 5, 8, 11]),
     "vitl": dict(embed_dim=1024, depth=24, num_heads=16, taps=[4, 11, 17, 23]),
+    "vitg": dict(embed_dim=1536, depth=40, num_heads=24, taps=[9, 19, 29, 39]),  # dinov2.py:381-395, SwiGLU FFN
 }
 PATCH = 14
 LN_EPS = 1e-6  # dinov2.py:95
@@ -76,9 +77,13 @@ def _block(x, sd, p, num_heads):
     h = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], LN_EPS)
     x = x + _attention(h, sd, p + "attn.", num_heads) * sd[p + "ls1.gamma"]
     h = F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], LN_EPS)
-    h = F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
-    h = F.gelu(h)  # exact erf (nn.GELU default, dinov2.py:61)
-    h = F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+    if p + "mlp.w12.weight" in sd:  # SwiGLUFFN.forward, dinov2_layers/swiglu_ffn.py:30-34 (ViT-g, dinov2.py:410)
+        x1, x2 = F.linear(h, sd[p + "mlp.w12.weight"], sd[p + "mlp.w12.bias"]).chunk(2, dim=-1)
+        h = F.linear(F.silu(x1) * x2, sd[p + "mlp.w3.weight"], sd[p + "mlp.w3.bias"])
+    else:
+        h = F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
+        h = F.gelu(h)  # exact erf (nn.GELU default, dinov2.py:61)
+        h = F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
     return x + h * sd[p + "ls2.gamma"]
 
 
@@ -138,12 +143,17 @@ def _fusion(sd, p, x0, x1=None, size=None):
 
 
 def dpt_head_forward(feats, sd, ph, pw, return_intermediates=False):
-    """dpt.py:150-184 (use_clstoken=False).  Returns the map BEFORE the final
+    """dpt.py:150-184; the use_clstoken readout (:153-156) is applied when the state dict holds
+    ``readout_projects``.  Returns the map BEFORE the final
     head ReLUs are all applied the reference way: conv3x3 -> ReLU -> conv1x1 -> ReLU."""
     h = "depth_head."
     outs = []
-    for i, (x, _cls) in enumerate(feats):
+    for i, (x, cls) in enumerate(feats):
         B, _, D = x.shape
+        if h + "readout_projects.0.0.weight" in sd:
+            readout = cls.unsqueeze(1).expand_as(x)
+            x = F.gelu(F.linear(torch.cat((x, readout), -1), sd[h + f"readout_projects.{i}.0.weight"],
+                                sd[h + f"readout_projects.{i}.0.bias"]))
         x = x.permute(0, 2, 1).contiguous().reshape(B, D, ph, pw)
         x = F.conv2d(x, sd[h + f"projects.{i}.weight"], sd[h + f"projects.{i}.bias"])
         if i == 0:

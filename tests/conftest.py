@@ -22,3 +22,9 @@ def golden_model():
 def golden_losses():
     import numpy as np
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_losses.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_model_options():
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_model_options.npz")))

@@ -49,17 +49,33 @@ def test_options_outside_the_hot_path_raise():
     with pytest.raises(KeyError):
         d.DepthAnythingV2(encoder="vitx")
     with pytest.raises(NotImplementedError):
-        d.DepthAnythingV2(encoder="vitg")
-    with pytest.raises(NotImplementedError):
         d.DepthAnythingV2(use_bn=True, **kw)
-    with pytest.raises(NotImplementedError):
-        d.DepthAnythingV2(use_clstoken=True, **kw)
     with pytest.raises(NotImplementedError):
         d.DepthAnything(encoder="vitb")
     with pytest.raises(NotImplementedError):
         d.DepthAnything(use_registers=True)
     with pytest.raises(RuntimeError):  # CPU tensor: no fallback
         d.get_contexts_ds(3, torch.ones(1, 1, 4, 4, dtype=torch.bool))
+
+
+def test_option_key_layouts_match_the_reference():
+    """use_clstoken adds depth_head.readout_projects.{i}.0.{weight,bias} (dpt.py:116-122); vitg swaps the
+    Mlp for SwiGLUFFNFused (mlp.w12 / mlp.w3, hidden 4096 = 2/3 * 4 * 1536 rounded up to 8; swiglu_ffn.py:44-63)."""
+    import distill_any_depth_b200 as d
+    from distill_any_depth_b200.dpt import swiglu_hidden
+    kw = synthetic.MODEL_PRESETS["vits"]
+    m = d.DepthAnythingV2(use_clstoken=True, **kw)
+    want = synthetic.param_shapes(use_clstoken=True, **kw)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == want and got["depth_head.readout_projects.3.0.weight"] == (384, 768)
+    assert m.depth_head.use_clstoken is True
+    assert swiglu_hidden(1536) == 4096 and swiglu_hidden(384) == 1024
+    with torch.device("meta"):  # 1.26e9 parameters: shapes only
+        g = d.DepthAnythingV2(**synthetic.MODEL_PRESETS["vitg"])
+    got = {k: tuple(v.shape) for k, v in g.state_dict().items()}
+    assert got == synthetic.param_shapes(**synthetic.MODEL_PRESETS["vitg"])
+    assert got["pretrained.blocks.39.mlp.w12.weight"] == (8192, 1536) and "pretrained.blocks.0.mlp.fc1.weight" not in got
+    assert g.pretrained.n_blocks == 40 and g.pretrained.num_heads == 24 and g.intermediate_layer_idx["vitg"] == [9, 19, 29, 39]
 
 
 def test_product_path_refuses_cpu_tensors():

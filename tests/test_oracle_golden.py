@@ -8,6 +8,7 @@ import torch
 
 import oracle
 from oracle.make_golden import MODEL_CASES, LOSS_CASES
+from oracle.make_golden_options import OPTION_CASES
 from distill_any_depth_b200 import synthetic
 from helpers import sub
 
@@ -24,6 +25,21 @@ def test_model_matches_reference_fixture(case, golden_model):
     np.testing.assert_allclose(sub(f).numpy(), golden_model[name + "/feat_sub"], rtol=1e-4, atol=2e-5)
     st = golden_model[name + "/depth_stats"]
     assert abs(d.mean().item() - st[0]) <= 1e-5 * max(1, abs(st[0]))
+    assert abs(d.double().pow(2).sum().item() - st[2]) <= 1e-4 * st[2]
+
+
+@pytest.mark.parametrize("case", OPTION_CASES, ids=lambda c: c[0])
+def test_option_branches_match_reference_fixture(case, golden_model_options):
+    """use_clstoken readout and ViT-g / SwiGLU against the live reference's recorded outputs."""
+    name, kw, B, H, W, ws, xs, hb = case
+    sd = synthetic.make_state_dict(seed=ws, head_bias=hb, **kw)
+    x = synthetic.make_images(B, H, W, seed=xs)
+    with torch.no_grad():
+        d, f = oracle.depth_anything_forward(x, sd, kw["encoder"])
+    g = golden_model_options
+    np.testing.assert_allclose(sub(d).numpy(), g[name + "/depth_sub"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(sub(f).numpy(), g[name + "/feat_sub"], rtol=1e-4, atol=2e-5)
+    st = g[name + "/depth_stats"]
     assert abs(d.double().pow(2).sum().item() - st[2]) <= 1e-4 * st[2]
 
 
