@@ -71,7 +71,8 @@ public:
     std::vector<void*> owned;
     bool packed[2] = {false, false};
     float* bqkv_scaled = nullptr;                       // [depth][3D] qkv bias with q part * 64^-0.5
-    std::map<std::pair<int, int>, float*> pos_tables;   // (H, W) -> [1 + ph*pw, D]
+    std::map<std::pair<int, int>, float*> pos_tables;   // (H, W) -> [1 + ph*pw, D]; nullptr = stale (weights changed)
+    std::map<std::pair<int, int>, float*> pos_storage;  // the buffers behind pos_tables, reused across weight updates
     std::unordered_map<std::string, std::pair<float*, long long>> captures;
     std::unordered_map<std::string, std::pair<float*, long long>> grads;   // caller-owned fp32 gradient accumulators
     bool attn_bwd_fp32 = getenv("DAD_ATTN_BWD_FP32") != nullptr;   // A/B switch: bf16 training with the fp32 attention backward
@@ -248,9 +249,13 @@ public:
         float*& tab = pos_tables[std::make_pair(H, W)];
         const size_t rows = 1 + static_cast<size_t>(H / 14) * (W / 14);
         if (!tab) {
-            void* p = nullptr;
-            DAD_TRY(alloc(&p, rows * D() * 4));
-            tab = reinterpret_cast<float*>(p);
+            float*& buf = pos_storage[std::make_pair(H, W)];   // a training loop invalidates the table every step: no new
+            if (!buf) {                                          // allocation per update
+                void* p = nullptr;
+                DAD_TRY(alloc(&p, rows * D() * 4));
+                buf = reinterpret_cast<float*>(p);
+            }
+            tab = buf;
             DAD_TRY(pos_table(P("pretrained.pos_embed"), P("pretrained.cls_token"), P("pretrained.patch_embed.proj.bias"),
                               tab, D(), H, W, st));
         }
