@@ -12,7 +12,8 @@ parameters - ``loss.backward()`` (tools/train_distillation.py:1556-1575) runs ``
 ``precision = "bf16"`` the forward is inference-only and its outputs are detached.
 
 Options: ``encoder="vitg"`` (SwiGLU FFN, dinov2.py:381-395) and ``use_clstoken=True`` (readout
-projection, dpt.py:116-122, 153-156) run forward-only; ``use_bn=True`` raises ``NotImplementedError``.
+projection, dpt.py:116-122, 153-156) run forward-only; so does ``use_bn=True`` (util/blocks.py:49-51) in ``eval()`` mode,
+with the running statistics folded into the convolutions when the weights are synchronised.
 """
 import ctypes
 import math
@@ -119,9 +120,8 @@ class DPTHead(_Params):
     def __init__(self, in_channels, features=256, use_bn=False, out_channels=(256, 512, 1024, 1024),
                  use_clstoken=False):
         super().__init__()
-        if use_bn:
-            raise NotImplementedError("use_bn=True is outside the hot path (no caller enables it)")
         oc = list(out_channels)
+        self.use_bn = bool(use_bn)
         self.use_clstoken = use_clstoken
         self.projects = nn.ModuleList([nn.Conv2d(in_channels, c, 1) for c in oc])
         self.resize_layers = nn.ModuleList([
@@ -143,6 +143,9 @@ class DPTHead(_Params):
                 rcu = _Params()
                 rcu.conv1 = nn.Conv2d(features, features, 3, padding=1)
                 rcu.conv2 = nn.Conv2d(features, features, 3, padding=1)
+                if use_bn:  # blocks.py:49-51: BatchNorm after each conv; eval-mode statistics are folded into the conv
+                    rcu.bn1 = nn.BatchNorm2d(features)
+                    rcu.bn2 = nn.BatchNorm2d(features)
                 setattr(fb, f"resConfUnit{u}", rcu)
             setattr(sc, f"refinenet{r}", fb)
         sc.output_conv1 = nn.Conv2d(features, features // 2, 3, padding=1)
@@ -188,15 +191,20 @@ class _NativeDepthModel(nn.Module):
 
     def _sync_weights(self, device):
         params = list(self.named_parameters())
-        sig = tuple((p.data_ptr(), p._version) for _, p in params)
+        use_bn = self.depth_head.use_bn
+        buffers = list(self.named_buffers()) if use_bn else []   # BatchNorm running statistics
+        sig = tuple((p.data_ptr(), p._version) for _, p in params + buffers)
         if sig == self._sig:
             return
         lib = _lib.load()
         st = _lib.stream_ptr()
+        folded = self._fold_batchnorm() if use_bn else {}
         for k, p in params:
             if p.device != device:
                 raise RuntimeError(f"parameter {k} is on {p.device}, input on {device}: call model.to(device)")
-            t = p.detach()
+            if use_bn and (".bn1." in k or ".bn2." in k):
+                continue   # lives on inside the folded convolution
+            t = folded.get(k, p).detach()
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
             _lib.check(lib.dad_model_set_weight(self._handle, self._student_key(k).encode(), _lib.ptr(t), t.numel(), st),
@@ -204,6 +212,22 @@ class _NativeDepthModel(nn.Module):
         torch.cuda.current_stream(device).synchronize()  # temporaries above may be freed after this
         self._sig = sig
         self._prepared = set()
+
+    @torch.no_grad()
+    def _fold_batchnorm(self):
+        """use_bn=True (util/blocks.py:49-51, 67-75), eval mode: ``bn(conv(x)) = conv'(x)`` with
+        ``W' = W * a[co]``, ``b' = (b - running_mean) * a + beta``, ``a = gamma / sqrt(running_var + eps)``.
+        Returns {conv parameter key: folded fp32 tensor}; the library never sees the BatchNorm layers."""
+        out = {}
+        for name, rcu in self.depth_head.named_modules():
+            if not hasattr(rcu, "bn1"):
+                continue
+            for conv, bn, c in ((rcu.conv1, rcu.bn1, "conv1"), (rcu.conv2, rcu.bn2, "conv2")):
+                a = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+                out[f"depth_head.{name}.{c}.weight"] = (conv.weight.double() * a[:, None, None, None]).float()
+                out[f"depth_head.{name}.{c}.bias"] = ((conv.bias.double() - bn.running_mean.double()) * a
+                                                      + bn.bias.double()).float()
+        return out
 
     def __del__(self):
         try:
@@ -229,11 +253,14 @@ class _NativeDepthModel(nn.Module):
         if self.precision not in _MODES:
             raise ValueError("precision must be 'bf16' or 'fp32'")
         mode = _MODES[self.precision]
+        if self.depth_head.use_bn and self.training:
+            raise NotImplementedError("use_bn=True runs with the running statistics only (call model.eval()): batch-statistics "
+                                      "BatchNorm is outside the hot path (no caller enables use_bn)")
         if (mode == 1 or self.bf16_backward) and captures is None and torch.is_grad_enabled():
             live = [(k, p) for k, p in self.named_parameters()
                     if p.requires_grad and not any(u in k for u in self._UNUSED)]
-            if live and (self._desc["encoder"] == "vitg" or self.depth_head.use_clstoken):
-                raise NotImplementedError("ViT-g / SwiGLU and the use_clstoken readout are forward-only here: run under "
+            if live and (self._desc["encoder"] == "vitg" or self.depth_head.use_clstoken or self.depth_head.use_bn):
+                raise NotImplementedError("ViT-g / SwiGLU, the use_clstoken readout and use_bn are forward-only here: run under "
                                           "torch.no_grad() (the training backward covers the Mlp encoder, SURVEY.md 8f N1)")
             if live:
                 return _TrainForward.apply(self, x, mode, tuple(k for k, _ in live), *[p for _, p in live])

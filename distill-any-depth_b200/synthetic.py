@@ -24,8 +24,9 @@ MODEL_PRESETS = {  # tools/train_distillation.py:713-730, :802-808; BASELINE.jso
 }
 
 
-def param_shapes(encoder, features, out_channels, use_clstoken=False):
-    """Ordered {key: shape} of the student state dict (``use_clstoken`` appends the readout projections, dpt.py:116-122)."""
+def param_shapes(encoder, features, out_channels, use_clstoken=False, use_bn=False):
+    """Ordered {key: shape} of the student state dict (``use_clstoken`` appends the readout projections, dpt.py:116-122;
+    ``use_bn`` the BatchNorm parameters and buffers of the residual conv units, util/blocks.py:49-51)."""
     cfg = ENCODERS[encoder]
     D, L = cfg["embed_dim"], cfg["depth"]
     s = {}
@@ -71,6 +72,14 @@ def param_shapes(encoder, features, out_channels, use_clstoken=False):
     s[sc + "output_conv1.weight"] = (Fe // 2, Fe, 3, 3); s[sc + "output_conv1.bias"] = (Fe // 2,)
     s[sc + "output_conv2.0.weight"] = (32, Fe // 2, 3, 3); s[sc + "output_conv2.0.bias"] = (32,)
     s[sc + "output_conv2.2.weight"] = (1, 32, 1, 1); s[sc + "output_conv2.2.bias"] = (1,)
+    if use_bn:
+        for r in (1, 2, 3, 4):
+            for u in (1, 2):
+                for c in (1, 2):
+                    q = sc + f"refinenet{r}.resConfUnit{u}.bn{c}."
+                    for leaf in ("weight", "bias", "running_mean", "running_var"):
+                        s[q + leaf] = (Fe,)
+                    s[q + "num_batches_tracked"] = ()
     if use_clstoken:  # appended last so the other tensors keep the values they have without the option
         for i in range(4):
             s[h + f"readout_projects.{i}.0.weight"] = (D, 2 * D); s[h + f"readout_projects.{i}.0.bias"] = (D,)
@@ -78,16 +87,24 @@ def param_shapes(encoder, features, out_channels, use_clstoken=False):
 
 
 def make_state_dict(encoder="vits", features=64, out_channels=(48, 96, 192, 384), seed=0,
-                    head_bias=0.25, head_gain=6.0, use_clstoken=False):
+                    head_bias=0.25, head_gain=6.0, use_clstoken=False, use_bn=False):
     """Random-init weights: Linear N(0, 0.02) (dinov2.py:331-336), conv
     U(+-1/sqrt(fan_in)) (PyTorch default), small random biases so every bias path
     is exercised, LayerNorm/LayerScale around 1, final bias ``head_bias`` > 0."""
     rng = np.random.Generator(np.random.PCG64(seed))
     sd = {}
-    for k, shp in param_shapes(encoder, features, out_channels, use_clstoken).items():
+    for k, shp in param_shapes(encoder, features, out_channels, use_clstoken, use_bn).items():
         n = int(np.prod(shp))
         leaf = k.rsplit(".", 1)[-1]
-        if k.endswith("gamma"):
+        if leaf == "num_batches_tracked":
+            sd[k] = torch.tensor(100, dtype=torch.int64)
+            continue
+        if ".bn" in k:  # BatchNorm of a trained net: scale near 1, shifts / running means of the activations' order
+            v = {"weight": lambda: 1.0 + 0.1 * rng.standard_normal(n, dtype=np.float32),
+                 "bias": lambda: 0.05 * rng.standard_normal(n, dtype=np.float32),
+                 "running_mean": lambda: 0.1 * rng.standard_normal(n, dtype=np.float32),
+                 "running_var": lambda: rng.uniform(0.5, 1.5, n).astype(np.float32)}[leaf]()
+        elif k.endswith("gamma"):
             v = 1.0 + 0.1 * rng.standard_normal(n, dtype=np.float32)
         elif ".norm" in k and leaf == "weight":
             v = 1.0 + 0.1 * rng.standard_normal(n, dtype=np.float32)

@@ -1,5 +1,6 @@
 """Pin the oracle's OPTION branches against the LIVE reference: the ``use_clstoken`` readout
-(dpt.py:116-122, 153-156) and the ViT-g / SwiGLU encoder (dinov2.py:381-395, dinov2_layers/swiglu_ffn.py).
+(dpt.py:116-122, 153-156), the ViT-g / SwiGLU encoder (dinov2.py:381-395, dinov2_layers/swiglu_ffn.py) and ``use_bn``
+(util/blocks.py:49-51, eval mode).
 
 Run in the build container only:  ``python -m oracle.make_golden_options``
 
@@ -27,6 +28,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 OPTION_CASES = [
     ("vits_clstoken_70x98", dict(synthetic.MODEL_PRESETS["vits"], use_clstoken=True), 2, 70, 98, 3, 1237, 0.25),
     ("vitb_clstoken_112", dict(synthetic.MODEL_PRESETS["vitb"], use_clstoken=True), 1, 112, 112, 5, 1239, 0.25),
+    ("vits_bn_70x98", dict(synthetic.MODEL_PRESETS["vits"], use_bn=True), 2, 70, 98, 8, 1240, 0.25),
     # ViT-g encoder on the ViT-B head shape (keeps the case small); the giant head preset is a GPU-only test
     ("vitg_70x98", dict(encoder="vitg", features=128, out_channels=[96, 192, 384, 768]), 1, 70, 98, 4, 1238, 0.25),
 ]

@@ -121,11 +121,18 @@ def vit_intermediate_layers(x, sd, encoder, return_all=False):
 
 
 def _rcu(x, sd, p):
-    """util/blocks.py:67-80: conv2(relu(conv1(relu(x)))) + x (non-inplace ReLU)."""
+    """util/blocks.py:67-80: conv2(relu(conv1(relu(x)))) + x (non-inplace ReLU); BatchNorm after each conv when the
+    state dict holds ``bn1`` / ``bn2`` (use_bn=True)."""
+    def bn(t, q):  # use_bn=True (blocks.py:49-51, 69-75), eval mode: running statistics, eps = 1e-5
+        if p + q + ".weight" not in sd:
+            return t
+        return F.batch_norm(t, sd[p + q + ".running_mean"], sd[p + q + ".running_var"], sd[p + q + ".weight"],
+                            sd[p + q + ".bias"], training=False, eps=1e-5)
+
     out = F.relu(x)
-    out = F.conv2d(out, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
+    out = bn(F.conv2d(out, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1), "bn1")
     out = F.relu(out)
-    out = F.conv2d(out, sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
+    out = bn(F.conv2d(out, sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1), "bn2")
     return out + x
 
 

@@ -118,7 +118,7 @@ def test_teacher_equals_student_and_api_contract():
     with pytest.raises(KeyError):
         d.DepthAnythingV2(encoder="vitx")
     with pytest.raises(NotImplementedError):
-        d.DepthAnythingV2(encoder="vits", features=64, out_channels=[48, 96, 192, 384], use_bn=True)
+        d.DepthAnything(use_registers=True)
     # weight updates are picked up (optimizer-style in-place change)
     with torch.no_grad():
         s.depth_head.scratch.output_conv2[2].bias.add_(0.5)

@@ -1,6 +1,6 @@
-"""GPU parity of the model OPTIONS: the ``use_clstoken`` readout (dpt.py:116-122, 153-156) and the
-ViT-g / SwiGLU encoder (dinov2.py:381-395, dinov2_layers/swiglu_ffn.py), forward-only, through the same front-end and
-C ABI as the main path.  Same tolerances as test_gpu_model.py: relative depth error <= 1e-4 (fp32 engine) / 2e-2 (bf16)."""
+"""GPU parity of the model OPTIONS: the ``use_clstoken`` readout (dpt.py:116-122, 153-156), the
+ViT-g / SwiGLU encoder (dinov2.py:381-395, dinov2_layers/swiglu_ffn.py) and ``use_bn`` (util/blocks.py:49-51, eval mode),
+forward-only, through the same front-end and C ABI as the main path.  Same tolerances as test_gpu_model.py: relative depth error <= 1e-4 (fp32 engine) / 2e-2 (bf16)."""
 import pytest
 import torch
 
@@ -87,6 +87,27 @@ def test_vitg_giant_head_engines_agree():
     assert rel32 <= 1e-4, rel32
     assert f_err <= 1e-4, f_err
     assert rel16 <= 2e-2, rel16
+
+
+def test_use_bn_tracks_running_statistics_updates():
+    """The folded convolutions are rebuilt when a BatchNorm BUFFER changes (buffers are part of the weight signature)."""
+    kw = dict(synthetic.MODEL_PRESETS["vits"], use_bn=True)
+    m, sd = build(kw, 8)
+    m.precision = "fp32"
+    x = synthetic.make_images(1, 70, 98, seed=1240)
+    with torch.no_grad():
+        d0, _ = m(x.cuda())
+        bn = m.depth_head.scratch.refinenet1.resConfUnit2.bn2
+        bn.running_mean.add_(0.5)
+        d1, _ = m(x.cuda())
+        sd2 = dict(sd)
+        sd2["depth_head.scratch.refinenet1.resConfUnit2.bn2.running_mean"] = bn.running_mean.cpu().clone()
+        d_ref, _ = oracle.depth_anything_forward(x, sd2, "vits")
+    assert (d1 - d0).abs().max().item() > 1e-3
+    assert rel_depth_err(d1.cpu(), d_ref).max().item() <= 1e-4
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(x.cuda())
 
 
 def test_options_are_forward_only():

@@ -49,8 +49,6 @@ def test_options_outside_the_hot_path_raise():
     with pytest.raises(KeyError):
         d.DepthAnythingV2(encoder="vitx")
     with pytest.raises(NotImplementedError):
-        d.DepthAnythingV2(use_bn=True, **kw)
-    with pytest.raises(NotImplementedError):
         d.DepthAnything(encoder="vitb")
     with pytest.raises(NotImplementedError):
         d.DepthAnything(use_registers=True)
@@ -76,6 +74,31 @@ def test_option_key_layouts_match_the_reference():
     assert got == synthetic.param_shapes(**synthetic.MODEL_PRESETS["vitg"])
     assert got["pretrained.blocks.39.mlp.w12.weight"] == (8192, 1536) and "pretrained.blocks.0.mlp.fc1.weight" not in got
     assert g.pretrained.n_blocks == 40 and g.pretrained.num_heads == 24 and g.intermediate_layer_idx["vitg"] == [9, 19, 29, 39]
+
+
+def test_use_bn_folding_reproduces_the_batchnorm_graph():
+    """use_bn=True (util/blocks.py:49-51): the front-end folds the eval-mode BatchNorm into the conv it follows before the
+    weights reach the library.  Host arithmetic only, so it is checked here: the oracle on the folded state dict (no bn
+    keys) equals the oracle on the BatchNorm graph, which is pinned to the live reference (golden vits_bn_70x98)."""
+    import distill_any_depth_b200 as d
+    import oracle
+    kw = dict(synthetic.MODEL_PRESETS["vits"], use_bn=True)
+    sd = synthetic.make_state_dict(seed=8, **kw)
+    m = d.DepthAnythingV2(**kw)
+    m.load_state_dict(sd, strict=True)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == synthetic.param_shapes(**kw)
+    folded = m._fold_batchnorm()
+    assert len(folded) == 4 * 2 * 2 * 2  # 4 fusion blocks x 2 units x 2 convs x (weight, bias)
+    plain = {k: folded.get(k, v) for k, v in sd.items() if ".bn1." not in k and ".bn2." not in k}
+    x = synthetic.make_images(1, 70, 98, seed=1240)
+    with torch.no_grad():
+        want, _ = oracle.depth_anything_forward(x, sd, "vits")
+        got, _ = oracle.depth_anything_forward(x, plain, "vits")
+    assert (got - want).abs().max().item() <= 2e-6 * want.abs().max().item()
+    # batch-statistics mode is not offered: the check runs before any device work
+    m.train()
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        m(x)
 
 
 def test_product_path_refuses_cpu_tensors():
