@@ -286,6 +286,30 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const void* pre, const vo
     }
 }
 
+// SwiGLU gate (swiglu_ffn.py:30-34): g = silu(x1) * x2 with [x1 | x2] = x12 row; dx1 = dg * x2 * sig * (1 + x1 * (1 - sig)),
+// dx2 = dg * silu(x1)
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const void* x12, const void* dg, void* dx12, int bf, long long rows, int Hd) {
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= rows * Hd) return;
+    const long long r = i / Hd;
+    const int c = static_cast<int>(i - r * Hd);
+    const long long o = r * 2 * Hd + c;
+    const float x1 = ldf(x12, o, bf), x2 = ldf(x12, o + Hd, bf), g = ldf(dg, i, bf);
+    const float sig = 1.0f / (1.0f + expf(-x1));
+    stf(dx12, o, bf, g * x2 * sig * (1.0f + x1 * (1.0f - sig)));
+    stf(dx12, o + Hd, bf, g * x1 * sig);
+}
+
+// dst[r * ldd + c] = src[r * lds + c] for c < cols (same element type): column slices of the readout's concat gradient
+__global__ void __launch_bounds__(256) copy_cols_kernel(const void* src, long long lds, void* dst, long long ldd, long long rows,
+                                                        int cols, int bf) {
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    stf(dst, r * ldd + c, bf, ldf(src, r * lds + c, bf));
+}
+
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const void* g, const void* y, const void* add, void* out, int bf, long long n) {
     const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
     if (i < n) stf(out, i, bf, (add ? ldf(add, i, bf) : 0.f) + (ldf(y, i, bf) > 0.f ? ldf(g, i, bf) : 0.f));
@@ -776,6 +800,22 @@ int gelu_bwd(const void* pre, const void* dout, void* dpre, int bf, long long n,
     debug_label("gelu_bwd");
     ProfScope prof(PROF_ELEM, static_cast<double>(n) * 12, st);
     gelu_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(pre, dout, dpre, bf, n);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int swiglu_bwd(const void* x12, const void* dg, void* dx12, int bf, long long rows, int Hd, cudaStream_t st) {
+    debug_label("swiglu_bwd");
+    ProfScope prof(PROF_ELEM, static_cast<double>(rows) * Hd * (bf ? 10 : 20), st);
+    swiglu_bwd_kernel<<<blocks_for(rows * Hd), 256, 0, st>>>(x12, dg, dx12, bf, rows, Hd);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int copy_cols(const void* src, long long lds, void* dst, long long ldd, long long rows, int cols, int bf, cudaStream_t st) {
+    debug_label("copy_cols");
+    ProfScope prof(PROF_ELEM, static_cast<double>(rows) * cols * (bf ? 4 : 8), st);
+    copy_cols_kernel<<<blocks_for(rows * cols), 256, 0, st>>>(src, lds, dst, ldd, rows, cols, bf);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

@@ -40,6 +40,10 @@ int layernorm_bwd(const float* x, const float* w, const void* dy, int dy_bf16, f
 int ls_residual(const float* xold, const void* y, int bf, const float* gamma, float* xnew, long long rows, int D, cudaStream_t st);
 int gelu_fwd(const void* pre, void* out, int bf, long long n, cudaStream_t st);
 int gelu_bwd(const void* pre, const void* dout, void* dpre, int bf, long long n, cudaStream_t st);
+// SwiGLU gate adjoint: x12 [rows, 2*Hd] = [x1 | x2], dg [rows, Hd] -> dx12 [rows, 2*Hd]  (swiglu_ffn.py:30-34)
+int swiglu_bwd(const void* x12, const void* dg, void* dx12, int bf, long long rows, int Hd, cudaStream_t st);
+// dst[r*ldd + c] = src[r*lds + c], c < cols (one element type)
+int copy_cols(const void* src, long long lds, void* dst, long long ldd, long long rows, int cols, int bf, cudaStream_t st);
 // out = (add ? add : 0) + g * (y > 0)
 int relu_bwd(const void* g, const void* y, const void* add, void* out, int bf, long long n, cudaStream_t st);
 int add_inplace(void* dst, int bf, const float* src, long long n, cudaStream_t st);   // dst += src (fp32)

@@ -556,9 +556,7 @@ int train_checks(Model& m, int B, int H, int W, int mode) {
     DAD_REQUIRE(B > 0 && H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0,
                 "input must be [B,3,H,W] with H, W positive multiples of 14 (got B=%d H=%d W=%d)", B, H, W);
     DAD_REQUIRE(static_cast<long long>(B) * (1 + (H / 14) * (W / 14)) < (1LL << 31) / 4, "batch too large for 32-bit row indices");
-    if (m.has_readout() || m.swiglu_hidden() > 0)
-        return set_error(DAD_ERR_UNSUPPORTED, "training (dad_forward_train / dad_backward) covers the Mlp encoder without the "
-                                              "use_clstoken readout; ViT-g / SwiGLU and use_clstoken are forward-only");
+    (void)m;
     return DAD_OK;
 }
 

@@ -45,6 +45,9 @@ struct Tape {
     std::vector<BlockTape> blk;
     float* xfinal = nullptr;
     void *tap[4], *pj[4], *rj[4], *lrn[4], *lrn_relu[4];
+    // use_clstoken readout (dpt.py:153-156): normalised patch tokens, normalised class tokens, [patch | cls] rows, pre-GELU
+    void *tapraw[4] = {nullptr, nullptr, nullptr, nullptr}, *cls[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *cat[4] = {nullptr, nullptr, nullptr, nullptr}, *rpre[4] = {nullptr, nullptr, nullptr, nullptr};
     FusionTape fu[4];
     void *o1 = nullptr, *up = nullptr, *t32 = nullptr;
     float* depth = nullptr;
@@ -62,12 +65,15 @@ struct Trainer {
     int Dm, L, F, heads, ph, pw, np, T;
     long long M, Mp;
     const int* oc;
+    int Hd = 0;             // SwiGLU hidden width (ViT-g); 0 = Mlp with GELU
+    bool readout = false;   // use_clstoken readout projections present
 
     Trainer(Model& model, int B_, int H_, int W_, int mode_, bool dry_, cudaStream_t st_)
         : m(model), B(B_), H(H_), W(W_), mode(mode_), bf(mode_ == 0), es(mode_ == 0 ? 2 : 4), dry(dry_), st(st_) {
         Dm = m.D(); L = m.desc.depth; F = m.desc.features; heads = m.desc.num_heads; oc = m.desc.out_channels;
         ph = H / 14; pw = W / 14; np = ph * pw; T = np + 1;
         M = static_cast<long long>(B) * T; Mp = static_cast<long long>(B) * np;
+        Hd = m.swiglu_hidden(); readout = m.has_readout();
     }
 
 #define RUN(expr) do { if (!dry) DAD_TRY(expr); } while (0)
@@ -88,7 +94,9 @@ struct Trainer {
         for (int i = 0; i < L; ++i) {
             BlockTape& b = t.blk[i];
             b.x0 = ar.f(M * Dm); b.n1 = a(ar, M * Dm); b.qkv = a(ar, M * 3 * Dm); b.att = a(ar, M * Dm); b.y1 = a(ar, M * Dm);
-            b.x1 = ar.f(M * Dm); b.n2 = a(ar, M * Dm); b.hpre = a(ar, M * 4 * Dm); b.h = a(ar, M * 4 * Dm); b.y2 = a(ar, M * Dm);
+            // Mlp: fc1 pre-activation and GELU output [M, 4D]; SwiGLU: x12 = w12(n2) [M, 2*Hd] and the gated product [M, Hd]
+            b.x1 = ar.f(M * Dm); b.n2 = a(ar, M * Dm); b.hpre = a(ar, M * (Hd ? 2 * Hd : 4 * Dm)); b.h = a(ar, M * (Hd ? Hd : 4 * Dm));
+            b.y2 = a(ar, M * Dm);
         }
         t.xfinal = ar.f(M * Dm);
         const int hs[4] = {4 * ph, 2 * ph, ph, (ph + 2 - 3) / 2 + 1};
@@ -96,6 +104,10 @@ struct Trainer {
         for (int j = 0; j < 4; ++j) {
             t.hs[j] = hs[j]; t.wsz[j] = wz[j];
             t.tap[j] = a(ar, Mp * Dm);
+            if (readout) {
+                t.tapraw[j] = a(ar, Mp * Dm); t.cls[j] = a(ar, static_cast<size_t>(B) * Dm); t.cat[j] = a(ar, Mp * 2 * Dm);
+                t.rpre[j] = a(ar, Mp * Dm);
+            }
             t.pj[j] = a(ar, Mp * oc[j]);
             t.rj[j] = (j == 2) ? t.pj[j] : a(ar, static_cast<size_t>(B) * hs[j] * wz[j] * oc[j]);
             const size_t n = static_cast<size_t>(B) * hs[j] * wz[j] * F;
@@ -153,13 +165,27 @@ struct Trainer {
             DAD_TRY(m.linear(mode, bt.att, M, Dm, m.proj[i], epi(m.P(b + "attn.proj.bias"), bt.y1), false, st));
             DAD_TRY(ls_residual(bt.x0, bt.y1, bf, m.P(b + "ls1.gamma"), bt.x1, M, Dm, st));
             DAD_TRY(layernorm(bt.x1, m.P(b + "norm2.weight"), m.P(b + "norm2.bias"), bt.n2, bf, nullptr, M, Dm, 1, 1, 0, LN_EPS, st));
-            DAD_TRY(m.linear(mode, bt.n2, M, Dm, m.fc1[i], epi(m.P(b + "mlp.fc1.bias"), bt.hpre), false, st));
-            DAD_TRY(gelu_fwd(bt.hpre, bt.h, bf, M * 4 * Dm, st));
-            DAD_TRY(m.linear(mode, bt.h, M, 4 * Dm, m.fc2[i], epi(m.P(b + "mlp.fc2.bias"), bt.y2), false, st));
+            if (Hd) {   // SwiGLUFFN (swiglu_ffn.py:30-34)
+                DAD_TRY(m.linear(mode, bt.n2, M, Dm, m.w12[i], epi(m.P(b + "mlp.w12.bias"), bt.hpre), false, st));
+                DAD_TRY(swiglu(bt.hpre, bt.h, bf, M, Hd, st));
+                DAD_TRY(m.linear(mode, bt.h, M, Hd, m.w3[i], epi(m.P(b + "mlp.w3.bias"), bt.y2), false, st));
+            } else {
+                DAD_TRY(m.linear(mode, bt.n2, M, Dm, m.fc1[i], epi(m.P(b + "mlp.fc1.bias"), bt.hpre), false, st));
+                DAD_TRY(gelu_fwd(bt.hpre, bt.h, bf, M * 4 * Dm, st));
+                DAD_TRY(m.linear(mode, bt.h, M, 4 * Dm, m.fc2[i], epi(m.P(b + "mlp.fc2.bias"), bt.y2), false, st));
+            }
             DAD_TRY(ls_residual(bt.x1, bt.y2, bf, m.P(b + "ls2.gamma"), xnext, M, Dm, st));
             if (tj < 4 && i == m.desc.taps[tj]) {
-                DAD_TRY(layernorm(xnext, m.P(p + "norm.weight"), m.P(p + "norm.bias"), t.tap[tj], bf, (tj == 3) ? feat_out : nullptr,
-                                  Mp, Dm, np, T, 1, LN_EPS, st));
+                DAD_TRY(layernorm(xnext, m.P(p + "norm.weight"), m.P(p + "norm.bias"), readout ? t.tapraw[tj] : t.tap[tj], bf,
+                                  (tj == 3) ? feat_out : nullptr, Mp, Dm, np, T, 1, LN_EPS, st));
+                if (readout) {   // tap = GELU(Linear(cat(patch, cls.expand_as(patch))))  (dpt.py:153-156)
+                    const std::string r = "depth_head.readout_projects." + std::to_string(tj) + ".0.";
+                    DAD_TRY(layernorm(xnext, m.P(p + "norm.weight"), m.P(p + "norm.bias"), t.cls[tj], bf, nullptr, B, Dm, 1, T, 0,
+                                      LN_EPS, st));
+                    DAD_TRY(concat_cls(t.tapraw[tj], t.cls[tj], t.cat[tj], bf, B, np, Dm, st));
+                    DAD_TRY(m.linear(mode, t.cat[tj], Mp, 2 * Dm, m.readout_proj[tj], epi(m.P(r + "bias"), t.rpre[tj]), false, st));
+                    DAD_TRY(gelu_fwd(t.rpre[tj], t.tap[tj], bf, Mp * Dm, st));
+                }
                 ++tj;
             }
         }
@@ -554,6 +580,7 @@ struct Trainer {
 
         // ---- reassemble: layer_rn -> resize -> projects; dtap[j] = gradient of the LayerNorm'd tap
         void* dtap[4];
+        float* dcls[4] = {nullptr, nullptr, nullptr, nullptr};
         for (int j = 0; j < 4; ++j) {
             const std::string js = std::to_string(j);
             const int hj = t.hs[j], wj = t.wsz[j];
@@ -654,8 +681,32 @@ struct Trainer {
             dtap[j] = a(ar, Mp * Dm);
             if (!dry) DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
             DAD_TRY(dgrad_linear(dpj, oc[j], Mp, oc[j], m.P(h + "projects." + js + ".weight"), Dm, dtap[j], ar));
+            if (readout) {
+                // dtap[j] is the gradient of GELU(Linear(cat)); take it back to the normalised patch tokens (left half of
+                // the concat, kept in dtap[j]) and to the class token (right half summed over the image's patches, fp32)
+                const std::string r = h + "readout_projects." + js + ".0.";
+                RUN(gelu_bwd(t.rpre[j], dtap[j], dtap[j], bf, Mp * Dm, st));
+                DAD_TRY(wgrad_linear(dtap[j], Dm, t.cat[j], 2 * Dm, Mp, Dm, 2 * Dm, G(r + "weight"), ar));
+                DAD_TRY(bias_grad(dtap[j], Dm, Mp, Dm, G(r + "bias")));
+                dcls[j] = ar.f(static_cast<size_t>(B) * Dm);
+                const size_t mk = ar.used;
+                void* dcat = a(ar, Mp * 2 * Dm);
+                if (!dry) DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
+                DAD_TRY(dgrad_linear(dtap[j], Dm, Mp, Dm, m.P(r + "weight"), 2 * Dm, dcat, ar));
+                if (!dry) {
+                    DAD_TRY(copy_cols(dcat, 2 * Dm, dtap[j], Dm, Mp, Dm, bf, st));
+                    DAD_CHECK_CUDA(cudaMemsetAsync(dcls[j], 0, static_cast<size_t>(B) * Dm * 4, st));
+                    for (int bi = 0; bi < B; ++bi) {
+                        const uint8_t* right = reinterpret_cast<const uint8_t*>(dcat) +
+                                               (static_cast<size_t>(bi) * np * 2 * Dm + Dm) * es;
+                        DAD_TRY(colsum(right, bf, 2 * Dm, nullptr, 0, 0, np, Dm, dcls[j] + static_cast<size_t>(bi) * Dm, nullptr,
+                                       nullptr, st));
+                    }
+                }
+                ar.used = mk;
+            }
         }
-        if (gfeat) RUN(add_inplace(dtap[3], bf, gfeat, Mp * Dm, st));
+        if (gfeat) RUN(add_inplace(dtap[3], bf, gfeat, Mp * Dm, st));   // features[3][0]: the normalised patch tokens
 
         // ---- encoder, last block first.  Gx = gradient of the residual stream (fp32 in both modes)
         float* Gx = ar.f(M * Dm);
@@ -671,23 +722,37 @@ struct Trainer {
             if (tj >= 0 && i == m.desc.taps[tj]) {
                 RUN(layernorm_bwd(xnext, m.P(p + "norm.weight"), dtap[tj], bf, Gx, G(p + "norm.weight"), G(p + "norm.bias"), Mp, Dm, np,
                                   T, 1, LN_EPS, st));
+                if (readout)   // the class-token rows of the same LayerNorm (input row b * T)
+                    RUN(layernorm_bwd(xnext, m.P(p + "norm.weight"), dcls[tj], 0, Gx, G(p + "norm.weight"), G(p + "norm.bias"), B, Dm,
+                                      1, T, 0, LN_EPS, st));
                 --tj;
             }
             const size_t mk = ar.used;
             void* dy = a(ar, M * Dm);        // gradient of the branch output before LayerScale
-            void* dh = a(ar, M * 4 * Dm);
+            void* dh = a(ar, M * (Hd ? 2 * Hd : 4 * Dm));
+            void* dg = Hd ? a(ar, M * Hd) : nullptr;   // SwiGLU: gradient of the gated product
             void* dn = a(ar, M * Dm);
             void* dqkv = a(ar, M * 3 * Dm);
             if (!dry) DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
             // x_{i+1} = x1 + gamma2 * y2
             RUN(colsum(Gx, 0, Dm, bt.y2, bf, Dm, M, Dm, G(b + "ls2.gamma"), m.P(b + "ls2.gamma"), dy, st));
-            DAD_TRY(wgrad_linear(dy, Dm, bt.h, 4 * Dm, M, Dm, 4 * Dm, G(b + "mlp.fc2.weight"), ar));
-            DAD_TRY(bias_grad(dy, Dm, M, Dm, G(b + "mlp.fc2.bias")));
-            DAD_TRY(dgrad_linear(dy, Dm, M, Dm, m.P(b + "mlp.fc2.weight"), 4 * Dm, dh, ar));
-            RUN(gelu_bwd(bt.hpre, dh, dh, bf, M * 4 * Dm, st));
-            DAD_TRY(wgrad_linear(dh, 4 * Dm, bt.n2, Dm, M, 4 * Dm, Dm, G(b + "mlp.fc1.weight"), ar));
-            DAD_TRY(bias_grad(dh, 4 * Dm, M, 4 * Dm, G(b + "mlp.fc1.bias")));
-            DAD_TRY(dgrad_linear(dh, 4 * Dm, M, 4 * Dm, m.P(b + "mlp.fc1.weight"), Dm, dn, ar));
+            if (Hd) {   // y2 = w3(silu(x1) * x2), [x1 | x2] = w12(n2)
+                DAD_TRY(wgrad_linear(dy, Dm, bt.h, Hd, M, Dm, Hd, G(b + "mlp.w3.weight"), ar));
+                DAD_TRY(bias_grad(dy, Dm, M, Dm, G(b + "mlp.w3.bias")));
+                DAD_TRY(dgrad_linear(dy, Dm, M, Dm, m.P(b + "mlp.w3.weight"), Hd, dg, ar));
+                RUN(swiglu_bwd(bt.hpre, dg, dh, bf, M, Hd, st));
+                DAD_TRY(wgrad_linear(dh, 2 * Hd, bt.n2, Dm, M, 2 * Hd, Dm, G(b + "mlp.w12.weight"), ar));
+                DAD_TRY(bias_grad(dh, 2 * Hd, M, 2 * Hd, G(b + "mlp.w12.bias")));
+                DAD_TRY(dgrad_linear(dh, 2 * Hd, M, 2 * Hd, m.P(b + "mlp.w12.weight"), Dm, dn, ar));
+            } else {
+                DAD_TRY(wgrad_linear(dy, Dm, bt.h, 4 * Dm, M, Dm, 4 * Dm, G(b + "mlp.fc2.weight"), ar));
+                DAD_TRY(bias_grad(dy, Dm, M, Dm, G(b + "mlp.fc2.bias")));
+                DAD_TRY(dgrad_linear(dy, Dm, M, Dm, m.P(b + "mlp.fc2.weight"), 4 * Dm, dh, ar));
+                RUN(gelu_bwd(bt.hpre, dh, dh, bf, M * 4 * Dm, st));
+                DAD_TRY(wgrad_linear(dh, 4 * Dm, bt.n2, Dm, M, 4 * Dm, Dm, G(b + "mlp.fc1.weight"), ar));
+                DAD_TRY(bias_grad(dh, 4 * Dm, M, 4 * Dm, G(b + "mlp.fc1.bias")));
+                DAD_TRY(dgrad_linear(dh, 4 * Dm, M, 4 * Dm, m.P(b + "mlp.fc1.weight"), Dm, dn, ar));
+            }
             RUN(layernorm_bwd(bt.x1, m.P(b + "norm2.weight"), dn, bf, Gx, G(b + "norm2.weight"), G(b + "norm2.bias"), M, Dm, 1, 1, 0,
                               LN_EPS, st));
             // x1 = x0 + gamma1 * y1

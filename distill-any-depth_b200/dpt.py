@@ -12,8 +12,9 @@ parameters - ``loss.backward()`` (tools/train_distillation.py:1556-1575) runs ``
 ``precision = "bf16"`` the forward is inference-only and its outputs are detached.
 
 Options: ``encoder="vitg"`` (SwiGLU FFN, dinov2.py:381-395) and ``use_clstoken=True`` (readout
-projection, dpt.py:116-122, 153-156) run forward-only; so does ``use_bn=True`` (util/blocks.py:49-51) in ``eval()`` mode,
-with the running statistics folded into the convolutions when the weights are synchronised.
+projection, dpt.py:116-122, 153-156) are part of the native forward AND backward; ``use_bn=True`` (util/blocks.py:49-51)
+runs forward-only in ``eval()`` mode, with the running statistics folded into the convolutions when the weights are
+synchronised.
 """
 import ctypes
 import math
@@ -259,9 +260,9 @@ class _NativeDepthModel(nn.Module):
         if (mode == 1 or self.bf16_backward) and captures is None and torch.is_grad_enabled():
             live = [(k, p) for k, p in self.named_parameters()
                     if p.requires_grad and not any(u in k for u in self._UNUSED)]
-            if live and (self._desc["encoder"] == "vitg" or self.depth_head.use_clstoken or self.depth_head.use_bn):
-                raise NotImplementedError("ViT-g / SwiGLU, the use_clstoken readout and use_bn are forward-only here: run under "
-                                          "torch.no_grad() (the training backward covers the Mlp encoder, SURVEY.md 8f N1)")
+            if live and self.depth_head.use_bn:
+                raise NotImplementedError("use_bn=True is forward-only here (folded running statistics): run under "
+                                          "torch.no_grad(); the training backward covers the graph without BatchNorm")
             if live:
                 return _TrainForward.apply(self, x, mode, tuple(k for k, _ in live), *[p for _, p in live])
         return self._run_native(x, mode, captures)

@@ -67,7 +67,7 @@ void dad_model_destroy(dad_model* m);
  *   "depth_head.readout_projects.{0..3}.0.{weight,bias}"   use_clstoken readout (dpt.py:116-122, 153-156)
  *   "pretrained.blocks.N.mlp.{w12,w3}.{weight,bias}"       SwiGLU FFN of ViT-g instead of mlp.fc1 / fc2
  *                                                          (dinov2_layers/swiglu_ffn.py:13-63, dinov2.py:410)
- * Both run in dad_forward only; dad_forward_train / dad_backward return DAD_ERR_UNSUPPORTED for them. */
+ * Both are honoured by dad_forward and by dad_forward_train / dad_backward. */
 int dad_model_set_weight(dad_model* m, const char* name, const float* dev_ptr, int64_t numel, void* stream);
 /* Pack weights for `mode` and build the positional table for (H, W) (interpolate_pos_encoding,
  * dinov2.py:179-210).  Idempotent; must precede dad_forward for that (mode, H, W). */
