@@ -150,7 +150,15 @@ class ClockSampler(threading.Thread):
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.h = None
+            try:  # CUDA ordinal -> NVML handle by UUID (the two numberings differ under CUDA_VISIBLE_DEVICES)
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nv = None
