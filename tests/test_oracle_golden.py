@@ -119,3 +119,19 @@ def test_preprocess_oracle_matches_reference_fixture():
         assert np.array_equal(psub(t.numpy()), g[name + "/tensor_sub"]), name
     assert P.get_size(640, 480, 518, 518) == (686, 518)
     assert P.get_size(1242, 375, 518, 518) == (1722, 518)
+
+
+def test_resize_size_arithmetic_matches_the_reference_sweep():
+    """Resize.get_size (util/transform.py:52-106) over 4050 (raw size, target, keep_aspect_ratio, method) cases recorded
+    from the live reference (oracle/make_golden_sizes.py): the product's host logic for all three methods, the oracle's
+    restatement for 'lower_bound' (the method on the path, dpt.py:240-250)."""
+    from distill_any_depth_b200 import preprocess
+    from oracle.make_golden_sizes import METHODS
+    from oracle.preprocess import get_size as oracle_get_size
+    rows = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_sizes.npz"))["rows"]
+    assert len(rows) == 4050
+    for w, h, target, keep, mi, nw, nh in rows.tolist():
+        got = preprocess.get_size(w, h, target, target, keep_aspect_ratio=bool(keep), resize_method=METHODS[mi])
+        assert got == (nw, nh), (w, h, target, keep, METHODS[mi], got, (nw, nh))
+        if mi == 0:
+            assert oracle_get_size(w, h, target, target, bool(keep)) == (nw, nh), (w, h, target, keep)
