@@ -40,7 +40,7 @@ def test_teacher_key_layout_and_mapping():
     want = student_to_teacher_keys({k: None for k in synthetic.param_shapes(**kw)})
     assert set(keys) == set(want)
     assert all(t._student_key(k) in synthetic.param_shapes(**kw) for k in keys)
-    assert float(t.backbone.blocks[0][0].ls1.gamma[0]) == pytest.approx(1e-5)  # ViT_DINO.py:587
+    assert float(t.backbone.blocks[0][0].ls1.gamma.detach()[0]) == pytest.approx(1e-5)  # ViT_DINO.py:587
 
 
 def test_options_outside_the_hot_path_raise():
