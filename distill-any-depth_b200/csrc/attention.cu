@@ -86,7 +86,19 @@ int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, 
         // per-tile maximum): 1.7x faster than the default on heavy-tailed logits that force rescales (0.429 vs 0.728 ms).
         const char* ev = getenv("DAD_ATT_VARIANT");  // read per call: tests switch it at run time
         const int variant = ev ? atoi(ev) : 2;
-        if (variant == 3)
+        if (variant == 4) {
+            // EXPERIMENTAL, opt-in only (see attention_tc4.cu): the per-CTA flag bytes live in a lazily grown device buffer,
+            // which is NOT capture-safe on its first use - warm up before capturing a CUDA graph with this variant.
+            static uint8_t* flags = nullptr;
+            static size_t flags_cap = 0;
+            const size_t need = static_cast<size_t>(B) * heads * cdiv(N, 128);
+            if (need > flags_cap) {
+                if (flags) DAD_CHECK_CUDA(cudaFree(flags));
+                DAD_CHECK_CUDA(cudaMalloc(&flags, need));
+                flags_cap = need;
+            }
+            DAD_TRY(attention_tc4(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, flags, st));
+        } else if (variant == 3)
             DAD_TRY(attention_tc3(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, st));
         else
             DAD_TRY(attention_tc(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, st));

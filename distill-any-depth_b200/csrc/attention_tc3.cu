@@ -37,7 +37,14 @@ constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P <= 2^8 relative to t
 
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int N, int D) {
+                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int N, int D,
+                     const uint8_t* __restrict__ only_if) {
+    if (only_if) {
+        // exactness net of attention_tc4: recompute only the CTAs it flagged (same grid, same CTA -> tile mapping); the
+        // flags are written by the previous kernel in the stream, so wait for it before reading them
+        pdl_wait();
+        if (!only_if[(static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
+    }
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -272,6 +279,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 // qkv [B*N, 3*D] bf16 (q pre-scaled) -> out [B*N, D] bf16
 int attention_tc3(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st) {
+    return attention_tc3_flagged(qkv, out, B, N, heads, nullptr, st);
+}
+
+// only_if == nullptr: every CTA runs; otherwise one byte per CTA (grid order x fastest, then head, then image)
+int attention_tc3_flagged(const bf16* qkv, bf16* out, int B, int N, int heads, const uint8_t* only_if, cudaStream_t st) {
     const int D = heads * HD;
     static bool configured = false;
     if (!configured) {
@@ -288,7 +300,8 @@ int attention_tc3(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStrea
     const dim3 grid(cdiv(N, BQ), heads, B);
     static const int pad = getenv("DAD_ATT_SMEM_PAD_KB") ? atoi(getenv("DAD_ATT_SMEM_PAD_KB")) * 1024 : 0;  // occupancy experiments
     if (pad) DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM + pad));
-    DAD_CHECK_CUDA(launch_pdl(attention_tc3_kernel, grid, dim3(ATT_THREADS), ATT_SMEM + pad, st, tm[0], tm[1], tm[2], out, N, D));
+    DAD_CHECK_CUDA(launch_pdl(attention_tc3_kernel, grid, dim3(ATT_THREADS), ATT_SMEM + pad, st, tm[0], tm[1], tm[2], out, N, D,
+                              only_if));
     return DAD_OK;
 }
 

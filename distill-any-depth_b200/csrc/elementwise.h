@@ -27,6 +27,9 @@ int resize_depth(const float* in, int B, int Hi, int Wi, int Ho, int Wo, float* 
 int minmax_normalize(const float* in, int B, long long L, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st);  // tcgen05 / TMEM
 int attention_tc3(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st); // 4 CTAs / SM variant
+int attention_tc3_flagged(const bf16* qkv, bf16* out, int B, int N, int heads, const uint8_t* only_if, cudaStream_t st);
+// EXPERIMENTAL (DAD_ATT_VARIANT=4): two softmax warpgroups per CTA, no in-kernel rescale, flagged CTAs redone by tc3
+int attention_tc4(const bf16* qkv, bf16* out, int B, int N, int heads, uint8_t* flags, cudaStream_t st);
 int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, cudaStream_t st);
 
 }  // namespace dad

@@ -2,6 +2,7 @@
 FFMA verification engine, attention (bf16 tensor-core and fp32).  References are plain PyTorch
 fp32 ops on the same (bf16-rounded where applicable) inputs."""
 import ctypes
+import os
 
 import pytest
 import torch
@@ -153,7 +154,14 @@ def test_conv_stride2_matches_conv2d(B, H, W, C, Co):
     assert (out - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
 
 
-@pytest.fixture(params=[2, 3], ids=["pipelined2cta", "serial4cta"])
+# variant 4 (attention_tc4.cu: two softmax warpgroups per CTA, no in-kernel rescale) is EXPERIMENTAL and has not run on
+# hardware yet: it joins the parametrisation only with DAD_TEST_EXPERIMENTAL=1
+_ATT_VARIANTS = {2: "pipelined2cta", 3: "serial4cta"}
+if os.environ.get("DAD_TEST_EXPERIMENTAL"):
+    _ATT_VARIANTS[4] = "twohalves_experimental"
+
+
+@pytest.fixture(params=list(_ATT_VARIANTS), ids=list(_ATT_VARIANTS.values()))
 def att_variant(request, monkeypatch):
     """Both tcgen05 attention kernels (attention_tc.cu / attention_tc3.cu) go through the same tests."""
     monkeypatch.setenv("DAD_ATT_VARIANT", str(request.param))
