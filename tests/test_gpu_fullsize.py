@@ -1,9 +1,10 @@
-"""BASELINE.json configurations at (or near) their full sizes, checked through size-independent
-properties, because the CPU oracle needs minutes per ViT-L image at these resolutions:
+"""BASELINE.json configurations at their full sizes.
 
-  * the fp32 verification mode is pinned to the oracle (<= 1e-4) by test_gpu_model.py at sizes the
-    oracle finishes in seconds; here the bf16 tensor-core mode must stay within the north_star
-    tolerance (2e-2 per-pixel relative depth) of that fp32 mode on the SAME device and weights;
+  * the headline sizes are compared DIRECTLY with the oracle and with the live reference's fixture
+    (tests/golden/golden_model_fullsize.npz, generator oracle/make_golden_fullsize.py): ViT-L 518x518 (B=2) and
+    ViT-L 1036x1036 (B=1), full depth map and feature map, in the fp32 verification mode (<= 1e-4) and in the
+    bf16 tensor-core mode (<= 2e-2 per-pixel relative depth).  The oracle needs ~1 s (518) / ~20 s (1036) per
+    image on the GPU box's host cores; the chain is  device == oracle == live reference  at these sizes;
   * images are independent: a batch of 32 must reproduce, bit for bit, what each
     image gives alone - this is what makes sharding by rank exact;
   * the composed distillation step (config 4) must equal its parts.
@@ -11,9 +12,14 @@ properties, because the CPU oracle needs minutes per ViT-L image at these resolu
 import pytest
 import torch
 
+import os
+
+import numpy as np
+
 import oracle
 from distill_any_depth_b200 import synthetic
-from helpers import rel_depth_err
+from helpers import rel_depth_err, sub
+from oracle.make_golden_fullsize import FULLSIZE_CASES, DEPTH_SUB, FEAT_SUB
 
 pytestmark = pytest.mark.gpu
 
@@ -37,6 +43,66 @@ def build(preset, seed, teacher=False, head_bias=0.25):
         m = d.DepthAnythingV2(**kw)
         m.load_state_dict(sd, strict=True)
     return m.cuda().eval(), sd, kw
+
+
+@pytest.fixture(scope="module")
+def golden_fullsize():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return dict(np.load(os.path.join(root, "tests", "golden", "golden_model_fullsize.npz")))
+
+
+_ORACLE_CACHE = {}
+
+
+def _oracle_forward(name):
+    """Oracle forward of a FULLSIZE case on the host cores (cached: the fp32 and bf16 tests share it)."""
+    if name not in _ORACLE_CACHE:
+        _, preset, B, H, W, ws, xs, hb = next(c for c in FULLSIZE_CASES if c[0] == name)
+        kw = synthetic.MODEL_PRESETS[preset]
+        sd = synthetic.make_state_dict(seed=ws, head_bias=hb, **kw)
+        x = synthetic.make_images(B, H, W, seed=xs)
+        torch.set_num_threads(os.cpu_count())
+        d, f = oracle.depth_anything_forward(x, sd, kw["encoder"])
+        _ORACLE_CACHE[name] = (x, d, f)
+    return _ORACLE_CACHE[name]
+
+
+@pytest.mark.parametrize("name", [c[0] for c in FULLSIZE_CASES])
+def test_oracle_matches_live_reference_fixture_at_headline_size(name, golden_fullsize):
+    """oracle == live reference (depth_anything_v2/dpt.py:211-225) at 518^2 / 1036^2 on THIS box's host BLAS."""
+    _, d, f = _oracle_forward(name)
+    g = golden_fullsize
+    np.testing.assert_allclose(sub(d, DEPTH_SUB).numpy(), g[name + "/depth_sub"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(sub(f, FEAT_SUB).numpy(), g[name + "/feat_sub"], rtol=1e-4, atol=5e-5)
+    st = g[name + "/depth_stats"]
+    assert abs(d.double().pow(2).sum().item() - st[2]) <= 1e-4 * st[2]
+
+
+@pytest.mark.parametrize("precision,tol,ftol", [("fp32", 1e-4, 1e-4), ("bf16", 2e-2, 6e-2)])
+@pytest.mark.parametrize("name", [c[0] for c in FULLSIZE_CASES])
+def test_headline_sizes_match_oracle_full_map(name, precision, tol, ftol, golden_fullsize):
+    """ViT-L 518x518 (B=2) and 1036x1036 (B=1, 5477 tokens): every pixel of the depth map and every feature against the
+    oracle, and the same sub-sample against the live reference's fixture (dinov2_layers/attention.py:49-62 at N=5477)."""
+    _, preset, B, H, W, ws, xs, hb = next(c for c in FULLSIZE_CASES if c[0] == name)
+    m, _, _ = build(preset, ws, head_bias=hb)
+    x, d_or, f_or = _oracle_forward(name)
+    m.precision = precision
+    depth, feat = m(x.cuda())
+    torch.cuda.synchronize()
+    assert depth.shape == d_or.shape and feat.shape == f_or.shape
+    rel = rel_depth_err(depth.cpu(), d_or).max().item()
+    f_err = ((feat.cpu() - f_or).abs().max() / f_or.abs().max()).item()
+    d_fix = torch.from_numpy(golden_fullsize[name + "/depth_sub"])
+    dmax = float(golden_fullsize[name + "/depth_stats"][1])
+    rel_fix = ((sub(depth.cpu(), DEPTH_SUB) - d_fix).abs() / d_fix.abs().clamp(min=0.1 * dmax)).max().item()
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_fullsize.jsonl"), "a") as fh:
+        fh.write('{"case": "%s", "precision": "%s", "rel_depth_vs_oracle": %.3e, "rel_depth_vs_reference_fixture": %.3e, '
+                 '"feat_rel_vs_oracle": %.3e}\n' % (name, precision, rel, rel_fix, f_err))
+    assert rel <= tol, rel
+    assert rel_fix <= tol, rel_fix
+    assert f_err <= ftol, f_err
 
 
 def test_config3_vitl_518_batch32_batch_independence_and_bf16_tolerance():

@@ -168,7 +168,7 @@ def att_variant(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("B,N,heads", [(1, 64, 1), (2, 785, 6), (1, 1370, 16), (1, 26, 2), (1, 200, 3)])
+@pytest.mark.parametrize("B,N,heads", [(1, 64, 1), (2, 785, 6), (1, 1370, 16), (1, 26, 2), (1, 200, 3), (1, 5477, 16), (2, 5477, 16)])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_attention_matches_softmax_reference(B, N, heads, mode, att_variant):
     L = _lib()

@@ -28,6 +28,21 @@ def test_model_matches_reference_fixture(case, golden_model):
     assert abs(d.double().pow(2).sum().item() - st[2]) <= 1e-4 * st[2]
 
 
+def test_vitl_518_matches_reference_fixture_at_headline_size():
+    """The bench workload's size (ViT-L 518x518): oracle vs the live reference's recorded outputs
+    (oracle/make_golden_fullsize.py; the 1036x1036 case is replayed by the GPU suite, where the oracle runs anyway)."""
+    from oracle.make_golden_fullsize import FULLSIZE_CASES, DEPTH_SUB, FEAT_SUB
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_model_fullsize.npz")))
+    name, preset, B, H, W, ws, xs, hb = FULLSIZE_CASES[0]
+    kw = synthetic.MODEL_PRESETS[preset]
+    sd = synthetic.make_state_dict(seed=ws, head_bias=hb, **kw)
+    x = synthetic.make_images(B, H, W, seed=xs)[:1]
+    with torch.no_grad():
+        d, f = oracle.depth_anything_forward(x, sd, kw["encoder"])
+    np.testing.assert_allclose(sub(d, DEPTH_SUB).numpy(), g[name + "/depth_sub"][:1], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(sub(f, FEAT_SUB).numpy(), g[name + "/feat_sub"][:1], rtol=1e-4, atol=5e-5)
+
+
 @pytest.mark.parametrize("case", OPTION_CASES, ids=lambda c: c[0])
 def test_option_branches_match_reference_fixture(case, golden_model_options):
     """use_clstoken readout and ViT-g / SwiGLU against the live reference's recorded outputs."""

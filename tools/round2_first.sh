@@ -7,7 +7,7 @@ set -u
 OUT=gpurun_out/round2_first
 mkdir -p $OUT
 echo "== attention kernel tests incl. experimental variant 4" | tee $OUT/summary.txt
-DAD_TEST_EXPERIMENTAL=1 timeout -s KILL 150 python -m pytest tests/test_gpu_kernels.py -k attention -q --timeout 60 -p no:cacheprovider \
+DAD_TEST_EXPERIMENTAL=1 timeout -s KILL 300 python -m pytest tests/test_gpu_kernels.py -k attention -q --timeout 90 -p no:cacheprovider \
     > $OUT/attn_tests.log 2>&1
 echo "pytest rc=$?" | tee -a $OUT/summary.txt
 tail -5 $OUT/attn_tests.log | tee -a $OUT/summary.txt
