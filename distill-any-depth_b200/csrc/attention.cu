@@ -1,7 +1,7 @@
 // Multi-head self-attention, head_dim 64, non-causal, no mask (reference
 // dinov2_layers/attention.py:49-62; q is pre-scaled: 64^-0.5 is folded into the packed qkv weights).
 //
-//   bf16 mode : attention_tc.cu (tcgen05.mma, S / P / O in TMEM, TMA-fed)
+//   bf16 mode : attention_tc5.cu (tcgen05.mma, S / P / O / row sums in TMEM, TMA-fed)
 //   fp32 mode : attention_f32_kernel below - verification mode, one query per thread, fp32 FFMA, expf.
 //
 // qkv layout: [B*N, 3*D] rows = tokens, columns = (3, heads, 64) as produced by the qkv GEMM.
@@ -80,28 +80,19 @@ int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, 
     const int D = heads * HD;
     ProfScope prof(PROF_ATTN, 4.0 * B * static_cast<double>(N) * N * D, st);
     if (is_bf16) {
-        // tcgen05 / TMEM kernels.  Default: attention_tc.cu (2 CTAs / SM, S / P double-buffered in TMEM) - the faster
-        // one when logits stay within 2^16 of the first key tile's maximum (0.358 vs 0.371 ms per ViT-L 518^2 B=32
-        // launch, 1.205 vs 1.322 ms at 1036^2).  DAD_ATT_VARIANT=3 selects attention_tc3.cu (4 serial CTAs / SM, exact
-        // per-tile maximum): 1.7x faster than the default on heavy-tailed logits that force rescales (0.429 vs 0.728 ms).
-        const char* ev = getenv("DAD_ATT_VARIANT");  // read per call: tests switch it at run time
-        const int variant = ev ? atoi(ev) : 2;
-        if (variant == 4) {
-            // EXPERIMENTAL, opt-in only (see attention_tc4.cu): the per-CTA flag bytes live in a lazily grown device buffer,
-            // which is NOT capture-safe on its first use - warm up before capturing a CUDA graph with this variant.
-            static uint8_t* flags = nullptr;
-            static size_t flags_cap = 0;
-            const size_t need = static_cast<size_t>(B) * heads * cdiv(N, 128);
-            if (need > flags_cap) {
-                if (flags) DAD_CHECK_CUDA(cudaFree(flags));
-                DAD_CHECK_CUDA(cudaMalloc(&flags, need));
-                flags_cap = need;
-            }
-            DAD_TRY(attention_tc4(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, flags, st));
-        } else if (variant == 3)
+        // tcgen05 / TMEM kernels.  Default: attention_tc5.cu (round 2: packed FFMA2 + MUFU / FMA-pipe exponentials, row sums
+        // on the tensor core, in-kernel exact fallback).  DAD_ATT_VARIANT=2 / 3 select the round-1 kernels (attention_tc.cu:
+        // lazy rescale, 2 CTAs / SM; attention_tc3.cu: 4 serial CTAs / SM, exact per-tile maximum) for A/B measurements.
+        const char* ev = getenv("DAD_ATT_VARIANT");   // read per call: tests switch it at run time
+        const char* ep = getenv("DAD_ATT_POLY5");      // pairs of every 8 exponentiated on the FMA pipe (0, 2, 3, 4, 5)
+        const int variant = ev ? atoi(ev) : 5;
+        const int poly = ep ? atoi(ep) : 4;
+        if (variant == 3)
             DAD_TRY(attention_tc3(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, st));
-        else
+        else if (variant == 2)
             DAD_TRY(attention_tc(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, st));
+        else
+            DAD_TRY(attention_tc5(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, poly, st));
         return DAD_OK;
     }
     {

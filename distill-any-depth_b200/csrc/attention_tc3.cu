@@ -35,19 +35,9 @@ constexpr int ATT_SMEM = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 256 + 1024;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P <= 2^8 relative to the reference maximum
 
-// FLAGGED = false: the kernel as measured and tested (only_if unused).  FLAGGED = true: exactness net of the experimental
-// attention_tc4 - only the CTAs it flagged are recomputed.
-template <bool FLAGGED>
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int N, int D,
-                     const uint8_t* __restrict__ only_if) {
-    if (FLAGGED) {
-        // same grid, same CTA -> tile mapping as attention_tc4; the flags are written by the previous kernel in the stream,
-        // so wait for it before reading them
-        pdl_wait();
-        if (!only_if[(static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
-    }
+                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int N, int D) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -282,16 +272,10 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 // qkv [B*N, 3*D] bf16 (q pre-scaled) -> out [B*N, D] bf16
 int attention_tc3(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st) {
-    return attention_tc3_flagged(qkv, out, B, N, heads, nullptr, st);
-}
-
-// only_if == nullptr: every CTA runs; otherwise one byte per CTA (grid order x fastest, then head, then image)
-int attention_tc3_flagged(const bf16* qkv, bf16* out, int B, int N, int heads, const uint8_t* only_if, cudaStream_t st) {
     const int D = heads * HD;
     static bool configured = false;
     if (!configured) {
-        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         configured = true;
     }
     CUtensorMap tm[3];
@@ -302,14 +286,8 @@ int attention_tc3_flagged(const bf16* qkv, bf16* out, int B, int N, int heads, c
         DAD_TRY(make_tmap_bf16(&tm[i], qkv + static_cast<long long>(i) * D, 3, dims, strides, box));
     }
     const dim3 grid(cdiv(N, BQ), heads, B);
-    static const int pad = getenv("DAD_ATT_SMEM_PAD_KB") ? atoi(getenv("DAD_ATT_SMEM_PAD_KB")) * 1024 : 0;  // occupancy experiments
-    if (pad) DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM + pad));
-    if (only_if)
-        DAD_CHECK_CUDA(launch_pdl(attention_tc3_kernel<true>, grid, dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N, D,
-                                  only_if));
-    else
-        DAD_CHECK_CUDA(launch_pdl(attention_tc3_kernel<false>, grid, dim3(ATT_THREADS), ATT_SMEM + pad, st, tm[0], tm[1], tm[2], out,
-                                  N, D, only_if));
+    DAD_CHECK_CUDA(launch_pdl(attention_tc3_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N, D));
+    DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 

@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* gdepth, cons
 }
 
 // training-forward output head on a saved (fp32 or bf16) ReLU'd 32-channel map: relu(dot(row, w) + b)
-__global__ void __launch_bounds__(256) head1x1_any_kernel(const void* in, int bf, const float* w, float bias, float* out, long long P) {
+__global__ void __launch_bounds__(256) head1x1_any_kernel(const void* in, int bf, const float* w, const float* bias, float* out, long long P) {
     const long long p = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
     if (p >= P) return;
     float s = 0.f;
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(256) head1x1_any_kernel(const void* in, int bf
         s = fmaf(v.x, w[4 * j], s); s = fmaf(v.y, w[4 * j + 1], s);
         s = fmaf(v.z, w[4 * j + 2], s); s = fmaf(v.w, w[4 * j + 3], s);
     }
-    out[p] = fmaxf(s + bias, 0.f);
+    out[p] = fmaxf(s + __ldg(bias), 0.f);
 }
 
 // ---------------------------------------------------------------- ConvTranspose / strided-conv helpers
@@ -927,7 +927,7 @@ int pack_linear_T(const float* w, void* out, int N, int K, int Np, cudaStream_t 
     return DAD_OK;
 }
 
-int head1x1_any(const void* in, int bf, const float* w, float bias, float* out, long long P, cudaStream_t st) {
+int head1x1_any(const void* in, int bf, const float* w, const float* bias, float* out, long long P, cudaStream_t st) {
     debug_label("head1x1_any");
     ProfScope prof(PROF_ELEM, static_cast<double>(P) * (32 * (bf ? 2 : 4) + 4), st);
     head1x1_any_kernel<<<blocks_for(P), 256, 0, st>>>(in, bf, w, bias, out, P);

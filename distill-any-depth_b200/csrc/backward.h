@@ -58,7 +58,7 @@ int transpose_pad_batched(const void* in, long long ld, int R, int C, void* out,
 int im2colT(const void* X, int B, int H, int W, int Ci, int taps, int stride, int Ho, int Wo, void* out, long long Pp, cudaStream_t st);
 // w [N][K] fp32 -> out [K][Np] bf16
 int pack_linear_T(const float* w, void* out, int N, int K, int Np, cudaStream_t st);
-int head1x1_any(const void* in, int bf, const float* w, float bias, float* out, long long P, cudaStream_t st);
+int head1x1_any(const void* in, int bf, const float* w, const float* bias, float* out, long long P, cudaStream_t st);
 // row-wise softmax of S [rows, T] in place; and dS = P * (dP - sum_j P*dP) in place of dP
 int softmax_rows(float* S, long long rows, int T, int ld, cudaStream_t st);
 int softmax_bwd_rows(const float* P, float* dP, long long rows, int T, int ld, cudaStream_t st);

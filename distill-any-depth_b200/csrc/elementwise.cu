@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const T* in, T* A, int B
 }
 
 // ---------------------------------------------------------------- fp32-mode output head: relu(dot(row[32], w) + b)
-__global__ void __launch_bounds__(256) head1x1_kernel(const float* in, const float* w, float bias, float* out, long long P) {
+__global__ void __launch_bounds__(256) head1x1_kernel(const float* in, const float* w, const float* bias, float* out, long long P) {
     const long long p = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
     if (p >= P) return;
     const float4* src = reinterpret_cast<const float4*>(in + p * 32);
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const float* in, const flo
         s = fmaf(v.x, w[4 * j], s); s = fmaf(v.y, w[4 * j + 1], s);
         s = fmaf(v.z, w[4 * j + 2], s); s = fmaf(v.w, w[4 * j + 3], s);
     }
-    out[p] = fmaxf(s + bias, 0.f);
+    out[p] = fmaxf(s + __ldg(bias), 0.f);
 }
 
 // ---------------------------------------------------------------- positional-embedding table (K2)
@@ -397,7 +397,7 @@ int im2col_s2(const void* in, void* A, int is_bf16, int B, int H, int W, int C, 
     return DAD_OK;
 }
 
-int head1x1(const float* in, const float* w, float bias, float* out, long long P, cudaStream_t st) {
+int head1x1(const float* in, const float* w, const float* bias, float* out, long long P, cudaStream_t st) {
     ProfScope prof(PROF_ELEM, static_cast<double>(P) * 33 * 4, st);
     head1x1_kernel<<<static_cast<unsigned>(cdivl(P, 256)), 256, 0, st>>>(in, w, bias, out, P);
     DAD_CHECK_LAUNCH();

@@ -10,7 +10,7 @@ int layernorm(const float* in, const float* w, const float* b, void* out, int is
               int D, int out_period, int in_period, int in_offset, float eps, cudaStream_t st);
 int bilinear_nhwc(const void* in, void* out, int is_bf16, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st);
 int im2col_s2(const void* in, void* A, int is_bf16, int B, int H, int W, int C, int Cp, cudaStream_t st);
-int head1x1(const float* in, const float* w, float bias, float* out, long long P, cudaStream_t st);
+int head1x1(const float* in, const float* w, const float* bias, float* out, long long P, cudaStream_t st);
 // use_clstoken readout input: out [B*np, 2D] = [tok | cls[b]]  (dpt.py:153-156)
 int concat_cls(const void* tok, const void* cls, void* out, int is_bf16, int B, int np, int D, cudaStream_t st);
 // ViT-g SwiGLU gate: out [rows, Hd] = silu(x12[:, :Hd]) * x12[:, Hd:]  (swiglu_ffn.py:30-34)
@@ -27,9 +27,8 @@ int resize_depth(const float* in, int B, int Hi, int Wi, int Ho, int Wo, float* 
 int minmax_normalize(const float* in, int B, long long L, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st);  // tcgen05 / TMEM
 int attention_tc3(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st); // 4 CTAs / SM variant
-int attention_tc3_flagged(const bf16* qkv, bf16* out, int B, int N, int heads, const uint8_t* only_if, cudaStream_t st);
-// EXPERIMENTAL (DAD_ATT_VARIANT=4): two softmax warpgroups per CTA, no in-kernel rescale, flagged CTAs redone by tc3
-int attention_tc4(const bf16* qkv, bf16* out, int B, int N, int heads, uint8_t* flags, cudaStream_t st);
+// round-2 default: FFMA2 + MUFU / FMA-pipe exponentials, tensor-core row sums, in-kernel exact fallback (attention_tc5.cu)
+int attention_tc5(const bf16* qkv, bf16* out, int B, int N, int heads, int poly_pairs, cudaStream_t st);
 int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, cudaStream_t st);
 
 }  // namespace dad

@@ -36,7 +36,7 @@ struct Epilogue {
     int scat_k = 0, scat_CoP = 0, scat_Co = 0, scat_H = 0, scat_W = 0;
     // Fused output head (N == 32): out_head[row] = relu(dot(relu(acc+bias), head_w) + head_b)
     const float* head_w = nullptr;
-    float head_b = 0.f;
+    const float* head_b = nullptr;   // device pointer (a by-value scalar would be baked into captured graphs)
     float* head_out = nullptr;
 };
 

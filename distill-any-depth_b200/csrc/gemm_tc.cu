@@ -410,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         sacc = fmaf(fmaxf(a, 0.f), g.epi.head_w[j], sacc);
                     }
                     long long grow;
-                    if (half == 0 && row_of(quarter * 32 + lane, grow)) g.epi.head_out[grow] = fmaxf(sacc + g.epi.head_b, 0.f);
+                    if (half == 0 && row_of(quarter * 32 + lane, grow)) g.epi.head_out[grow] = fmaxf(sacc + __ldg(g.epi.head_b), 0.f);
                 }
             } else {
                 // 16-column pieces: lane -> (row = pass * 8 + lane / 4, 4 columns = (lane % 4) * 4)

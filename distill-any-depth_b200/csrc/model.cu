@@ -235,12 +235,9 @@ public:
         DAD_TRY(need(s + "output_conv2.0.bias", 32));
         DAD_TRY(need(s + "output_conv2.2.weight", 32));
         DAD_TRY(need(s + "output_conv2.2.bias", 1));
-        DAD_CHECK_CUDA(cudaMemcpyAsync(&head_bias_host, P(s + "output_conv2.2.bias"), 4, cudaMemcpyDeviceToHost, st));
-        DAD_CHECK_CUDA(cudaStreamSynchronize(st));
         packed[mode] = true;
         return DAD_OK;
     }
-    float head_bias_host = 0.f;
 
     int prepare(int mode, int H, int W, cudaStream_t st) {
         DAD_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (bf16) or 1 (fp32)");
@@ -534,12 +531,12 @@ public:
         if (mode == 0) {
             // conv3x3 -> ReLU -> conv1x1 -> ReLU (-> F.relu) fused in the GEMM epilogue
             Epilogue eh; eh.bias = P(s + "output_conv2.0.bias"); eh.head_w = P(s + "output_conv2.2.weight");
-            eh.head_b = head_bias_host; eh.head_out = depth_out;
+            eh.head_b = P(s + "output_conv2.2.bias"); eh.head_out = depth_out;
             DAD_TRY(conv(mode, up, B, H, W, F2, output_conv2_0, 9, eh, dry, st));
         } else {
             Epilogue eh; eh.bias = P(s + "output_conv2.0.bias"); eh.act = ACT_RELU; eh.out = t32;
             DAD_TRY(conv(mode, up, B, H, W, F2, output_conv2_0, 9, eh, dry, st));
-            if (!dry) DAD_TRY(head1x1(t32, P(s + "output_conv2.2.weight"), head_bias_host, depth_out,
+            if (!dry) DAD_TRY(head1x1(t32, P(s + "output_conv2.2.weight"), P(s + "output_conv2.2.bias"), depth_out,
                                       static_cast<long long>(B) * H * W, st));
         }
         if (dry) *ws_needed = ar.used + 1024;

@@ -297,5 +297,52 @@ __device__ __forceinline__ float ex2_fma(float x) {
     return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
 }
 
+
+// ----------------------------------------------------------------- packed fp32 pairs (sm_100 FFMA2 / FADD2)
+// Two fp32 values travel in one 64-bit register pair; one instruction issue per PAIR.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t r, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// (lo, hi) -> packed bf16 pair, round to nearest even: lo in bits [0,16), hi in bits [16,32)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// 2^x for a PAIR on the FMA / ALU pipes (no MUFU), packed arithmetic: both inputs are clamped to [-126, 128], so the
+// result is never a wrapped exponent: x >= 128 gives a value that rounds to +inf in bf16 (callers detect the overflow
+// in the row sum), x <= -126 gives a denormal-sized value.  Same minimax cubic as ex2_fma (max relative error 7.5e-5).
+__device__ __forceinline__ void ex2_fma2(float x0, float x1, float& y0, float& y1) {
+    x0 = fminf(fmaxf(x0, -126.0f), 128.0f);
+    x1 = fminf(fmaxf(x1, -126.0f), 128.0f);
+    const uint64_t x = pack2(x0, x1);
+    const uint64_t t = fadd2(x, pack2(12582912.0f, 12582912.0f));
+    const uint64_t n = fadd2(t, pack2(-12582912.0f, -12582912.0f));          // round(x)
+    const uint64_t r = ffma2(n, pack2(-1.0f, -1.0f), x);                     // x - round(x) in [-0.5, 0.5]
+    uint64_t p = ffma2(r, pack2(0.0551716648f, 0.0551716648f), pack2(0.2426111251f, 0.2426111251f));
+    p = ffma2(p, r, pack2(0.6932609677f, 0.6932609677f));
+    p = ffma2(p, r, pack2(0.9999280572f, 0.9999280572f));
+    float p0, p1, t0, t1;
+    unpack2(p, p0, p1);
+    unpack2(t, t0, t1);
+    y0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+    y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
 }  // namespace ptx
 }  // namespace dad

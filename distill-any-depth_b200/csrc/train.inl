@@ -238,7 +238,7 @@ struct Trainer {
         Epilogue eh = epi(m.P(s + "output_conv2.0.bias"), t.t32); eh.act = ACT_RELU;
         DAD_TRY(m.conv(mode, t.up, B, H, W, F2, m.output_conv2_0, 9, eh, false, st));
         const long long P = static_cast<long long>(B) * H * W;
-        DAD_TRY(head1x1_any(t.t32, bf, m.P(s + "output_conv2.2.weight"), m.head_bias_host, t.depth, P, st));
+        DAD_TRY(head1x1_any(t.t32, bf, m.P(s + "output_conv2.2.weight"), m.P(s + "output_conv2.2.bias"), t.depth, P, st));
         DAD_CHECK_CUDA(cudaMemcpyAsync(depth_out, t.depth, P * 4, cudaMemcpyDeviceToDevice, st));
         return DAD_OK;
     }

@@ -62,12 +62,20 @@ def shard_loss_weights(partials, group=None):
 def allreduce_gradients(parameters, group=None, average=False, bucket_bytes=256 << 20):
     """SUM (or mean) all-reduce of the .grad of `parameters` through flat fp32 buckets (one collective per bucket;
     NVSwitch reduces in the fabric, so buckets are sized for launch latency, not link count).  Parameters whose .grad is
-    None on this rank are treated as zeros when any bucket-mate has a gradient; returns the number of collectives."""
+    None on this rank but not on another are treated as zeros; parameters without a gradient on every rank are left at
+    None.  Returns the number of collectives (including the has-grad bitmap exchange)."""
     params = [p for p in parameters if p.requires_grad]
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or not params:
         return 0
     world = dist.get_world_size(group)
-    n_coll, bucket, size = 0, [], 0
+    # parameters without a gradient on EVERY rank stay at .grad = None, as in single-process training (the optimiser
+    # then skips them: no weight decay / moment update on mask_token, refinenet4.resConfUnit1): one tiny MAX all-reduce
+    # of a has-grad bitmap decides it (counted in the returned number of collectives)
+    has = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], dtype=torch.float32, device=params[0].device)
+    dist.all_reduce(has, op=dist.ReduceOp.MAX, group=group)
+    keep = has.cpu().tolist()
+    params = [p for p, k in zip(params, keep) if k > 0]
+    n_coll, bucket, size = 1, [], 0
 
     def flush():
         nonlocal n_coll, bucket, size

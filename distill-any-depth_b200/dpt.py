@@ -197,6 +197,11 @@ class _NativeDepthModel(nn.Module):
         sig = tuple((p.data_ptr(), p._version) for _, p in params + buffers)
         if sig == self._sig:
             return
+        # upload only what changed since the last call (an optimiser step changes every trained parameter; a manual edit
+        # of one tensor re-uploads one tensor); any BatchNorm change re-folds the affected convolutions
+        prev = self._sig_by_key if getattr(self, "_sig_by_key", None) is not None else {}
+        now = {k: (p.data_ptr(), p._version) for k, p in params + buffers}
+        bn_changed = use_bn and any(prev.get(k) != now[k] for k, _ in buffers)
         lib = _lib.load()
         st = _lib.stream_ptr()
         folded = self._fold_batchnorm() if use_bn else {}
@@ -204,7 +209,13 @@ class _NativeDepthModel(nn.Module):
             if p.device != device:
                 raise RuntimeError(f"parameter {k} is on {p.device}, input on {device}: call model.to(device)")
             if use_bn and (".bn1." in k or ".bn2." in k):
+                bn_changed = bn_changed or prev.get(k) != now[k]
                 continue   # lives on inside the folded convolution
+        for k, p in params:
+            if use_bn and (".bn1." in k or ".bn2." in k):
+                continue
+            if prev.get(k) == now[k] and not (bn_changed and k in folded):
+                continue
             t = folded.get(k, p).detach()
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
@@ -212,6 +223,7 @@ class _NativeDepthModel(nn.Module):
                        f"set_weight({k})")
         torch.cuda.current_stream(device).synchronize()  # temporaries above may be freed after this
         self._sig = sig
+        self._sig_by_key = now
         self._prepared = set()
 
     @torch.no_grad()

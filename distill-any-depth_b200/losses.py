@@ -3,6 +3,9 @@ same names, positional signatures and return conventions, computed by the sm_100
 ``csrc/losses.cu`` through the C ABI.  No host sync, no per-image Python loop; every function
 returns device tensors.  CUDA tensors only - there is no CPU fallback.
 """
+import functools
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -10,6 +13,32 @@ from . import _lib
 
 _STRATEGY = {"none": 0, "global": 1, "hybrid": 2, "local": 2}
 _ws_cache = {}
+
+
+def _first_cuda_device(objs):
+    for a in objs:
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, (list, tuple)):
+            d = _first_cuda_device(a)
+            if d is not None:
+                return d
+    return None
+
+
+def _on_tensor_device(fn):
+    """Run ``fn`` with the CUDA device of its first tensor argument current: the C ABI launches on the current device
+    and ``_lib.stream_ptr()`` / ``_workspace`` use that device's current stream, so tensors living on ``cuda:1`` while
+    ``cuda:0`` is current (the reference's ``.to(device)`` usage) get the right device, stream and scratch buffer."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _first_cuda_device(list(args) + list(kwargs.values()))
+        if dev is None:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 def _workspace(device, rows, K):
@@ -60,6 +89,7 @@ def _new_partials(device, want):
 
 
 # ------------------------------------------------------------------------------------------ SSI
+@_on_tensor_device
 def masked_shift_and_scale(depth_preds, depth_gt, mask_valid):
     """``:449-533`` - per (b, c) lower-median / mean-absolute-deviation alignment.
     Returns ``(depth_pred_aligned, depth_gt_aligned)``."""
@@ -78,12 +108,15 @@ def masked_shift_and_scale(depth_preds, depth_gt, mask_valid):
 def masked_l1_loss(preds, target, mask_valid, dense=False):
     """``:535-542`` (elementwise; kept in torch ops on the device - it is a single fused pass when
     reached through :class:`SSILoss`)."""
-    e = (preds - target).abs() * mask_valid
+    mv = mask_valid if mask_valid.dtype == torch.bool else (mask_valid != 0)
+    e = (preds - target).abs()
+    e = torch.where(mv, e, torch.zeros((), dtype=e.dtype, device=e.device))   # reference: loss[~mask] = 0 (NaN-safe)
     if dense:
         return e
     return e.sum() / (mask_valid.sum() + 1e-6)
 
 
+@_on_tensor_device
 def _ssi(depth_preds, depth_gt, mask_valid, dense, want_partials=False):
     p, g = _f32(depth_preds, "depth_preds"), _f32(depth_gt, "depth_gt")
     rows, L = _rows_L(p)
@@ -108,12 +141,14 @@ def _gout(g, device):
 
 class _SSIFn(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, pred, gt, mask):
         out, _ = _ssi(pred.detach(), gt, mask, False)
         ctx.save_for_backward(pred.detach(), gt.detach(), mask)
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         pred, gt, mask = ctx.saved_tensors
         p, t = _f32(pred, "depth_preds"), _f32(gt, "depth_gt")
@@ -131,6 +166,7 @@ class _HDNFn(torch.autograd.Function):
     """mode 'dr': contexts from (level, gt, mask) on the fly; mode 'ctx': explicit bool [K,B,1,H,W] contexts."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, pred, gt, mode, level, mask_or_ctx):
         ctx.mode, ctx.level = mode, level
         if mode == "dr":
@@ -142,6 +178,7 @@ class _HDNFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         pred, gt, aux = ctx.saved_tensors
         aux = aux if ctx.has_aux else None
@@ -166,11 +203,13 @@ class _HDNFn(torch.autograd.Function):
 
 class _GradFn(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, depth):
         ctx.save_for_backward(depth.detach())
         return _grad(depth.detach())[0]
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         (depth,) = ctx.saved_tensors
         d = _f32(depth, "depth")
@@ -183,11 +222,13 @@ class _GradFn(torch.autograd.Function):
 
 class _FeatFn(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, student, teacher):
         ctx.save_for_backward(student.detach(), teacher.detach())
         return _feat(student.detach(), teacher.detach())[0]
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         student, teacher = ctx.saved_tensors
         s, t = _f32(student, "student_features"), _f32(teacher, "teacher_features")
@@ -204,12 +245,14 @@ class _DistillFn(torch.autograd.Function):
     of the training loop feeds two student outputs, tools/train_distillation.py:1524-1529)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, a, b, strategy, num_segments):
         ctx.strategy, ctx.nseg = strategy, num_segments
         ctx.save_for_backward(a.detach(), b.detach())
         return _distill(a.detach(), b.detach(), strategy, num_segments)[0]
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         a, b = ctx.saved_tensors
         fa, fb = _f32(a, "student_depth"), _f32(b, "teacher_depth")
@@ -250,6 +293,7 @@ class SSILoss(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------ HDN
+@_on_tensor_device
 def get_contexts_dr(level, depth_gt, mask_valid):
     """``:544-576`` -> bool ``[2**level - 1, B, 1, H, W]``.  The returned tensor remembers how it was
     made so :func:`compute_hdn_loss` can take the fused path that never reads it."""
@@ -264,11 +308,26 @@ def get_contexts_dr(level, depth_gt, mask_valid):
     _lib.check(_lib.load().dad_contexts_dr(level, _lib.ptr(g), _lib.ptr(m), B, L, _lib.ptr(out), _lib.ptr(ws),
                                            ws.numel(), _lib.stream_ptr()), "get_contexts_dr")
     ctx = out.view(torch.bool)
-    ctx._dad_dr = (level, depth_gt.data_ptr(), depth_gt._version, tuple(depth_gt.shape),
-                   None if mask_valid is None else (mask_valid.data_ptr(), mask_valid._version), mask_valid)
+    # tag for the fused path: valid only while gt / mask / the contexts themselves are unmodified (weak reference to gt:
+    # a re-allocated tensor at the same address never matches)
+    ctx._dad_dr = (level, weakref.ref(depth_gt), depth_gt._version, tuple(depth_gt.shape),
+                   None if mask_valid is None else (mask_valid.data_ptr(), mask_valid._version), mask_valid, ctx._version)
     return ctx
 
 
+def _dr_tag(mask_valid_list, depth_gt):
+    """The (level, mask) of contexts made by :func:`get_contexts_dr` from exactly this ``depth_gt``, else None."""
+    tag = getattr(mask_valid_list, "_dad_dr", None)
+    if tag is None or tag[1]() is not depth_gt or tag[2] != depth_gt._version or tag[3] != tuple(depth_gt.shape):
+        return None
+    if tag[4] is not None and tag[4] != (tag[5].data_ptr(), tag[5]._version):
+        return None
+    if tag[6] != mask_valid_list._version:   # the contexts were edited in place: use them as given
+        return None
+    return tag[0], tag[5]
+
+
+@_on_tensor_device
 def _hdn(depth_preds, depth_gt, mask_valid_list, want_partials=False):
     p, g = _f32(depth_preds, "depth_preds"), _f32(depth_gt, "depth_gt")
     if p.dim() != 4 or p.shape[1] != 1:
@@ -277,11 +336,9 @@ def _hdn(depth_preds, depth_gt, mask_valid_list, want_partials=False):
     lib = _lib.load()
     out = _new_scalar(p.device)
     part = _new_partials(p.device, want_partials)
-    tag = getattr(mask_valid_list, "_dad_dr", None)
-    if tag is not None and tag[1] == depth_gt.data_ptr() and tag[2] == depth_gt._version \
-            and tag[3] == tuple(depth_gt.shape) \
-            and (tag[4] is None or tag[4] == (tag[5].data_ptr(), tag[5]._version)):
-        level, m = tag[0], _mask_u8(tag[5], g)
+    tag = _dr_tag(mask_valid_list, depth_gt)
+    if tag is not None:
+        level, m = tag[0], _mask_u8(tag[1], g)
         ws = _workspace(p.device, B, 2 ** level - 1)
         _lib.check(lib.dad_hdn_loss_dr(level, _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), B, L, _lib.ptr(out),
                                        _lib.ptr(part), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "compute_hdn_loss")
@@ -300,15 +357,14 @@ def _hdn(depth_preds, depth_gt, mask_valid_list, want_partials=False):
 def compute_hdn_loss(ssi_loss, depth_preds, depth_gt, mask_valid_list):
     """``:686-707``.  ``ssi_loss`` is accepted for signature parity (the kernel *is* SSI-MAE)."""
     if _wants_grad(depth_preds):
-        tag = getattr(mask_valid_list, "_dad_dr", None)
-        if tag is not None and tag[1] == depth_gt.data_ptr() and tag[2] == depth_gt._version \
-                and tag[3] == tuple(depth_gt.shape) \
-                and (tag[4] is None or tag[4] == (tag[5].data_ptr(), tag[5]._version)):
-            return _HDNFn.apply(depth_preds, depth_gt, "dr", tag[0], tag[5])
+        tag = _dr_tag(mask_valid_list, depth_gt)
+        if tag is not None:
+            return _HDNFn.apply(depth_preds, depth_gt, "dr", tag[0], tag[1])
         return _HDNFn.apply(depth_preds, depth_gt, "ctx", 0, mask_valid_list)
     return _hdn(depth_preds, depth_gt, mask_valid_list)[0]
 
 
+@_on_tensor_device
 def hdn_loss_dr(depth_preds, depth_gt, mask_valid=None, level=3, want_partials=False):
     """Fused ``compute_hdn_loss(SSILoss(), p, g, get_contexts_dr(level, g, mask))`` (training call
     site ``:1547-1553``) without materialising the contexts."""
@@ -325,6 +381,7 @@ def hdn_loss_dr(depth_preds, depth_gt, mask_valid=None, level=3, want_partials=F
     return (out, part) if want_partials else out
 
 
+@_on_tensor_device
 def get_contexts_dp(level, depth_gt, mask_valid):
     """``:578-644`` -> bool ``[2**level - 1, B, 1, H, W]``: depth-percentile bins between the
     ``nanquantile`` values of the valid pixels (exact order statistics by radix select + ATen's lerp)."""
@@ -343,6 +400,7 @@ def get_contexts_dp(level, depth_gt, mask_valid):
     return out.view(torch.bool)
 
 
+@_on_tensor_device
 def get_contexts_ds(level, mask_valid):
     """``:646-673`` -> bool ``[1 + 4 + ... + 4**(level-1), B, 1, H, W]``: valid mask AND an n x n spatial
     grid per level (template side = ``mask_valid.shape[-1]``; square maps, as upstream)."""
@@ -363,6 +421,7 @@ def get_contexts_ds(level, mask_valid):
 
 
 # ------------------------------------------------------------------------------------------ Sobel
+@_on_tensor_device
 def _grad(depth, want_partials=False):
     d = _f32(depth, "depth")
     if d.dim() != 4 or d.shape[1] != 1:
@@ -383,6 +442,7 @@ def gradient_preservation_loss(depth):
 
 
 # ------------------------------------------------------------------------------------------ feature cosine
+@_on_tensor_device
 def _feat(student_features, teacher_features, want_partials=False):
     s, t = _f32(student_features, "student_features"), _f32(teacher_features, "teacher_features")
     if s.dim() != 3 or t.dim() != 3 or s.shape[0] != t.shape[0]:
@@ -419,6 +479,7 @@ def feature_distillation_loss(student_features, teacher_features, device=None):
 
 
 # ------------------------------------------------------------------------------------------ normalised L1
+@_on_tensor_device
 def _distill(student_depth, teacher_depth, norm_strategy, num_segments=4, want_partials=False, want_norm=False):
     if norm_strategy not in _STRATEGY:
         raise ValueError(f"Unknown normalization strategy: {norm_strategy}")

@@ -1,5 +1,5 @@
 """Device time + accuracy of the tcgen05 attention kernel at the ViT-L shapes (not a pytest file).
-usage: DAD_ATT_VARIANT={2,3,4} DAD_ATT_POLY={0,2,3,4} python tests/gpu_attn_time.py [B N heads [scale]]
+usage: DAD_ATT_VARIANT={5,2,3} DAD_ATT_POLY5={0,2,3,4,5} python tests/gpu_attn_time.py [B N heads [scale]]
 (scale = std of the random q/k/v; 0.5 gives the no-rescale regime of a random-init model, 1.5 forces rescales)"""
 import os
 import sys
@@ -29,5 +29,5 @@ flops = 4.0 * B * heads * N * N * 64
 q, k, v = qkv[:N].float().view(N, 3, heads, 64).permute(1, 2, 0, 3)
 ref = (torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v).permute(1, 0, 2).reshape(N, heads * 64)
 err = (out[:N].float() - ref).abs().max().item() / ref.abs().max().item()
-print(f"variant={os.environ.get('DAD_ATT_VARIANT', '2')} poly={os.environ.get('DAD_ATT_POLY', '-')} scale={scale} B={B} N={N} h={heads}: {ms:.3f} ms  "
+print(f"variant={os.environ.get('DAD_ATT_VARIANT', '5')} poly={os.environ.get('DAD_ATT_POLY5', '-')} scale={scale} B={B} N={N} h={heads}: {ms:.3f} ms  "
       f"{flops / ms / 1e9:.0f} TFLOP/s  max_err/max_ref={err:.2e}", flush=True)

@@ -221,3 +221,49 @@ def test_cuda_graph_capture_replays_bit_identically():
             assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b))
     with pytest.raises(ValueError):
         cap(x0[:2])
+
+
+def test_cuda_graph_replay_sees_weight_updates_including_the_head_bias():
+    """graph.py contract: after a weight update, one eager forward repacks the operands in place and the captured graph
+    then computes with the NEW weights.  output_conv2.2.bias used to travel by value inside the captured kernel
+    parameters (stale after an optimiser step); it is a device pointer now."""
+    import distill_any_depth_b200 as d
+    for precision in ("bf16", "fp32"):
+        m, _, _ = build("vits", 0)
+        m.precision = precision
+        x = synthetic.make_images(2, 70, 98, seed=3).cuda()
+        cap = d.capture(lambda t: m(t), x)
+        before = [t.clone() for t in cap(x)]
+        with torch.no_grad():
+            m.depth_head.scratch.output_conv2[2].bias.add_(0.75)
+            m.depth_head.scratch.output_conv2[0].weight.mul_(1.5)
+            m.pretrained.blocks[0].mlp.fc1.bias.add_(0.05)
+        eager = [t.clone() for t in m(x)]          # repacks in place
+        after = cap(x)
+        torch.cuda.synchronize()
+        assert not torch.equal(before[0], eager[0])
+        assert torch.equal(after[0], eager[0]) and torch.equal(after[1], eager[1]), precision
+        assert float((eager[0] - before[0]).abs().min()) > 0.1   # the bias shift reached every pixel
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_losses_run_on_the_tensors_device_not_the_current_one():
+    """Tensors on cuda:1 while cuda:0 is current (the reference's .to(device) usage): every loss entry point must launch
+    on the tensors' device and stream."""
+    import distill_any_depth_b200 as d
+    pred, gt, mask = synthetic.make_depth_pair(3, 56, 84, seed=8)
+    feats = synthetic.make_features(3, 49, 96, seed=1)
+    feats_t = synthetic.make_features(3, 49, 128, seed=2)
+    ref = dict(ssi=oracle.SSILoss()(pred, gt, mask), grad=oracle.gradient_preservation_loss(pred),
+               hdn=oracle.compute_hdn_loss(oracle.SSILoss(), pred, gt, oracle.get_contexts_dr(3, gt, mask)),
+               dist=oracle.distillation_loss(pred, gt, "hybrid"), feat=oracle.feature_distillation_loss(feats, feats_t))
+    dev = torch.device("cuda:1")
+    torch.cuda.set_device(0)
+    p, g, mk = pred.to(dev), gt.to(dev), mask.to(dev)
+    got = dict(ssi=d.SSILoss()(p, g, mk), grad=d.gradient_preservation_loss(p),
+               hdn=d.compute_hdn_loss(d.SSILoss(), p, g, d.get_contexts_dr(3, g, mk)),
+               dist=d.distillation_loss(p, g, "hybrid"), feat=d.feature_distillation_loss(feats.to(dev), feats_t.to(dev)))
+    assert torch.cuda.current_device() == 0
+    for k in ref:
+        assert got[k].device == dev
+        assert abs(float(got[k]) - float(ref[k])) <= 1e-3 * max(abs(float(ref[k])), 1e-6), k

@@ -154,16 +154,13 @@ def test_conv_stride2_matches_conv2d(B, H, W, C, Co):
     assert (out - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
 
 
-# variant 4 (attention_tc4.cu: two softmax warpgroups per CTA, no in-kernel rescale) is EXPERIMENTAL and has not run on
-# hardware yet: it joins the parametrisation only with DAD_TEST_EXPERIMENTAL=1
-_ATT_VARIANTS = {2: "pipelined2cta", 3: "serial4cta"}
-if os.environ.get("DAD_TEST_EXPERIMENTAL"):
-    _ATT_VARIANTS[4] = "twohalves_experimental"
+# 5 = attention_tc5.cu (the default), 2 / 3 = the round-1 kernels kept for A/B measurements
+_ATT_VARIANTS = {5: "tc5_default", 2: "pipelined2cta", 3: "serial4cta"}
 
 
 @pytest.fixture(params=list(_ATT_VARIANTS), ids=list(_ATT_VARIANTS.values()))
 def att_variant(request, monkeypatch):
-    """Both tcgen05 attention kernels (attention_tc.cu / attention_tc3.cu) go through the same tests."""
+    """All tcgen05 attention kernels (attention_tc5.cu / attention_tc.cu / attention_tc3.cu) go through the same tests."""
     monkeypatch.setenv("DAD_ATT_VARIANT", str(request.param))
     return request.param
 
@@ -206,5 +203,33 @@ def test_attention_lazy_rescale_path(att_variant):
     torch.cuda.synchronize()
     r = qq.double().reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
     ref = ((r[0] @ r[1].transpose(-2, -1)).softmax(-1) @ r[2]).transpose(1, 2).reshape(B * N, D).float()
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("poly", [0, 2, 3, 4, 5])
+def test_attention_tc5_overflow_falls_back_to_exact_passes(poly, monkeypatch):
+    """attention_tc5 exponentiates against the FIRST key tile's row maximum; later logits more than 127 log2 units above
+    it make the tensor-core row sum non-finite, and the CTA must then redo its work in-kernel (max pass + exact pass).
+    Rows that overflow and rows that do not share CTAs here; every FMA-pipe / MUFU split is exercised."""
+    monkeypatch.setenv("DAD_ATT_VARIANT", "5")
+    monkeypatch.setenv("DAD_ATT_POLY5", str(poly))
+    L = _lib()
+    lib = L.load()
+    B, N, heads = 2, 700, 2
+    D = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn(B, N, 3, heads, 64, device="cuda", generator=g)
+    qkv[:, :, 0] *= 0.7
+    qkv[:, 200:330, 1] *= 14.0   # logit std ~ 8 * 0.7 * 14 = 78 (113 log2 units): far beyond the first tile's maximum
+    qkv[0, :, 0, 1] *= 0.05      # image 0 / head 1: small logits everywhere -> no overflow in those CTAs
+    qq = qkv.reshape(B * N, 3 * D).bfloat16().contiguous()
+    out = torch.full((B * N, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(lib.dad_attention(L.ptr(qq), L.ptr(out), B, N, heads, 0, L.stream_ptr()), "dad_attention")
+    torch.cuda.synchronize()
+    r = qq.double().reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = r[0] @ r[1].transpose(-2, -1)
+    assert ((s[..., 64:].max(-1).values - s[..., :64].max(-1).values) * 1.4427 > 130).any(), "test does not overflow"
+    ref = (s.softmax(-1) @ r[2]).transpose(1, 2).reshape(B * N, D).float()
     assert torch.isfinite(out.float()).all()
     assert (out.float() - ref).abs().max().item() <= 3e-2 * max(1.0, ref.abs().max().item())

@@ -252,9 +252,10 @@ def _train_worker(rank, world, port, q):
     t64 = lambda a, b: torch.tensor([float(a), float(b)], dtype=torch.float64)
     w = shard_loss_weights({"ssi": ("ssi", t64(0, sl(mask).sum())), "grad": ("grad", t64(0, pred.numel()))})
     (w["ssi"] * ssi + 0.2 * w["grad"] * grad).backward()
-    n = allreduce_gradients(net.parameters(), bucket_bytes=64)   # tiny buckets: several collectives
+    unused = torch.nn.Parameter(torch.zeros(3))   # no gradient on any rank (the reference's mask_token): must stay None
+    n = allreduce_gradients(list(net.parameters()) + [unused], bucket_bytes=64)   # tiny buckets: several collectives
     if rank == 0:
-        q.put(([p.grad.clone() for p in net.parameters()], n))
+        q.put(([p.grad.clone() for p in net.parameters()], n, unused.grad is None))
     dist.destroy_process_group()
 
 
@@ -277,7 +278,8 @@ def test_two_rank_training_gradient_equals_single_process_full_batch():
     procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got, n_coll = q.get(timeout=120)
+    got, n_coll, unused_stays_none = q.get(timeout=120)
+    assert unused_stays_none
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
