@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--size", type=int, default=518)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the same-box PyTorch-eager GPU baseline (an extra)")
     ap.add_argument("--graph", type=int, default=1, choices=[0, 1],
                     help="1 (default): capture one step (forward + losses [+ all-reduce]) in a CUDA graph after warm-up and "
                          "replay it in the timed loops; 0: launch every kernel from the host each step")
@@ -114,6 +115,60 @@ def cpu_baseline(a):
         best = min(best, time.perf_counter() - t)
     return dict(value=1.0 / best, unit="images/s", cores=cores, kind="port",
                 sample="B=1 of the same workload (oracle fp32 forward + SSI + HDN-DR on host threads), best of 2 after 1 warm-up")
+
+
+def gpu_eager_baseline(a, dev):
+    """Same-box GPU baseline: the reference algorithm as plain PyTorch eager ops on the B200 - the oracle's
+    functions on CUDA tensors, i.e. cuBLAS / cuDNN / ATen kernels with the reference's naive attention
+    (dinov2_layers/attention.py:49-62) - in fp32 (TF32 off) and under torch.autocast(bfloat16).  A stated extra, never the
+    target: it says what the hand-written kernels buy over the library path on the same GPU."""
+    import torch
+    import oracle
+    from distill_any_depth_b200 import synthetic
+    kw = synthetic.MODEL_PRESETS[a.encoder]
+    sd = {k: v.to(dev) for k, v in synthetic.make_state_dict(seed=1, **kw).items()}
+    B = a.batch
+    x = synthetic.make_images(B, a.size, a.size, seed=1234).to(dev)
+    _, gt, _ = synthetic.make_depth_pair(B, a.size, a.size, seed=7)
+    gt = gt.to(dev)
+    full = torch.ones_like(gt, dtype=torch.bool)
+    ssi = oracle.SSILoss()
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    def step(autocast):
+        with torch.no_grad():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                depth, _ = oracle.depth_anything_forward(x, sd, kw["encoder"])
+            depth = depth.float()
+            l1 = ssi(depth, gt, full)
+            l2 = oracle.compute_hdn_loss(ssi, depth, gt, oracle.get_contexts_dr(3, gt, None))
+        return torch.stack([l1, l2])
+
+    out = {}
+    try:
+        for name, ac in (("fp32_tf32_off", False), ("autocast_bf16", True)):
+            step(ac)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 2
+            e0.record()
+            for _ in range(n):
+                last = step(ac)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            out[name] = dict(value=B / ms * 1e3, unit="images/s", ms_per_step=ms, batch=B, losses=[float(v) for v in last.cpu()])
+        out["what"] = ("reference algorithm (oracle port) as PyTorch eager ops on this GPU: cuBLAS / cuDNN / ATen, naive attention; "
+                       "2 steps after 1 warm-up, inputs resident in HBM")
+    except Exception as ex:  # an extra: never let it take the bench line down
+        out["error"] = f"{type(ex).__name__}: {ex}"
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        del sd, x
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(a):
@@ -506,11 +561,14 @@ def run_b200(a):
     e2e_value = imgs / max(ms_e2e, wall_e2e if world == 1 else ms_e2e) * 1e3
     gt_ = prof.get("gemm_tc")
     traffic = None
-    try:  # DRAM bytes per launch from the committed ncu --set full capture (tools/summarize_ncu.py), not measured live
+    traffic_source = None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture (tools/summarize_ncu.py): ncu cannot run inside
+        # a timed bench, so this figure is FROM THE PROFILE of the same command, and labelled so
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             tr = json.load(f)
         if a.workload == "c3" and a.batch == 32:
             traffic = tr["classes"]["gemm_tc"]["dram_bytes_per_launch"]
+            traffic_source = "from_profile: profiles/roofline_traffic.json (" + str(tr.get("source", "ncu --set full")) + ")"
     except Exception:
         pass
     roofline = None
@@ -520,7 +578,7 @@ def run_b200(a):
         # inside a long step), from MEASURED_PEAKS.json.
         ach = gt_["work_per_step"] / (gt_["ms_per_step"] * 1e-3) / 1e12
         roofline = dict(bound="tensor", achieved=ach, peak=pk["tf_sustained"], unit="TFLOP/s", frac=ach / pk["tf_sustained"],
-                        traffic=traffic, flops_per_launch=gt_["work_per_step"] / gt_["launches_per_step"],
+                        traffic=traffic, traffic_source=traffic_source, flops_per_launch=gt_["work_per_step"] / gt_["launches_per_step"],
                         kernel="tcgen05 GEMM / implicit-GEMM conv kernels (gemm_tc, gemm_tc2, conv_tc2: all launches of a step)", peak_source=pk["src"] + " sustained bf16",
                         launches_per_step=gt_["launches_per_step"], avg_launch_ms=gt_["avg_launch_ms"],
                         share_of_step=gt_["ms_per_step"] / (ms_dev / a.steps))
@@ -538,6 +596,9 @@ def run_b200(a):
                 gpu_launches=int(launches), clocks=sampler.result(), roofline=roofline, kernel_breakdown=prof)
     if world == 1 and not a.no_cpu_baseline and a.workload == "c3":
         line["cpu_baseline"] = cpu_baseline(a)
+    if world == 1 and not a.no_gpu_eager and a.workload == "c3":
+        torch.set_grad_enabled(False)
+        line["gpu_eager_baseline"] = gpu_eager_baseline(a, dev)
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     finish_ranks()
 

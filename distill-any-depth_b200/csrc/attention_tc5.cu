@@ -1,22 +1,28 @@
 // Fused multi-head attention on the 5th-gen tensor cores (sm_100a), head_dim 64, non-causal, no mask
 // (reference dinov2_layers/attention.py:49-62; 64^-0.5 is folded into the packed qkv weights).
 //
-// Round-2 kernel.  Same tiling as attention_tc.cu (CTA = image x head x 128 queries, two CTAs per SM, 64-key tiles,
-// S double-buffered in TMEM, P consumed from TMEM as the A operand of the second MMA), rebuilt around what
-// tools/softmax_bench.cu measured on a B200 (exp2 results per clock per SM, 2 softmax warps per scheduler):
-//     FFMA + MUFU + FADD + CVT per element (round 1)            13.3
-//     FFMA2 + MUFU + CVT, half of the pairs on the FMA pipe      19.4     (MUFU alone: 16 by construction)
-// so the softmax threads now execute NOTHING but  a = s * log2e - ref  (one packed FFMA2 per pair), the exponential
-// (MUFU for some pairs, a packed cubic on the FMA pipe for the others) and the bf16 pack:
-//   * the row sum  l = sum_j P  is computed by the TENSOR CORE: a third MMA per key tile multiplies P (TMEM) by a constant
-//     all-ones [64 x 16] operand into 16 extra accumulator columns (+12 % tensor-pipe time, which has slack);
-//   * there is no running maximum and no rescale in the loop: P is taken relative to the row maximum of the FIRST key
-//     tile (floating point keeps full relative precision for P up to 2^127).  If a later score exceeds that reference
-//     by more than 127 log2 units the row sum comes out non-finite; the CTA then repeats its work INSIDE the same launch:
-//     one pass that only tracks the exact row maximum, one pass that exponentiates against it.  No flag buffer, no second
-//     kernel, nothing allocated: exact for any input, capture-safe, and the fast path carries no check at all;
-//   * P overwrites its own S columns in place, which frees TMEM for the row-sum accumulator
-//     (256 columns per CTA: S0/P0 [0,64) S1/P1 [64,128) | O [128,192) | L [192,208)).
+// Round-2 kernel: PERSISTENT CTAs (two per SM), work item = (image, head, 128 queries), 64-key tiles.  Built around
+// three measurements taken on a B200 (profiles/attention_r2.md):
+//  (1) tools/softmax_bench.cu - exp2 results per clock per SM, 2 softmax warps per scheduler:
+//        FFMA + MUFU + FADD + CVT per element (round 1)          13.3
+//        FFMA2 + MUFU + CVT, part of the pairs on the FMA pipe   17.6 - 19.4   (MUFU alone: 16 by construction)
+//      so the softmax threads execute nothing but  a = s * log2e - ref  (one packed FFMA2 per pair), the exponential
+//      (MUFU for some pairs, a packed cubic on the FMA pipe for the others) and the bf16 pack:
+//        * the row sum  l = sum_j P  is computed by the TENSOR CORE: a third MMA per key tile multiplies P (TMEM) by a
+//          constant all-ones [64 x 16] operand into 16 extra accumulator columns;
+//        * no running maximum and no rescale in the loop: P is taken relative to the row maximum of the FIRST key tile
+//          (floating point keeps full relative precision for P up to 2^127).  A later score more than 127 log2 units
+//          above that reference makes the row sum non-finite; the work item is then put on the CTA's redo list and
+//          recomputed at the end of the same launch with the exact row maximum (one max-only pass + one exact pass).
+//          No flag buffer, no second kernel, nothing allocated, and the fast path carries no check at all.
+//  (2) ncu source page of the one-CTA-per-item version: 21 % of the softmax warps' time went to per-CTA start-up / drain
+//      -> persistent CTAs whose TMA / MMA warps stream straight into the next item (Q double-buffered).
+//      The next score tile's barrier is probed with a non-blocking test_wait before the second half of the exponentials,
+//      so the ~90-clock latency of a successful try_wait is off the critical path.
+//  (3) two further restructurings were built and measured and are NOT used (profiles/attention_r2.md): releasing the score
+//      buffer as soon as S is in registers (Q K^T of tile g+2 issued at the start of tile g) with P in its own
+//      single / double buffer ran 0.42 - 0.43 ms per ViT-L launch against 0.333 ms for this kernel.
+// TMEM (256 columns per CTA): S0/P0 [0,64) S1/P1 [64,128) | O [128,192) | L [192,208): P is written in place of S.
 // Roles (192 threads): warps 0-3 softmax (thread = query row), warp 4 TMA producer, warp 5 tcgen05.mma issuer.
 #include <cstdlib>
 
@@ -29,14 +35,15 @@ namespace dad {
 namespace {
 
 constexpr int BQ = 128, BKV = 64, HD = 64;
-constexpr int Q_BYTES = BQ * HD * 2;      // 16 KB
+constexpr int Q_BYTES = BQ * HD * 2;      // 16 KB (x2: the next item's Q is prefetched)
 constexpr int KV_BYTES = BKV * HD * 2;    // 8 KB
 constexpr int ONES_BYTES = 16 * 128;      // [16 "n" rows][64 k] bf16, K-major, all 1.0
 constexpr int KV_STAGES = 4;
 constexpr int ATT_THREADS = 192;
 constexpr int TMEM_COLS = 256;
 constexpr int S_COL = 0, O_COL = 128, L_COL = 192;
-constexpr int ATT_SMEM = Q_BYTES + 2 * KV_STAGES * KV_BYTES + ONES_BYTES + 1024 + 256;
+constexpr int MAX_ITEMS_PER_CTA = 2048;   // redo bitmap: one bit per item of this CTA
+constexpr int ATT_SMEM = 2 * Q_BYTES + 2 * KV_STAGES * KV_BYTES + ONES_BYTES + 512 + MAX_ITEMS_PER_CTA / 8 + 1024;
 constexpr float LOG2E = 1.4426950408889634f;
 
 enum : int { MODE_FAST = 0, MODE_MAXPASS = 1, MODE_EXACT = 2 };
@@ -82,29 +89,31 @@ __device__ __forceinline__ float max32(const uint32_t (&x)[32], int col0, int nv
 template <int PP>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int N, int D) {
+                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int N, int D, int heads, int total) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = smem + Q_BYTES;
-    uint8_t* sV = smem + Q_BYTES + KV_STAGES * KV_BYTES;
-    uint8_t* sOnes = smem + Q_BYTES + 2 * KV_STAGES * KV_BYTES;
+    uint8_t* sQ = smem;                                   // [2][Q_BYTES]
+    uint8_t* sK = smem + 2 * Q_BYTES;
+    uint8_t* sV = sK + KV_STAGES * KV_BYTES;
+    uint8_t* sOnes = sV + KV_STAGES * KV_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES);
-    uint64_t* q_full = bars;
-    uint64_t* k_full = bars + 1;                      // [KV_STAGES]
-    uint64_t* v_full = bars + 1 + KV_STAGES;          // [KV_STAGES]
-    uint64_t* kv_empty = bars + 1 + 2 * KV_STAGES;    // [KV_STAGES]
-    uint64_t* s_full = bars + 1 + 3 * KV_STAGES;      // [2]
+    uint64_t* q_full = bars;                          // [2]
+    uint64_t* q_empty = bars + 2;                     // [2]
+    uint64_t* k_full = bars + 4;                      // [KV_STAGES]
+    uint64_t* v_full = k_full + KV_STAGES;            // [KV_STAGES]
+    uint64_t* kv_empty = v_full + KV_STAGES;          // [KV_STAGES]
+    uint64_t* s_full = kv_empty + KV_STAGES;          // [2]
     uint64_t* p_full = s_full + 2;                    // [2], 128 arrivals
-    uint64_t* done = s_full + 4;                      // last P V of a pass retired
-    uint64_t* verdict = s_full + 5;                   // softmax -> TMA / MMA warps: repeat the pass loop?
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
-    volatile int* again = reinterpret_cast<volatile int*>(tmem_slot + 1);
-    int* overflow = reinterpret_cast<int*>(tmem_slot + 2);
+    uint64_t* done = p_full + 2;                      // last P V / L of an item retired
+    uint64_t* main_done = done + 1;                   // softmax -> TMA / MMA warps: the redo bitmap is final
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(main_done + 1);
+    uint32_t* redo = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [MAX_ITEMS_PER_CTA / 32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
     const int T = (N + BKV - 1) / BKV;
+    const int QT = (N + BQ - 1) / BQ;
+    const int G = gridDim.x;
+    const int n_mine = (total - static_cast<int>(blockIdx.x) + G - 1) / G;   // items blockIdx.x, blockIdx.x + G, ...
 
     if (warp == 4 && lane == 0) {
         ptx::prefetch_tmap(&tmQ);
@@ -113,23 +122,24 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     if (warp < 4) {   // all-ones operand of the row-sum MMA (swizzle-invariant), visible to the async proxy
         reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        if (threadIdx.x < MAX_ITEMS_PER_CTA / 32) redo[threadIdx.x] = 0u;
         ptx::fence_proxy_async_smem();
     }
     if (warp == 5) {
         if (lane == 0) {
-            ptx::mbar_init(q_full, 1);
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(&q_full[i], 1);
+                ptx::mbar_init(&q_empty[i], 1);
+                ptx::mbar_init(&s_full[i], 1);
+                ptx::mbar_init(&p_full[i], 128);
+            }
             for (int i = 0; i < KV_STAGES; ++i) {
                 ptx::mbar_init(&k_full[i], 1);
                 ptx::mbar_init(&v_full[i], 1);
                 ptx::mbar_init(&kv_empty[i], 1);
             }
-            for (int i = 0; i < 2; ++i) {
-                ptx::mbar_init(&s_full[i], 1);
-                ptx::mbar_init(&p_full[i], 128);
-            }
             ptx::mbar_init(done, 1);
-            ptx::mbar_init(verdict, 1);
-            *overflow = 0;
+            ptx::mbar_init(main_done, 1);
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -142,25 +152,38 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tmem = *tmem_slot;
     pdl_wait();  // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
+    // Every role walks the same sequence of STREAMS: the main stream (all n_mine items back to back), then one
+    // single-item stream per redo pass.  g = running key-tile counter, it = running item counter over all streams:
+    // they index the ring stages and give every barrier its phase parity.
+    const auto redo_bit = [&](int i) { return (reinterpret_cast<volatile uint32_t*>(redo)[i >> 5] >> (i & 31)) & 1u; };
+
     if (warp == 4) {
         if (lane == 0) {
             // ---------------------------------------------------------------- TMA producer
-            ptx::mbar_arrive_expect_tx(q_full, Q_BYTES);
-            ptx::tma_load_3d(sQ, &tmQ, q_full, h * HD, q0, b);
-            int g = 0;
-            for (int pass = 0;; ++pass) {
+            int g = 0, it = 0;
+            auto stream_item = [&](int w) {
+                const int qt = w % QT, bh = w / QT, h = bh % heads, b = bh / heads;
+                const int qb = it & 1;
+                ptx::mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&q_full[qb], Q_BYTES);
+                ptx::tma_load_3d(sQ + qb * Q_BYTES, &tmQ, &q_full[qb], h * HD, qt * BQ, b);
                 for (int j = 0; j < T; ++j, ++g) {
                     const int s = g % KV_STAGES;
-                    const uint32_t ph = (g / KV_STAGES) & 1;
-                    ptx::mbar_wait(&kv_empty[s], ph ^ 1);
+                    ptx::mbar_wait(&kv_empty[s], ((g / KV_STAGES) & 1) ^ 1);
                     ptx::mbar_arrive_expect_tx(&k_full[s], KV_BYTES);
                     ptx::tma_load_3d(sK + s * KV_BYTES, &tmK, &k_full[s], h * HD, j * BKV, b);
                     ptx::mbar_arrive_expect_tx(&v_full[s], KV_BYTES);
                     ptx::tma_load_3d(sV + s * KV_BYTES, &tmV, &v_full[s], h * HD, j * BKV, b);
                 }
-                ptx::mbar_wait(verdict, pass & 1);
-                if (!*again) break;
-            }
+                ++it;
+            };
+            for (int i = 0; i < n_mine; ++i) stream_item(blockIdx.x + i * G);
+            ptx::mbar_wait(main_done, 0);
+            for (int i = 0; i < n_mine; ++i)
+                if (redo_bit(i)) {
+                    stream_item(blockIdx.x + i * G);   // max-only pass
+                    stream_item(blockIdx.x + i * G);   // exact pass
+                }
         }
     } else if (warp == 5) {
         // -------------------------------------------------------------------- MMA issuer
@@ -168,11 +191,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_bmn(BQ, HD);
         constexpr uint32_t idesc_l = ptx::make_idesc_bf16(BQ, 16);
         constexpr uint32_t kDescHiMn = (1024u >> 4) | (1u << 14) | (2u << 29);
-        const uint32_t q_lo = ptx::desc_lo_sw128(ptx::smem_u32(sQ));
+        const uint32_t q_lo0 = ptx::desc_lo_sw128(ptx::smem_u32(sQ));
         const uint32_t k_lo0 = ptx::desc_lo_sw128(ptx::smem_u32(sK));
         const uint32_t v_lo0 = ptx::desc_lo_mn_sw128(ptx::smem_u32(sV));
         const uint32_t one_lo = ptx::desc_lo_sw128(ptx::smem_u32(sOnes));
-        auto issue_qk = [&](int g) {  // S[g & 1] = Q K_g^T
+        int g0 = 0, it = 0;
+        auto issue_qk = [&](int g, uint32_t q_lo) {  // S[g & 1] = Q K_g^T
             const int s = g % KV_STAGES;
             ptx::mbar_wait(&k_full[s], (g / KV_STAGES) & 1);
             ptx::tc_fence_after();
@@ -186,16 +210,19 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             __syncwarp();
         };
-        ptx::mbar_wait(q_full, 0);
-        int g0 = 0;
-        for (int pass = 0;; ++pass) {
-            issue_qk(g0);
-            if (T > 1) issue_qk(g0 + 1);
+        auto mma_item = [&]() {
+            const int qb = it & 1;
+            const uint32_t q_lo = q_lo0 + qb * (Q_BYTES >> 4);
+            ptx::mbar_wait(&q_full[qb], (it >> 1) & 1);
+            // the first two S tiles of an item are issued while the softmax warps may still be storing the previous
+            // item's output: S[g & 1] only has to be past P V of tile g - 2 (in-order pipe); O / L are not touched here
+            issue_qk(g0, q_lo);
+            if (T > 1) issue_qk(g0 + 1, q_lo);
             for (int j = 0; j < T; ++j) {
                 const int g = g0 + j;
                 const int s = g % KV_STAGES;
-                ptx::mbar_wait(&p_full[g & 1], (g >> 1) & 1);       // P_g written in place of S[g & 1]
-                ptx::mbar_wait(&v_full[s], (g / KV_STAGES) & 1);
+                ptx::mbar_wait(&p_full[g & 1], (g >> 1) & 1);       // P_g written in place of S[g & 1]; for j == 0 also:
+                ptx::mbar_wait(&v_full[s], (g / KV_STAGES) & 1);    // the previous item's O / L have been read out
                 ptx::tc_fence_after();
                 const uint32_t v_lo = v_lo0 + s * (KV_BYTES >> 4);
                 const uint32_t tP = tmem + S_COL + (g & 1) * BKV;
@@ -209,27 +236,42 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         ptx::umma_bf16_ts(tmem + L_COL, tP + k * 8, ptx::make_desc(one_lo + 2 * k, ptx::kDescHiSw128),
                                           idesc_l, (j | k) != 0 ? 1u : 0u);
                     ptx::umma_commit(&kv_empty[s]);                  // K_g / V_g stage free once these retire
-                    if (j == T - 1) ptx::umma_commit(done);
+                    if (j == T - 1) {
+                        ptx::umma_commit(done);
+                        ptx::umma_commit(&q_empty[qb]);              // every Q K^T of this item has retired
+                    }
                 }
                 __syncwarp();
-                if (j + 2 < T) issue_qk(g + 2);                      // executes after P V_g (in-order pipe): S[g & 1] is free
+                if (j + 2 < T) issue_qk(g + 2, q_lo);                // executes after P V_g (in-order pipe): S[g & 1] is free
             }
             g0 += T;
-            ptx::mbar_wait(verdict, pass & 1);
-            if (!*again) break;
-        }
+            ++it;
+        };
+        for (int i = 0; i < n_mine; ++i) mma_item();
         pdl_launch_dependents();
+        ptx::mbar_wait(main_done, 0);
+        for (int i = 0; i < n_mine; ++i)
+            if (redo_bit(i)) {
+                mma_item();
+                mma_item();
+            }
     } else {
         // -------------------------------------------------------------------- softmax (warps 0-3)
         const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
         const uint32_t tS = tmem + lane_base + S_COL, tO = tmem + lane_base + O_COL, tL = tmem + lane_base + L_COL;
         const uint64_t sc2 = ptx::pack2(LOG2E, LOG2E);
-        uint64_t nref2 = 0;
         uint32_t v_lo[32], v_hi[32], pk[16];
-        int mode = MODE_FAST;
-        int g0 = 0;
-        float rmax = -INFINITY, l = 1.f;
-        for (int pass = 0;; ++pass) {
+        int g0 = 0, it = 0;
+        float rmax = -INFINITY;   // MAXPASS result, consumed by the EXACT pass that follows it
+
+        auto softmax_item = [&](int w, int idx, int mode) {
+            const int qt = w % QT, bh = w / QT, h = bh % heads, b = bh / heads;
+            uint64_t nref2 = 0;
+            if (mode == MODE_EXACT) {
+                const float m = rmax * LOG2E;
+                nref2 = ptx::pack2(-m, -m);
+            }
+            if (mode == MODE_MAXPASS) rmax = -INFINITY;
             ptx::mbar_wait(&s_full[g0 & 1], (g0 >> 1) & 1);
             ptx::tc_fence_after();
             ptx::tmem_ld_32x32(tS + (g0 & 1) * BKV, v_lo);
@@ -239,6 +281,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 const int nvalid = min(BKV, N - j * BKV);
                 ptx::tmem_ld_wait();                                   // first half of tile j is in registers
                 ptx::tmem_ld_32x32(tS + buf * BKV + 32, v_hi);          // second half: in flight during the first exps
+                uint32_t next_ready = 1u;
                 if (mode == MODE_MAXPASS) {
                     ptx::tmem_ld_wait();
                     rmax = fmaxf(rmax, fmaxf(max32(v_lo, 0, nvalid), max32(v_hi, 32, nvalid)));
@@ -252,12 +295,15 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     if (nvalid < BKV) mask16(pk, 0, nvalid);
                     ptx::tmem_st_32x16(tS + buf * BKV, pk);             // P columns [0,16) <- keys [0,32) (S lo is in registers)
                     ptx::tmem_ld_wait();                                // second half arrived
+                    // S_{j+1} follows P V_{j-1} in the tensor pipe and lands about now: probe its barrier (non-blocking);
+                    // the probe's latency hides behind the second half of the exponentials
+                    if (j + 1 < T) next_ready = ptx::mbar_test_wait(&s_full[buf ^ 1], ((g + 1) >> 1) & 1);
                     exp32<PP>(v_hi, sc2, nref2, pk);
                     if (nvalid < BKV) mask16(pk, 32, nvalid);
                     ptx::tmem_st_32x16(tS + buf * BKV + 16, pk);
                 }
                 if (j + 1 < T) {                                       // request the next tile's first half before draining
-                    ptx::mbar_wait(&s_full[buf ^ 1], ((g + 1) >> 1) & 1);
+                    if (mode == MODE_MAXPASS || !next_ready) ptx::mbar_wait(&s_full[buf ^ 1], ((g + 1) >> 1) & 1);
                     ptx::tc_fence_after();
                     ptx::tmem_ld_32x32(tS + (buf ^ 1) * BKV, v_lo);
                 }
@@ -266,58 +312,50 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 ptx::mbar_arrive(&p_full[buf]);
             }
             g0 += T;
-            ptx::mbar_wait(done, pass & 1);
+            ptx::mbar_wait(done, it & 1);
             ptx::tc_fence_after();
-            bool repeat;
-            if (mode == MODE_MAXPASS) {
-                const float m = rmax * LOG2E;
-                nref2 = ptx::pack2(-m, -m);
-                mode = MODE_EXACT;
-                repeat = true;
-            } else {
-                uint32_t lv[8];
-                ptx::tmem_ld_32x8(tL, lv);
-                ptx::tmem_ld_wait();
-                l = __uint_as_float(lv[0]);
-                repeat = false;
-                if (mode == MODE_FAST) {   // a non-finite row sum anywhere in the CTA: redo with the exact maximum
-                    const bool bad = !(l < 3.0e38f);
-                    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(overflow, 1);
-                    ptx::named_bar_sync(1, 128);
-                    repeat = *reinterpret_cast<volatile int*>(overflow) != 0;
-                    if (repeat) mode = MODE_MAXPASS;
-                }
-            }
-            if (repeat) ptx::tc_fence_before();   // TMEM reads above are complete before the next pass's MMAs overwrite
-            if (threadIdx.x == 0) {
-                *again = repeat ? 1 : 0;
-                __threadfence_block();
-            }
-            if (repeat) ptx::named_bar_sync(1, 128);   // every softmax thread has read L before the verdict releases the MMAs
-            if (threadIdx.x == 0) ptx::mbar_arrive(verdict);
-            if (!repeat) break;
-        }
-        // final: O / l -> bf16 -> global (each thread owns one 128-byte row segment)
-        const int row = q0 + warp * 32 + lane;
-        const float inv = 1.0f / l;
-        bf16* dst = out + (static_cast<long long>(b) * N + row) * D + h * HD;
-#pragma unroll 1
-        for (int c = 0; c < HD / 32; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld_32x32(tO + c * 32, o);
+            ++it;
+            if (mode == MODE_MAXPASS) return;
+            uint32_t lv[8];
+            ptx::tmem_ld_32x8(tL, lv);
             ptx::tmem_ld_wait();
-            if (row < N) {
+            const float l = __uint_as_float(lv[0]);
+            if (mode == MODE_FAST) {   // a non-finite row sum: the whole item goes on the redo list (rare)
+                const bool bad = !(l < 3.0e38f);
+                if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&redo[idx >> 5], 1u << (idx & 31));
+            }
+            // O / l -> bf16 -> global (each thread owns one 128-byte row segment); a redone item overwrites this later
+            const int row = qt * BQ + warp * 32 + lane;
+            const float inv = 1.0f / l;
+            bf16* dst = out + (static_cast<long long>(b) * N + row) * D + h * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD / 32; ++c) {
+                uint32_t o[32];
+                ptx::tmem_ld_32x32(tO + c * 32, o);
+                ptx::tmem_ld_wait();
+                if (row < N) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 w;
-                    w.x = ptx::cvt_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
-                    w.y = ptx::cvt_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-                    w.z = ptx::cvt_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-                    w.w = ptx::cvt_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(dst + c * 32 + i) = w;
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 wv;
+                        wv.x = ptx::cvt_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+                        wv.y = ptx::cvt_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                        wv.z = ptx::cvt_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                        wv.w = ptx::cvt_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + i) = wv;
+                    }
                 }
             }
-        }
+            ptx::tc_fence_before();   // O / L reads are complete before this thread's next p_full arrive releases P V
+        };
+
+        for (int i = 0; i < n_mine; ++i) softmax_item(blockIdx.x + i * G, i, MODE_FAST);
+        ptx::named_bar_sync(1, 128);          // every softmax thread has published its redo bits
+        if (threadIdx.x == 0) ptx::mbar_arrive(main_done);
+        for (int i = 0; i < n_mine; ++i)
+            if (redo_bit(i)) {
+                softmax_item(blockIdx.x + i * G, i, MODE_MAXPASS);
+                softmax_item(blockIdx.x + i * G, i, MODE_EXACT);
+            }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -330,20 +368,26 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 template <int PP>
 int launch5(const CUtensorMap* tm, bf16* out, int B, int N, int heads, cudaStream_t st) {
     static bool configured = false;
+    static int sms = 0;
     if (!configured) {
         DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        int dev = 0;
+        DAD_CHECK_CUDA(cudaGetDevice(&dev));
+        DAD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
-    const dim3 grid(cdiv(N, BQ), heads, B);
-    DAD_CHECK_CUDA(launch_pdl(attention_tc5_kernel<PP>, grid, dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N,
-                              heads * HD));
+    const long long total = static_cast<long long>(B) * heads * cdiv(N, BQ);
+    const int grid = static_cast<int>(total < 2LL * sms ? total : 2LL * sms);
+    DAD_REQUIRE(cdiv(total, grid) <= MAX_ITEMS_PER_CTA, "attention: %lld work items exceed the per-CTA redo bitmap", total);
+    DAD_CHECK_CUDA(launch_pdl(attention_tc5_kernel<PP>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N,
+                              heads * HD, heads, static_cast<int>(total)));
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }
 
 }  // namespace
 
-// qkv [B*N, 3*D] bf16 (q pre-scaled) -> out [B*N, D] bf16.  poly_pairs = pairs of every 8 on the FMA pipe (0..5).
+// qkv [B*N, 3*D] bf16 (q pre-scaled) -> out [B*N, D] bf16.  poly_pairs = pairs of every 8 on the FMA pipe (0, 2..5).
 int attention_tc5(const bf16* qkv, bf16* out, int B, int N, int heads, int poly_pairs, cudaStream_t st) {
     const int D = heads * HD;
     CUtensorMap tm[3];
@@ -355,10 +399,10 @@ int attention_tc5(const bf16* qkv, bf16* out, int B, int N, int heads, int poly_
     }
     switch (poly_pairs) {
         case 0: return launch5<0>(tm, out, B, N, heads, st);
-        case 2: return launch5<2>(tm, out, B, N, heads, st);
         case 3: return launch5<3>(tm, out, B, N, heads, st);
+        case 4: return launch5<4>(tm, out, B, N, heads, st);
         case 5: return launch5<5>(tm, out, B, N, heads, st);
-        default: return launch5<4>(tm, out, B, N, heads, st);
+        default: return launch5<2>(tm, out, B, N, heads, st);
     }
 }
 

@@ -124,7 +124,45 @@ __global__ void __launch_bounds__(256) mm_apply_kernel(const float* x, float* ou
         out[b * L + i] = (x[b * L + i] - mn) / range;
 }
 
+// colorize_depth_maps (distillanydepth/utils/image_util.py:69-118): x = clip((d - min) / (max - min), 0, 1) in fp32 (or
+// d * 0 when min == max), matplotlib's Colormap.__call__ index  min(int(x * 256), 255)  into the 256-entry LUT, masked
+// pixels set to 0.  Writes the float CHW image and / or the uint8 HWC image of tools/testers/infer.py:139-140
+// ((rgb * 255).astype(uint8), chw2hwc) in the same pass.
+__global__ void __launch_bounds__(256) colorize_kernel(const float* __restrict__ d, const uint8_t* __restrict__ valid, long long HW,
+                                                       float dmin, float dmax, int degenerate, const float* __restrict__ lut,
+                                                       float* __restrict__ out_chw, uint8_t* __restrict__ out_hwc) {
+    __shared__ float slut[768];
+    for (int i = threadIdx.x; i < 768; i += 256) slut[i] = lut[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const float range = dmax - dmin;
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < HW; i += static_cast<long long>(gridDim.x) * 256) {
+        const float v = d[b * HW + i];
+        float x = degenerate ? v * 0.f : fminf(fmaxf(__fdiv_rn(v - dmin, range), 0.f), 1.f);
+        int idx = static_cast<int>(x * 256.f);          // numpy: float32 * 256 -> astype(int) truncates
+        idx = idx < 0 ? 0 : (idx > 255 ? 255 : idx);    // x == 1 -> N - 1; NaN -> matplotlib's "bad" colour is out of scope
+        const bool ok = valid == nullptr || valid[b * HW + i] != 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float col = ok ? slut[idx * 3 + c] : 0.f;
+            if (out_chw) out_chw[(b * 3 + c) * HW + i] = col;
+            if (out_hwc) out_hwc[(b * HW + i) * 3 + c] = static_cast<uint8_t>(col * 255.f);
+        }
+    }
+}
+
 }  // namespace
+
+int colorize_depth(const float* depth, const uint8_t* valid, int B, long long HW, float dmin, float dmax, int degenerate,
+                   const float* lut, float* out_chw, uint8_t* out_hwc, cudaStream_t st) {
+    DAD_REQUIRE(depth && lut && (out_chw || out_hwc) && B > 0 && HW > 0 && B <= 65535, "colorize_depth: bad arguments");
+    const long long blocks = cdivl(HW, 256 * 4);
+    const int gx = static_cast<int>(blocks < 1 ? 1 : (blocks > 1184 ? 1184 : blocks));
+    ProfScope prof(PROF_ELEM, B * static_cast<double>(HW) * (4.0 + (out_chw ? 12.0 : 0.0) + (out_hwc ? 3.0 : 0.0)), st);
+    colorize_kernel<<<dim3(gx, B), 256, 0, st>>>(depth, valid, HW, dmin, dmax, degenerate, lut, out_chw, out_hwc);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
 
 int preprocess_image(const uint8_t* src, int h, int w, long long pitch, int swap_rb, int nh, int nw, const double* mean,
                      const double* stdv, float* dst, cudaStream_t st) {

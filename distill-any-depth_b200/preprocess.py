@@ -118,3 +118,73 @@ def normalize_minmax(depth):
         _lib.check(_lib.load().dad_minmax_normalize(_lib.ptr(d), B, L, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
                                                     _lib.stream_ptr()), "normalize_minmax")
     return out
+
+
+# ------------------------------------------------------------------------------------------ colourise (8f N2)
+# matplotlib's "Spectral" colormap data (matplotlib/_cm.py `_Spectral_data`: the 11-class ColorBrewer Spectral scheme,
+# RGB / 255) restated here because matplotlib is not a dependency of this package.
+_SPECTRAL = ((158, 1, 66), (213, 62, 79), (244, 109, 67), (253, 174, 97), (254, 224, 139), (255, 255, 191),
+             (230, 245, 152), (171, 221, 164), (102, 194, 165), (50, 136, 189), (94, 79, 162))
+_lut_cache = {}
+
+
+def colormap_lut(cmap="Spectral", N=256):
+    """256 x 3 float64 lookup table of a ``LinearSegmentedColormap.from_list`` colormap, computed as matplotlib's
+    ``colors._create_lookup_table`` does (nodes at ``linspace(0, 1, len(colors))``, linear interpolation in float64,
+    clip to [0, 1]); ``name_r`` reverses the node order (``Colormap.reversed``)."""
+    name, rev = (cmap[:-2], True) if cmap.endswith("_r") else (cmap, False)
+    if name != "Spectral":
+        raise NotImplementedError(f"colormap {cmap!r}: only Spectral / Spectral_r (the reference's choice, "
+                                  "tools/testers/infer.py:137) are built in")
+    cols = np.asarray(_SPECTRAL, dtype=np.float64) / 255.0
+    if rev:
+        cols = cols[::-1]
+    x = np.linspace(0.0, 1.0, len(cols)) * (N - 1)
+    xind = (N - 1) * np.linspace(0.0, 1.0, N)
+    ind = np.searchsorted(x, xind)[1:-1]
+    dist = (xind[1:-1] - x[ind - 1]) / (x[ind] - x[ind - 1])
+    lut = np.empty((N, 3), dtype=np.float64)
+    for c in range(3):
+        y = cols[:, c]
+        lut[:, c] = np.concatenate([[y[0]], dist * (y[ind] - y[ind - 1]) + y[ind - 1], [y[-1]]])
+    return np.clip(lut, 0.0, 1.0)
+
+
+def _device_lut(cmap, device):
+    key = (cmap, str(device))
+    t = _lut_cache.get(key)
+    if t is None:
+        t = torch.from_numpy(colormap_lut(cmap).astype(np.float32)).to(device).contiguous()
+        _lut_cache[key] = t
+    return t
+
+
+def colorize_depth_maps(depth_map, min_depth=None, max_depth=None, cmap="Spectral", valid_mask=None, as_uint8_hwc=False):
+    """``colorize_depth_maps`` (distillanydepth/utils/image_util.py:69-118) on the device: ``[(B,) H, W]`` (any singleton
+    dims squeezed, as upstream) -> float ``[B, 3, H, W]`` in [0, 1]; ``min_depth == max_depth`` (including both ``None``)
+    colours everything with the first LUT entry, as upstream's ``depth * 0``.  With ``as_uint8_hwc`` the same pass also
+    returns ``(rgb * 255).astype(uint8)`` as ``[B, H, W, 3]`` (tools/testers/infer.py:139-140).  The result stays on the
+    GPU (upstream returns a CPU tensor)."""
+    if not isinstance(depth_map, torch.Tensor) or not depth_map.is_cuda:
+        raise RuntimeError("colorize_depth_maps: CUDA tensors only (no CPU fallback)")
+    assert depth_map.dim() >= 2, "Invalid dimension"
+    d = depth_map.detach().squeeze().float().contiguous()
+    if d.dim() < 3:
+        d = d[None]
+    if d.dim() != 3:
+        raise ValueError("colorize_depth_maps expects [(B,) H, W] after squeezing")
+    B, H, W = d.shape
+    valid = None
+    if valid_mask is not None:
+        valid = valid_mask.detach().to(d.device).squeeze()
+        valid = (valid[None] if valid.dim() < 3 else valid).expand(B, H, W)
+        valid = (valid != 0).contiguous().view(torch.uint8)
+    degenerate = 1 if min_depth == max_depth else 0
+    lo, hi = (0.0, 0.0) if degenerate else (float(min_depth), float(max_depth))
+    lut = _device_lut(cmap, d.device)
+    out = torch.empty(B, 3, H, W, dtype=torch.float32, device=d.device)
+    out8 = torch.empty(B, H, W, 3, dtype=torch.uint8, device=d.device) if as_uint8_hwc else None
+    with torch.cuda.device(d.device):
+        _lib.check(_lib.load().dad_colorize_depth(_lib.ptr(d), _lib.ptr(valid), B, H * W, lo, hi, degenerate, _lib.ptr(lut),
+                                                  _lib.ptr(out), _lib.ptr(out8), _lib.stream_ptr()), "colorize_depth_maps")
+    return (out, out8) if as_uint8_hwc else out

@@ -172,6 +172,13 @@ int dad_resize_depth(const float* in, int B, int H, int W, int h, int w, float* 
 /* per image (d - min) / (max - min) (tools/testers/infer.py:135); workspace: 8 bytes per image. */
 int dad_minmax_normalize(const float* in, int B, int64_t L, float* out, void* workspace, size_t workspace_bytes,
                          void* stream);
+/* colorize_depth_maps (distillanydepth/utils/image_util.py:69-118) + the uint8 HWC conversion of
+ * tools/testers/infer.py:137-140: depth [B, HW] fp32 -> x = clip((d - dmin) / (dmax - dmin), 0, 1) (d * 0 when
+ * `degenerate`, i.e. dmin == dmax) -> lut[min(int(x * 256), 255)] (matplotlib's Colormap.__call__; `lut` = device
+ * pointer to 256 x 3 fp32) -> pixels with valid == 0 set to 0 (valid may be NULL) -> out_chw [B,3,HW] fp32 and / or
+ * out_hwc [B,HW,3] uint8 = (rgb * 255) truncated; either output may be NULL. */
+int dad_colorize_depth(const float* depth, const uint8_t* valid, int B, int64_t HW, float dmin, float dmax, int degenerate,
+                       const float* lut, float* out_chw, uint8_t* out_hwc, void* stream);
 
 /* ------------------------------------------------------------------ kernel-level test entry points
  * out[M,N] (fp32) = A[M,K] (bf16 bits / fp32) * W[N,K]^T through the tcgen05 (mode 0) or FFMA (mode 1)

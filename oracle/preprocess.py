@@ -56,3 +56,30 @@ def normalize_minmax(depth):
     mn, mx = flat.min(1).values, flat.max(1).values
     shp = (-1,) + (1,) * (depth.dim() - 1)
     return (depth - mn.reshape(shp)) / (mx - mn).reshape(shp)
+
+
+def colorize_depth_maps(depth_map, min_depth=None, max_depth=None, lut=None, valid_mask=None):
+    """Restatement of ``colorize_depth_maps`` (distillanydepth/utils/image_util.py:69-118) with matplotlib's
+    ``Colormap.__call__`` spelled out (matplotlib is not installed in this image: PARITY UNPINNED for the colormap table
+    itself - ``lut`` is the 256 x 3 float64 table of ``distill_any_depth_b200.preprocess.colormap_lut``, which restates
+    matplotlib's ``_create_lookup_table`` on the published ColorBrewer Spectral data).  numpy in, ``[B, 3, H, W]`` float64
+    out; ``xa = depth * N; xa[xa == N] = N - 1; astype(int)`` as in matplotlib/colors.py."""
+    depth = np.array(depth_map, copy=True).squeeze()
+    if depth.ndim < 3:
+        depth = depth[np.newaxis, :, :]
+    if min_depth != max_depth:
+        depth = ((depth - min_depth) / (max_depth - min_depth)).clip(0, 1)
+    else:
+        depth = depth * 0.
+    N = lut.shape[0]
+    xa = np.array(depth, copy=True)
+    xa *= N
+    xa[xa == N] = N - 1
+    idx = np.clip(xa, 0, N - 1).astype(int)
+    img = np.rollaxis(lut[idx], 3, 1).copy()
+    if valid_mask is not None:
+        vm = np.asarray(valid_mask).squeeze()
+        vm = vm[np.newaxis, np.newaxis] if vm.ndim < 3 else vm[:, np.newaxis]
+        vm = np.repeat(np.broadcast_to(vm, (img.shape[0], 1) + img.shape[2:]), 3, axis=1)
+        img[~vm] = 0
+    return img

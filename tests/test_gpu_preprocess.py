@@ -81,3 +81,31 @@ def test_infer_image_end_to_end():
     assert got.shape == (120, 200) and got.dtype == np.float32
     den = np.maximum(np.abs(ref), 0.1 * np.abs(ref).max())
     assert (np.abs(got - ref) / den).max() <= 1e-4
+
+
+@pytest.mark.parametrize("cmap", ["Spectral", "Spectral_r"])
+def test_colorize_depth_maps_matches_oracle(cmap):
+    """colorize_depth_maps (utils/image_util.py:69-118) + the uint8 HWC image of tools/testers/infer.py:137-140: the LUT
+    index is integer work - bit-exact against the numpy restatement, including x == 0, x == 1, bin edges k / 256, values
+    outside [min, max], a validity mask and the degenerate min == max branch."""
+    from distill_any_depth_b200 import preprocess
+    lut = preprocess.colormap_lut(cmap)
+    rng = np.random.Generator(np.random.PCG64(3))
+    d = rng.random((2, 61, 45), dtype=np.float32)
+    d[0, 0, :8] = [0.0, 1.0, 0.5, 0.25, 255.0 / 256.0, 1.0 / 256.0, -0.3, 1.7]
+    d[1, 3, :4] = np.nextafter(np.float32([0.5, 0.25, 0.75, 1.0]), np.float32(0))
+    mask = rng.random((2, 61, 45)) > 0.2
+    dt, mt = torch.from_numpy(d).cuda(), torch.from_numpy(mask).cuda()
+    for lo, hi, vm, vmt in ((0.0, 1.0, None, None), (0.1, 0.8, mask, mt), (None, None, None, None), (0.3, 0.3, mask, mt)):
+        got, got8 = preprocess.colorize_depth_maps(dt[:, None], lo, hi, cmap=cmap, valid_mask=vmt, as_uint8_hwc=True)
+        ref = P.colorize_depth_maps(d[:, None], lo, hi, lut=lut, valid_mask=vm)
+        assert tuple(got.shape) == ref.shape == (2, 3, 61, 45)
+        assert np.array_equal(got.cpu().numpy(), ref.astype(np.float32)), (lo, hi)
+        ref8 = (ref * 255).astype(np.uint8).transpose(0, 2, 3, 1)
+        # the uint8 image truncates lut * 255: the device multiplies the fp32 table entry, numpy the float64 one - equal
+        # unless a product sits within 1e-5 of an integer (never the case for this table; asserted here)
+        assert np.array_equal(got8.cpu().numpy(), ref8), (lo, hi)
+    single = preprocess.colorize_depth_maps(dt[0], 0.0, 1.0, cmap=cmap)   # [H, W] input -> [1, 3, H, W]
+    assert tuple(single.shape) == (1, 3, 61, 45)
+    with pytest.raises(NotImplementedError):
+        preprocess.colorize_depth_maps(dt, 0.0, 1.0, cmap="magma")

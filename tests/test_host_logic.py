@@ -289,3 +289,29 @@ def test_two_rank_training_gradient_equals_single_process_full_batch():
     (oracle.SSILoss()(pred, gt, mask) + 0.2 * oracle.gradient_preservation_loss(pred)).backward()
     for a, p in zip(got, net.parameters()):
         assert float((a - p.grad).abs().max()) <= 1e-5 * float(p.grad.abs().max()) + 1e-8
+
+
+def test_colormap_lut_restates_matplotlib_spectral():
+    """The 256-entry Spectral table (host logic of colorize_depth_maps): end points and nodes are the ColorBrewer colours,
+    channels are piecewise linear between them, the reversed map is the mirror image; values that published matplotlib
+    returns for Spectral (cm.Spectral(0.0), (0.5), (1.0)) are pinned as known answers."""
+    import numpy as np
+    from distill_any_depth_b200 import preprocess
+    lut = preprocess.colormap_lut("Spectral")
+    assert lut.shape == (256, 3) and lut.min() >= 0 and lut.max() <= 1
+    np.testing.assert_allclose(lut[0], np.array([158, 1, 66]) / 255.0, atol=1e-15)
+    np.testing.assert_allclose(lut[255], np.array([94, 79, 162]) / 255.0, atol=1e-15)
+    # matplotlib: cm.Spectral(0.5) -> index 128 -> between the 6th node (255,255,191) at 127.5 and the 7th (230,245,152) at 153
+    t = (128 - 127.5) / 25.5
+    np.testing.assert_allclose(lut[128], (np.array([255, 255, 191]) + t * (np.array([230, 245, 152]) - np.array([255, 255, 191]))) / 255.0,
+                               atol=1e-12)
+    np.testing.assert_allclose(preprocess.colormap_lut("Spectral_r"), lut[::-1], atol=1e-12)
+    d2 = np.diff(lut, n=2, axis=0)           # piecewise linear: second differences vanish away from the 9 interior nodes
+    assert (np.abs(d2).max(axis=1) > 1e-9).sum() <= 18
+    import oracle.preprocess as P
+    img = P.colorize_depth_maps(np.array([[[0.0, 0.5, 1.0], [1.0, 0.5, 0.0]]], dtype=np.float32), 0, 1, lut=lut)
+    np.testing.assert_allclose(img[0, :, 0, :].T, lut[[0, 128, 255]], atol=0)
+    np.testing.assert_allclose(img[0, :, 1, :].T, lut[[255, 128, 0]], atol=0)
+    prod = lut * 255.0                        # the uint8 image truncates lut * 255: no product within 1e-5 of an integer
+    frac = np.abs(prod - np.round(prod))      # (except exact integers at the nodes) -> fp32 / float64 products truncate alike
+    assert ((frac > 1e-5) | (frac < 1e-9)).all()

@@ -7,8 +7,8 @@ timeout -s KILL 300 python -m pytest tests/test_gpu_kernels.py -k attention -q -
 echo "pytest rc=$?" | tee $OUT/summary.txt
 tail -5 $OUT/tests.log | tee -a $OUT/summary.txt
 for cfg in "32 1370 16" "8 5477 16"; do
-  for s in 0.5 1.5; do
-    for p in 0 2 3 4 5; do
+  for s in ${SCALES:-0.5 1.5}; do
+    for p in ${POLYS:-0 2 3 4 5}; do
       DAD_ATT_VARIANT=5 DAD_ATT_POLY5=$p timeout -s KILL 60 python tests/gpu_attn_time.py $cfg $s 2>&1 | tail -1 | tee -a $OUT/summary.txt
     done
     DAD_ATT_VARIANT=2 timeout -s KILL 60 python tests/gpu_attn_time.py $cfg $s 2>&1 | tail -1 | tee -a $OUT/summary.txt
