@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--graph", type=int, default=1, choices=[0, 1],
                     help="1 (default): capture one step (forward + losses [+ all-reduce]) in a CUDA graph after warm-up and "
                          "replay it in the timed loops; 0: launch every kernel from the host each step")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "train", "train4"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "train", "train4", "infer"],
                     help="c3 (default, the metric's config): ViT-L 518^2 B=32 bf16 fwd + SSI + HDN-DR; the others are "
                          "BASELINE.json's remaining GPU configs, for DESIGN.md's table (not bench lines): c2 ViT-B 392^2 "
                          "B=16 + SSI/grad; c4 distillation step teacher ViT-L + student ViT-B 392^2 B=16/GPU, 5 losses; "
@@ -323,6 +323,64 @@ def run_train(a):
                           loss=float(loss), gpu_launches=int(launches), kernel_breakdown=breakdown)))
 
 
+# ---------------------------------------------------------------------------------- infer_image throughput (not a bench line)
+def run_infer(a):
+    """SURVEY 8f N2 / VERDICT r1 weak 10: the inference path a user calls - ``model.infer_image(raw_bgr_uint8)``
+    (depth_anything_v2/dpt.py:227-235): uint8 image H2D -> /255, INTER_CUBIC resize, normalise (one kernel) -> forward ->
+    bilinear resize back to the raw resolution -> depth map D2H.  One image per call, as upstream; plus the colourised
+    uint8 visualisation (tools/testers/infer.py:134-140) as a second timed variant."""
+    import numpy as np
+    import torch
+    import distill_any_depth_b200 as d
+    from distill_any_depth_b200 import synthetic, _lib, preprocess
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    kw = synthetic.MODEL_PRESETS[a.encoder]
+    model = d.DepthAnythingV2(**kw)
+    model.load_state_dict(synthetic.make_state_dict(seed=1, **kw), strict=True)
+    model = model.to(dev).eval()
+    model.precision = a.precision
+    torch.set_grad_enabled(False)
+    rng = np.random.Generator(np.random.PCG64(5))
+    h, w = 480, 640
+    raws = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(4)]
+
+    def plain(i):
+        return model.infer_image(raws[i & 3], a.size)
+
+    def coloured(i):
+        image, (hh, ww) = model.image2tensor(raws[i & 3], a.size)
+        depth, _ = model(image)
+        depth = preprocess.resize_depth(depth, (hh, ww))
+        norm = preprocess.normalize_minmax(depth)
+        _, rgb8 = preprocess.colorize_depth_maps(norm, 0.0, 1.0, cmap="Spectral_r", as_uint8_hwc=True)
+        return rgb8[0].cpu().numpy()
+
+    out = {}
+    n = max(a.steps, 8) * 4
+    for name, fn in (("infer_image", plain), ("infer_image_colourised", coloured)):
+        for i in range(max(a.warmup, 3)):
+            fn(i)
+        torch.cuda.synchronize()
+        l0 = lib.dad_launch_count()
+        t0 = time.perf_counter()
+        for i in range(n):
+            res = fn(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[name] = dict(value=n / dt, unit="images/s", ms_per_image=dt / n * 1e3, launches_per_image=(lib.dad_launch_count() - l0) / n,
+                         out_shape=list(res.shape), out_dtype=str(res.dtype))
+    nw, nh = preprocess.get_size(w, h, a.size, a.size)
+    print(json.dumps(dict(metric="images/sec through DepthAnythingV2.infer_image (one image per call, host uint8 in, host map out)",
+                          value=out["infer_image"]["value"], unit="images/s", n_gpus=1, steps=n, warmup=max(a.warmup, 3),
+                          ms_per_step=out["infer_image"]["ms_per_image"], higher_is_better=True, dtype=a.precision, data="synthetic",
+                          config=dict(workload=f"infer_image: {h}x{w} BGR uint8 -> {a.encoder} at {nh}x{nw} {a.precision} -> {h}x{w} fp32 "
+                                               f"depth (SURVEY 8f N2; not the headline metric)"),
+                          e2e=dict(value=out["infer_image"]["value"], unit="images/s", h2d_bytes_per_step=h * w * 3,
+                                   d2h_bytes_per_step=h * w * 4),
+                          variants=out)))
+
+
 # ---------------------------------------------------------------------------------- B200 arm
 def run_b200(a):
     import ctypes
@@ -338,6 +396,8 @@ def run_b200(a):
     assert torch.cuda.is_available(), "bench.py (impl b200) needs a GPU; there is no CPU fallback"
     if a.workload in ("train", "train4"):
         return run_train(a)
+    if a.workload == "infer":
+        return run_infer(a)
     torch.set_grad_enabled(False)   # inference benchmark: never take the differentiable (activation-tape) forward
     # stdout must carry exactly ONE JSON line: NCCL prints its version banner to the process's stdout (fd 1), so fd 1 is
     # pointed at stderr for the rest of the run and the JSON line is written to a saved duplicate of the real stdout
@@ -541,13 +601,22 @@ def run_b200(a):
             rec.update(bound="hbm", achieved_gbs=per_s / 1e9, frac=per_s / 1e9 / pk_["hbm"])
 
     def finish_ranks():
-        # Multi-rank exit: rendezvous, then leave WITHOUT tearing NCCL / the captured graphs down.  destroy_process_group()
-        # (and interpreter finalisation with graph-captured NCCL kernels alive) was observed to hang on a 2-GPU box after the
-        # JSON line had been printed; every rank has finished its work at the barrier, so a hard exit with code 0 is safe.
+        # Multi-rank exit: rendezvous, drop the CUDA graphs (they contain this communicator's NCCL kernels), then
+        # destroy the process group.  Round 1 left through os._exit(0) because destroy_process_group() hung while the
+        # captured graphs were still alive; DAD_BENCH_CLEAN_EXIT=0 keeps that path as an escape hatch.
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
-            time.sleep(0.5)   # let the peers' last NCCL kernels drain before this rank's buffers go away
+            if os.environ.get("DAD_BENCH_CLEAN_EXIT", "1") != "0":
+                # Clean teardown: the captured graphs hold NCCL kernels of this communicator; they must be destroyed
+                # BEFORE the process group (destroying the communicator under live graph nodes is what used to hang)
+                graphs.clear()
+                import gc
+                gc.collect()
+                torch.cuda.synchronize()
+                dist.destroy_process_group()
+                return
+            time.sleep(0.5)   # legacy exit (DAD_BENCH_CLEAN_EXIT=0): leave without tearing NCCL down
             sys.stdout.flush()
             sys.stderr.flush()
             os._exit(0)

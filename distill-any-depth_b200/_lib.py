@@ -45,7 +45,7 @@ PROTOTYPES = {
     "dad_preprocess_image": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dad_resize_depth": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "dad_minmax_normalize": (_i, [_vp, _i, _i64, _vp, _vp, _sz, _vp]),
-    "dad_colorize_depth": (_i, [_vp, _vp, _i, _i64, _c.c_float, _c.c_float, _i, _vp, _vp, _vp, _vp]),
+    "dad_colorize_depth": (_i, [_vp, _vp, _i, _i64, _c.c_float, _c.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
     "dad_hdn_loss_dr": (_i, [_i, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dad_hdn_loss": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dad_grad_loss": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -139,8 +139,8 @@ int dad_resize_depth(const float* in, int B, int H, int W, int h, int w, float* 
 }
 
 int dad_colorize_depth(const float* depth, const uint8_t* valid, int B, int64_t HW, float dmin, float dmax, int degenerate,
-                       const float* lut, float* out_chw, uint8_t* out_hwc, void* stream) {
-    return dad::colorize_depth(depth, valid, B, HW, dmin, dmax, degenerate, lut, out_chw, out_hwc, ST(stream));
+                       const float* lut, const uint8_t* lut_u8, float* out_chw, uint8_t* out_hwc, void* stream) {
+    return dad::colorize_depth(depth, valid, B, HW, dmin, dmax, degenerate, lut, lut_u8, out_chw, out_hwc, ST(stream));
 }
 
 int dad_minmax_normalize(const float* in, int B, int64_t L, float* out, void* ws, size_t wsb, void* stream) {

@@ -26,7 +26,7 @@ int preprocess_image(const uint8_t* src, int h, int w, long long pitch, int swap
 int resize_depth(const float* in, int B, int Hi, int Wi, int Ho, int Wo, float* out, cudaStream_t st);
 int minmax_normalize(const float* in, int B, long long L, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 int colorize_depth(const float* depth, const uint8_t* valid, int B, long long HW, float dmin, float dmax, int degenerate,
-                   const float* lut, float* out_chw, uint8_t* out_hwc, cudaStream_t st);
+                   const float* lut, const uint8_t* lut_u8, float* out_chw, uint8_t* out_hwc, cudaStream_t st);
 int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st);  // tcgen05 / TMEM
 int attention_tc3(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st); // 4 CTAs / SM variant
 // round-2 default: FFMA2 + MUFU / FMA-pipe exponentials, tensor-core row sums, in-kernel exact fallback (attention_tc5.cu)

@@ -130,9 +130,11 @@ __global__ void __launch_bounds__(256) mm_apply_kernel(const float* x, float* ou
 // ((rgb * 255).astype(uint8), chw2hwc) in the same pass.
 __global__ void __launch_bounds__(256) colorize_kernel(const float* __restrict__ d, const uint8_t* __restrict__ valid, long long HW,
                                                        float dmin, float dmax, int degenerate, const float* __restrict__ lut,
-                                                       float* __restrict__ out_chw, uint8_t* __restrict__ out_hwc) {
+                                                       const uint8_t* __restrict__ lut_u8, float* __restrict__ out_chw,
+                                                       uint8_t* __restrict__ out_hwc) {
     __shared__ float slut[768];
-    for (int i = threadIdx.x; i < 768; i += 256) slut[i] = lut[i];
+    __shared__ uint8_t slut8[768];   // (float64 table * 255) truncated on the host: numpy's float64 product, bit for bit
+    for (int i = threadIdx.x; i < 768; i += 256) { slut[i] = lut[i]; slut8[i] = lut_u8 ? lut_u8[i] : 0; }
     __syncthreads();
     const int b = blockIdx.y;
     const float range = dmax - dmin;
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(256) colorize_kernel(const float* __restrict__
         for (int c = 0; c < 3; ++c) {
             const float col = ok ? slut[idx * 3 + c] : 0.f;
             if (out_chw) out_chw[(b * 3 + c) * HW + i] = col;
-            if (out_hwc) out_hwc[(b * HW + i) * 3 + c] = static_cast<uint8_t>(col * 255.f);
+            if (out_hwc) out_hwc[(b * HW + i) * 3 + c] = ok ? slut8[idx * 3 + c] : 0;
         }
     }
 }
@@ -154,12 +156,13 @@ __global__ void __launch_bounds__(256) colorize_kernel(const float* __restrict__
 }  // namespace
 
 int colorize_depth(const float* depth, const uint8_t* valid, int B, long long HW, float dmin, float dmax, int degenerate,
-                   const float* lut, float* out_chw, uint8_t* out_hwc, cudaStream_t st) {
+                   const float* lut, const uint8_t* lut_u8, float* out_chw, uint8_t* out_hwc, cudaStream_t st) {
     DAD_REQUIRE(depth && lut && (out_chw || out_hwc) && B > 0 && HW > 0 && B <= 65535, "colorize_depth: bad arguments");
+    DAD_REQUIRE(!out_hwc || lut_u8, "colorize_depth: the uint8 output needs the uint8 table");
     const long long blocks = cdivl(HW, 256 * 4);
     const int gx = static_cast<int>(blocks < 1 ? 1 : (blocks > 1184 ? 1184 : blocks));
     ProfScope prof(PROF_ELEM, B * static_cast<double>(HW) * (4.0 + (out_chw ? 12.0 : 0.0) + (out_hwc ? 3.0 : 0.0)), st);
-    colorize_kernel<<<dim3(gx, B), 256, 0, st>>>(depth, valid, HW, dmin, dmax, degenerate, lut, out_chw, out_hwc);
+    colorize_kernel<<<dim3(gx, B), 256, 0, st>>>(depth, valid, HW, dmin, dmax, degenerate, lut, lut_u8, out_chw, out_hwc);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

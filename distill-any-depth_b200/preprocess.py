@@ -154,7 +154,9 @@ def _device_lut(cmap, device):
     key = (cmap, str(device))
     t = _lut_cache.get(key)
     if t is None:
-        t = torch.from_numpy(colormap_lut(cmap).astype(np.float32)).to(device).contiguous()
+        lut64 = colormap_lut(cmap)
+        t = (torch.from_numpy(lut64.astype(np.float32)).to(device).contiguous(),
+             torch.from_numpy((lut64 * 255).astype(np.uint8)).to(device).contiguous())   # numpy's float64 product, truncated
         _lut_cache[key] = t
     return t
 
@@ -181,10 +183,11 @@ def colorize_depth_maps(depth_map, min_depth=None, max_depth=None, cmap="Spectra
         valid = (valid != 0).contiguous().view(torch.uint8)
     degenerate = 1 if min_depth == max_depth else 0
     lo, hi = (0.0, 0.0) if degenerate else (float(min_depth), float(max_depth))
-    lut = _device_lut(cmap, d.device)
+    lut, lut8 = _device_lut(cmap, d.device)
     out = torch.empty(B, 3, H, W, dtype=torch.float32, device=d.device)
     out8 = torch.empty(B, H, W, 3, dtype=torch.uint8, device=d.device) if as_uint8_hwc else None
     with torch.cuda.device(d.device):
         _lib.check(_lib.load().dad_colorize_depth(_lib.ptr(d), _lib.ptr(valid), B, H * W, lo, hi, degenerate, _lib.ptr(lut),
-                                                  _lib.ptr(out), _lib.ptr(out8), _lib.stream_ptr()), "colorize_depth_maps")
+                                                  _lib.ptr(lut8), _lib.ptr(out), _lib.ptr(out8), _lib.stream_ptr()),
+                   "colorize_depth_maps")
     return (out, out8) if as_uint8_hwc else out

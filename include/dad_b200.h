@@ -176,9 +176,10 @@ int dad_minmax_normalize(const float* in, int B, int64_t L, float* out, void* wo
  * tools/testers/infer.py:137-140: depth [B, HW] fp32 -> x = clip((d - dmin) / (dmax - dmin), 0, 1) (d * 0 when
  * `degenerate`, i.e. dmin == dmax) -> lut[min(int(x * 256), 255)] (matplotlib's Colormap.__call__; `lut` = device
  * pointer to 256 x 3 fp32) -> pixels with valid == 0 set to 0 (valid may be NULL) -> out_chw [B,3,HW] fp32 and / or
- * out_hwc [B,HW,3] uint8 = (rgb * 255) truncated; either output may be NULL. */
+ * out_hwc [B,HW,3] uint8 = lut_u8[index] where lut_u8 (256 x 3 bytes, device) holds (float64 table * 255) truncated, i.e.
+ * numpy's `(rgb * 255).astype(np.uint8)` bit for bit; either output may be NULL (lut_u8 may be NULL without out_hwc). */
 int dad_colorize_depth(const float* depth, const uint8_t* valid, int B, int64_t HW, float dmin, float dmax, int degenerate,
-                       const float* lut, float* out_chw, uint8_t* out_hwc, void* stream);
+                       const float* lut, const uint8_t* lut_u8, float* out_chw, uint8_t* out_hwc, void* stream);
 
 /* ------------------------------------------------------------------ kernel-level test entry points
  * out[M,N] (fp32) = A[M,K] (bf16 bits / fp32) * W[N,K]^T through the tcgen05 (mode 0) or FFMA (mode 1)

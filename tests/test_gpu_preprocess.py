@@ -102,8 +102,7 @@ def test_colorize_depth_maps_matches_oracle(cmap):
         assert tuple(got.shape) == ref.shape == (2, 3, 61, 45)
         assert np.array_equal(got.cpu().numpy(), ref.astype(np.float32)), (lo, hi)
         ref8 = (ref * 255).astype(np.uint8).transpose(0, 2, 3, 1)
-        # the uint8 image truncates lut * 255: the device multiplies the fp32 table entry, numpy the float64 one - equal
-        # unless a product sits within 1e-5 of an integer (never the case for this table; asserted here)
+        # the uint8 image is numpy's float64 product truncated (a host-computed uint8 table indexed on the device)
         assert np.array_equal(got8.cpu().numpy(), ref8), (lo, hi)
     single = preprocess.colorize_depth_maps(dt[0], 0.0, 1.0, cmap=cmap)   # [H, W] input -> [1, 3, H, W]
     assert tuple(single.shape) == (1, 3, 61, 45)

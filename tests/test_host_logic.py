@@ -312,6 +312,6 @@ def test_colormap_lut_restates_matplotlib_spectral():
     img = P.colorize_depth_maps(np.array([[[0.0, 0.5, 1.0], [1.0, 0.5, 0.0]]], dtype=np.float32), 0, 1, lut=lut)
     np.testing.assert_allclose(img[0, :, 0, :].T, lut[[0, 128, 255]], atol=0)
     np.testing.assert_allclose(img[0, :, 1, :].T, lut[[255, 128, 0]], atol=0)
-    prod = lut * 255.0                        # the uint8 image truncates lut * 255: no product within 1e-5 of an integer
-    frac = np.abs(prod - np.round(prod))      # (except exact integers at the nodes) -> fp32 / float64 products truncate alike
-    assert ((frac > 1e-5) | (frac < 1e-9)).all()
+    # the uint8 image truncates the FLOAT64 product lut * 255 (254 / 255 * 255 = 253.99999999999997 -> 253): the device
+    # therefore indexes a uint8 table computed here in float64, never its own fp32 product
+    assert (lut[255] * 255).astype(np.uint8).tolist() == [94, 79, 162]
