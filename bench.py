@@ -388,7 +388,8 @@ def run_b200(a):
     import torch.distributed as dist
     import distill_any_depth_b200 as d
     from distill_any_depth_b200 import synthetic, _lib, losses
-    from distill_any_depth_b200.dist import finish_losses
+    from distill_any_depth_b200.dist import stack_partials, finish_stacked
+    from distill_any_depth_b200.step import distillation_step_partials, combine_step_losses
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -435,32 +436,46 @@ def run_b200(a):
         teacher = teacher.to(dev).eval()
         teacher.precision = a.precision
 
-    def step_c4(x):
-        out = d.distillation_step_losses(model, teacher, x, x)
-        return torch.stack([out["batch_loss"], out["hdn_loss"]])
+    # A step is split in two halves.  compute(x): the forwards and the loss kernels, returning either the finished loss
+    # scalars (1 GPU) or the stacked per-rank (numerator, denominator) partials (N > 1) - pure device work, capturable in a
+    # CUDA graph.  finish(out): on N > 1 the ONE all-reduce of the partials plus the ratios, launched
+    # eagerly AFTER the graph replay: a captured graph that contains NCCL kernels made destroy_process_group() hang at
+    # exit (round 1 left through os._exit for that reason); with compute-only graphs the teardown is clean.
+    meta = {}
 
-    def losses_of(depth):
+    def compute(x):
+        if a.workload == "c4":
+            if world == 1:
+                out = d.distillation_step_losses(model, teacher, x, x)
+                return torch.stack([out["batch_loss"], out["hdn_loss"]])
+            names, kinds, vec = stack_partials(distillation_step_partials(model, teacher, x, x))
+            meta["names"], meta["kinds"] = names, kinds
+            return vec
+        depth, _ = model(x)
         if a.workload == "c5":   # forward only; the D2H read is one element of the depth map
             return depth.view(-1)[:2].clone()
+        first = ("ssi", losses._ssi(depth, gt, full, False, want_partials=True))
         if a.workload == "c2":
-            ssi, p1 = losses._ssi(depth, gt, full, False, want_partials=True)
-            gr, p2 = losses._grad(depth, want_partials=True)
-            if world > 1:
-                out = finish_losses({"ssi": ("ssi", p1), "grad": ("grad", p2)})
-                return torch.stack([out["ssi"], out["grad"]])
-            return torch.stack([ssi, gr])
-        ssi, p1 = losses._ssi(depth, gt, full, False, want_partials=True)
-        hdn, p2 = losses.hdn_loss_dr(depth, gt, None, 3, want_partials=True)
-        if world > 1:  # full-batch losses: ONE all-reduce of the (num, den) partials
-            out = finish_losses({"ssi": ("ssi", p1), "hdn": ("hdn", p2)})
-            return torch.stack([out["ssi"], out["hdn"]])
-        return torch.stack([ssi, hdn])
+            second = ("grad", losses._grad(depth, want_partials=True))
+        else:
+            second = ("hdn", losses.hdn_loss_dr(depth, gt, None, 3, want_partials=True))
+        if world == 1:
+            return torch.stack([first[1][0], second[1][0]])
+        names, kinds, vec = stack_partials({first[0]: (first[0], first[1][1]), second[0]: (second[0], second[1][1])})
+        meta["names"], meta["kinds"] = names, kinds
+        return vec
+
+    def finish(out):
+        if world == 1 or a.workload == "c5":
+            return out
+        fin = finish_stacked(meta["names"], meta["kinds"], out)   # all-reduce in place + ratios
+        if a.workload == "c4":
+            fin = combine_step_losses(fin)
+            return torch.stack([fin["batch_loss"], fin["hdn_loss"]])
+        return torch.stack([fin[n] for n in meta["names"]])
 
     def step_device():
-        if a.workload == "c4":
-            return step_c4(x_dev)
-        depth, _ = model(x_dev)
-        return losses_of(depth)
+        return finish(compute(x_dev))
 
     def step_e2e(i):
         buf = x_stage[i & 1]
@@ -469,10 +484,7 @@ def run_b200(a):
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         torch.cuda.current_stream().wait_event(ev)
-        if a.workload == "c4":
-            return step_c4(buf).cpu()
-        depth, _ = model(buf)
-        return losses_of(depth).cpu()  # D2H read of the step's result
+        return finish(compute(buf)).cpu()  # D2H read of the step's result
 
     def barrier():
         if world > 1:
@@ -504,7 +516,8 @@ def run_b200(a):
 
     # ---- CUDA graphs: one step is ~240 dependent launches; replaying a captured graph removes the per-launch host
     # and front-end cost.  The same kernels run with the same arguments (tensor maps are baked into the nodes; the
-    # workspace, inputs and outputs are static buffers).  Multi-GPU: the loss all-reduce is captured with the step.
+    # workspace, inputs and outputs are static buffers).  Multi-GPU: the graph holds the compute half only; the ONE
+    # all-reduce of the loss partials is launched eagerly after each replay (see compute / finish above).
     graphs = {}
     if a.graph:
         try:
@@ -514,11 +527,7 @@ def run_b200(a):
                 for key, xin in (("dev", x_dev), ("s0", x_stage[0]), ("s1", x_stage[1])):
                     gph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(gph, stream=cap_stream):
-                        if a.workload == "c4":
-                            out_static = step_c4(xin)
-                        else:
-                            depth_, _ = model(xin)
-                            out_static = losses_of(depth_)
+                        out_static = compute(xin)   # compute only: no collective inside the graph
                     graphs[key] = (gph, out_static)
             torch.cuda.current_stream().wait_stream(cap_stream)
             torch.cuda.synchronize()
@@ -532,7 +541,7 @@ def run_b200(a):
         def step_device():  # noqa: F811
             gph, out_static = graphs["dev"]
             gph.replay()
-            return out_static
+            return finish(out_static)
 
         def issue_copy(i):  # H2D of step i's batch from pinned host memory, on the copy stream
             with torch.cuda.stream(copy_stream):
@@ -553,7 +562,7 @@ def run_b200(a):
                 pending[i + 1] = issue_copy(i + 1)   # buffer (i + 1) & 1 was last read by step i - 1, which has completed
             gph, out_static = graphs["s%d" % (i & 1)]
             gph.replay()
-            return out_static.cpu()
+            return finish(out_static).cpu()
 
         for i in range(2):
             step_device()
@@ -574,10 +583,7 @@ def run_b200(a):
     # ---- per-kernel-class device times (separate pass so the events do not perturb the timed loops; launched
     # from the host, not replayed, because the events bracket individual launches)
     def step_host():
-        if a.workload == "c4":
-            return step_c4(x_dev)
-        depth_, _ = model(x_dev)
-        return losses_of(depth_)
+        return finish(compute(x_dev))
 
     lib.dad_profile_enable(1)
     psteps = max(1, min(a.steps, 3))
@@ -614,6 +620,13 @@ def run_b200(a):
                 import gc
                 gc.collect()
                 torch.cuda.synchronize()
+                # belt and braces: the work is done and the JSON line is out; if the teardown ever stalls, leave after 30 s
+                # (rc 0) instead of hanging the launcher, and say so on stderr
+                def _watchdog():
+                    time.sleep(30)
+                    print("bench: destroy_process_group() did not return within 30 s; exiting", file=sys.stderr, flush=True)
+                    os._exit(0)
+                threading.Thread(target=_watchdog, daemon=True).start()
                 dist.destroy_process_group()
                 return
             time.sleep(0.5)   # legacy exit (DAD_BENCH_CLEAN_EXIT=0): leave without tearing NCCL down
@@ -656,7 +669,7 @@ def run_b200(a):
                 vs_baseline=None,
                 dtype=a.precision, data="synthetic",
                 config=dict(workload=workload_name(a), global_batch=B * world, per_gpu_batch=B,
-                            parallelism=f"dp{world} (images sharded by rank; one all-reduce of loss partials per step)",
+                            parallelism=f"dp{world} (images sharded by rank; one all-reduce of loss partials per step, outside the graph)",
                             l2="working set (activations ~9 GB/step at B=32) >> 126 MB L2; no explicit flush",
                             cuda_graph=bool(a.graph),
                             losses=[float(v) for v in last.cpu()]),

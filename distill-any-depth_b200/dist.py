@@ -21,21 +21,32 @@ def shard_batch(x, rank=None, world=None):
     return x[lo:hi]
 
 
-def finish_losses(partials, group=None):
-    """partials: {name: (kind, float64[2] tensor)} of per-rank (numerator, denominator).
-    One all-reduce over the stacked vector; returns {name: fp32 scalar tensor} of full-batch losses."""
+def stack_partials(partials):
+    """{name: (kind, float64[2])} -> (names, kinds, float64 [n, 2] tensor).  Pure device ops, no collective: this half can
+    sit inside a captured CUDA graph while the all-reduce of :func:`finish_stacked` stays outside it (a graph that holds
+    NCCL kernels keeps the communicator busy at teardown: ``destroy_process_group`` was observed to hang on it)."""
     names = sorted(partials)
     vec = torch.stack([partials[n][1].to(torch.float64) for n in names])  # [n, 2]
+    return names, [partials[n][0] for n in names], vec
+
+
+def finish_stacked(names, kinds, vec, group=None):
+    """ONE all-reduce (sum) of the stacked per-rank (numerator, denominator) partials, in place, then the ratios."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
     out = {}
-    for i, n in enumerate(names):
-        kind = partials[n][0]
+    for i, (n, kind) in enumerate(zip(names, kinds)):
         v = vec[i, 0] / (vec[i, 1] + LOSS_EPS[kind])
         if kind == "feat":
             v = 1.0 - v
         out[n] = v.to(torch.float32)
     return out
+
+
+def finish_losses(partials, group=None):
+    """partials: {name: (kind, float64[2] tensor)} of per-rank (numerator, denominator).
+    One all-reduce over the stacked vector; returns {name: fp32 scalar tensor} of full-batch losses."""
+    return finish_stacked(*stack_partials(partials), group=group)
 
 
 # ---------------------------------------------------------------------------------------------- data-parallel training

@@ -18,16 +18,10 @@ from .dist import finish_losses
 DEFAULT_LAMBDAS = dict(sc=0.5, lg=0.5, feat=1.0, grad=0.2, hdn=0.8)
 
 
-def distillation_step_losses(student_model, teacher_model, global_image, local_image, normalization="hybrid",
-                             lambdas=None, use_hdn_loss=True, hdn_level=3, hdn_variant="dr", dedup_student=False):
-    """Returns ``dict(sc_loss, lg_loss, feat_loss, grad_loss, hdn_loss, batch_loss)`` of fp32 device scalars.
-
-    ``dedup_student``: the reference runs the student twice, on ``global_image`` and ``local_image``
-    (``:1509-1510``) even when both are the same tensor (NYU path, ``:1480-1484``); with ``True`` and identical
-    inputs the second, bit-identical forward is elided.
-    """
-    lam = dict(DEFAULT_LAMBDAS)
-    lam.update(lambdas or {})
+def distillation_step_partials(student_model, teacher_model, global_image, local_image, normalization="hybrid",
+                               use_hdn_loss=True, hdn_level=3, hdn_variant="dr", dedup_student=False):
+    """The three forwards and the per-rank (numerator, denominator) partials of the five loss terms:
+    ``{name: (kind, float64[2])}``.  No collective: capturable in a CUDA graph on any number of ranks."""
     if use_hdn_loss and hdn_variant != "dr":
         # the reference passes mask_valid_list=None for any other variant and crashes (:1547)
         raise NotImplementedError("train() only wires hdn_variant='dr' (tools/train_distillation.py:1547)")
@@ -48,15 +42,36 @@ def distillation_step_losses(student_model, teacher_model, global_image, local_i
         if use_hdn_loss:
             parts["hdn_loss"] = ("hdn", losses.hdn_loss_dr(student_local_disp, teacher_local_disp, None, hdn_level,
                                                            want_partials=True)[1])
-        out = finish_losses(parts)  # one all-reduce of the stacked partials when torch.distributed is initialised
-        if not use_hdn_loss:
-            out["hdn_loss"] = torch.zeros((), device=local_image.device)
-        batch = (lam["sc"] * out["sc_loss"] + lam["lg"] * out["lg_loss"] + lam["feat"] * out["feat_loss"]
-                 + lam["grad"] * out["grad_loss"])
-        if use_hdn_loss:
-            batch = batch + lam["hdn"] * out["hdn_loss"]
-        out["batch_loss"] = batch
+    return parts
+
+
+def combine_step_losses(out, lambdas=None, use_hdn_loss=True):
+    """``batch_loss`` = the lambda-weighted sum (``:1556-1560``) of finished loss scalars; fills ``hdn_loss`` / ``batch_loss``."""
+    lam = dict(DEFAULT_LAMBDAS)
+    lam.update(lambdas or {})
+    if not use_hdn_loss:
+        out["hdn_loss"] = torch.zeros((), device=out["sc_loss"].device)
+    batch = (lam["sc"] * out["sc_loss"] + lam["lg"] * out["lg_loss"] + lam["feat"] * out["feat_loss"]
+             + lam["grad"] * out["grad_loss"])
+    if use_hdn_loss:
+        batch = batch + lam["hdn"] * out["hdn_loss"]
+    out["batch_loss"] = batch
     return out
+
+
+def distillation_step_losses(student_model, teacher_model, global_image, local_image, normalization="hybrid",
+                             lambdas=None, use_hdn_loss=True, hdn_level=3, hdn_variant="dr", dedup_student=False):
+    """Returns ``dict(sc_loss, lg_loss, feat_loss, grad_loss, hdn_loss, batch_loss)`` of fp32 device scalars.
+
+    ``dedup_student``: the reference runs the student twice, on ``global_image`` and ``local_image``
+    (``:1509-1510``) even when both are the same tensor (NYU path, ``:1480-1484``); with ``True`` and identical
+    inputs the second, bit-identical forward is elided.
+    """
+    parts = distillation_step_partials(student_model, teacher_model, global_image, local_image, normalization,
+                                       use_hdn_loss, hdn_level, hdn_variant, dedup_student)
+    with torch.no_grad():
+        out = finish_losses(parts)  # one all-reduce of the stacked partials when torch.distributed is initialised
+        return combine_step_losses(out, lambdas, use_hdn_loss)
 
 
 def distillation_train_step(student_model, teacher_model, global_image, local_image, optimizer=None, normalization="hybrid",
