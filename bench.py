@@ -454,11 +454,15 @@ def run_b200(a):
         depth, _ = model(x)
         if a.workload == "c5":   # forward only; the D2H read is one element of the depth map
             return depth.view(-1)[:2].clone()
-        first = ("ssi", losses._ssi(depth, gt, full, False, want_partials=True))
         if a.workload == "c2":
+            first = ("ssi", losses._ssi(depth, gt, full, False, want_partials=True))
             second = ("grad", losses._grad(depth, want_partials=True))
-        else:
+        elif os.environ.get("DAD_BENCH_SEPARATE_LOSSES"):   # A/B: the two separate kernel sequences of round 1
+            first = ("ssi", losses._ssi(depth, gt, full, False, want_partials=True))
             second = ("hdn", losses.hdn_loss_dr(depth, gt, None, 3, want_partials=True))
+        else:   # SSILoss + HDN-DR of the same maps: one shared sweep (losses_fused.cu)
+            ssi_v, hdn_v, p_ssi, p_hdn = losses.ssi_hdn_dr(depth, gt, None, 3, want_partials=True)
+            first, second = ("ssi", (ssi_v, p_ssi)), ("hdn", (hdn_v, p_hdn))
         if world == 1:
             return torch.stack([first[1][0], second[1][0]])
         names, kinds, vec = stack_partials({first[0]: (first[0], first[1][1]), second[0]: (second[0], second[1][1])})

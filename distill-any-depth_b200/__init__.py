@@ -5,7 +5,7 @@ from . import synthetic  # noqa: F401
 from .dpt import DepthAnythingV2, DPTHead  # noqa: F401
 from .dam import DepthAnything  # noqa: F401
 from .losses import (masked_shift_and_scale, masked_l1_loss, SSILoss, get_contexts_dr, get_contexts_dp,  # noqa: F401
-                     get_contexts_ds, compute_hdn_loss, hdn_loss_dr, gradient_preservation_loss,
+                     get_contexts_ds, compute_hdn_loss, hdn_loss_dr, ssi_hdn_dr, gradient_preservation_loss,
                      feature_distillation_loss, distillation_loss, global_normalize, hybrid_normalize,
                      local_normalize, normalize_depth)
 from . import dist  # noqa: F401

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "dad_minmax_normalize": (_i, [_vp, _i, _i64, _vp, _vp, _sz, _vp]),
     "dad_colorize_depth": (_i, [_vp, _vp, _i, _i64, _c.c_float, _c.c_float, _i, _vp, _vp, _vp, _vp, _vp]),
     "dad_hdn_loss_dr": (_i, [_i, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "dad_ssi_hdn_dr_loss": (_i, [_i, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dad_hdn_loss": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dad_grad_loss": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "dad_feat_cos_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -72,6 +72,11 @@ int dad_hdn_loss_dr(int level, const float* pred, const float* gt, const uint8_t
     return dad::hdn_loss_dr(level, pred, gt, mask, B, L, out_scalar, partials, ws, wsb, ST(stream));
 }
 
+int dad_ssi_hdn_dr_loss(int level, const float* pred, const float* gt, const uint8_t* mask, int B, int64_t L, float* out_ssi,
+                        float* out_hdn, double* partials_ssi, double* partials_hdn, void* ws, size_t wsb, void* stream) {
+    return dad::ssi_hdn_dr_fused(level, pred, gt, mask, B, L, out_ssi, out_hdn, partials_ssi, partials_hdn, ws, wsb, ST(stream));
+}
+
 int dad_hdn_loss(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, int64_t L, float* out_scalar,
                  double* partials, void* ws, size_t wsb, void* stream) {
     if (!ctx) return dad::set_error(DAD_ERR_INVALID, "hdn_loss: null contexts");

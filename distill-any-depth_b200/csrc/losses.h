@@ -13,6 +13,11 @@ int ssi_loss(const float* pred, const float* gt, const uint8_t* mask, int rows, 
              float* out_scalar, double* partials, void* ws, size_t ws_bytes, cudaStream_t st);
 int hdn_loss_dr(int level, const float* pred, const float* gt, const uint8_t* mask, int B, long long L, float* out_scalar,
                 double* partials, void* ws, size_t ws_bytes, cudaStream_t st);
+// SSILoss()(pred, gt, mask) and compute_hdn_loss(SSILoss(), pred, gt, get_contexts_dr(level, gt, mask)) in one sweep
+// sequence (losses_fused.cu); level 1..3; workspace >= ssi_hdn_fused_workspace_bytes(B) (<= loss_workspace_bytes(B, 8))
+size_t ssi_hdn_fused_workspace_bytes(int B);
+int ssi_hdn_dr_fused(int level, const float* pred, const float* gt, const uint8_t* mask, int B, long long L, float* out_ssi,
+                     float* out_hdn, double* partials_ssi, double* partials_hdn, void* ws, size_t ws_bytes, cudaStream_t st);
 int hdn_loss_ctx(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, long long L, float* out_scalar,
                  double* partials, void* ws, size_t ws_bytes, cudaStream_t st);
 int contexts_dr(int level, const float* gt, const uint8_t* mask, int B, long long L, uint8_t* ctx_out, void* ws,

@@ -520,38 +520,24 @@ public:
         void* o1 = ar.take(static_cast<size_t>(B) * H1 * W1 * F2 * es);
         Epilogue eo1; eo1.bias = P(s + "output_conv1.bias"); eo1.out = o1; eo1.out_bf16 = bf;
         DAD_TRY(conv(mode, p1, B, H1, W1, F, output_conv1, 9, eo1, dry, st));
-        // K16 + K17: the 296^2 -> 518^2 upsample feeds only the head convolution.  In bf16 mode the two run image GROUP by
-        // image group through ONE small `up` buffer sized to stay resident in the 126 MB L2: the upsampled tensor (2.2 GB per
-        // 32-image step at ViT-L 518^2) is written and read back in L2 and never travels to HBM (the buffer is rewritten
-        // before its dirty lines are evicted).  The head conv itself is bound by shared-memory operand bandwidth (N = 32),
-        // not by DRAM, so gathering the bilinear taps inside its A-operand load would only add smem traffic.
-        const size_t img_up_bytes = static_cast<size_t>(H) * W * F2 * es;
-        int group = B;
-        if (mode == 0) {
-            group = static_cast<int>((72u << 20) / img_up_bytes);
-            group = group < 1 ? 1 : (group > B ? B : group);
-        }
-        void* up = ar.take(static_cast<size_t>(group) * img_up_bytes);
+        // K16 + K17.  Measured and rejected in round 2: (a) running upsample + head conv per L2-sized image
+        // group through one small buffer keeps the 2.2 GB upsampled tensor out of HBM but is no faster (the head conv is
+        // bound by shared-memory operand bandwidth at N = 32, the per-image launches lose tail efficiency); (b) gathering
+        // the bilinear taps inside the conv's A-operand load adds shared-memory traffic to that same bottleneck.
+        void* up = ar.take(static_cast<size_t>(B) * H * W * F2 * es);
         if (!dry && getenv("DAD_DEBUG_SYNC"))
-            fprintf(stderr, "dad[debug]: ws=%p bytes=%zu used=%zu o1=%p up=%p (H1=%d W1=%d H=%d W=%d F2=%d es=%zu group=%d)\n", ws,
-                    ws_bytes, ar.used, o1, up, H1, W1, H, W, F2, es, group);
+            fprintf(stderr, "dad[debug]: ws=%p bytes=%zu used=%zu o1=%p up=%p (H1=%d W1=%d H=%d W=%d F2=%d es=%zu)\n", ws,
+                    ws_bytes, ar.used, o1, up, H1, W1, H, W, F2, es);
         float* t32 = mode == 1 ? reinterpret_cast<float*>(ar.take(static_cast<size_t>(B) * H * W * 32 * 4)) : nullptr;
         DAD_REQUIRE(!ar.overflow, "forward: workspace arena overflow (head)");
+        debug_label("head bilinear");
+        if (!dry) DAD_TRY(bilinear_nhwc(o1, up, bf, B, H1, W1, H, W, F2, st));
         if (mode == 0) {
             // conv3x3 -> ReLU -> conv1x1 -> ReLU (-> F.relu) fused in the GEMM epilogue
-            for (int b0 = 0; b0 < B; b0 += group) {
-                const int nb = (B - b0) < group ? (B - b0) : group;
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(o1) + static_cast<size_t>(b0) * H1 * W1 * F2 * es;
-                debug_label("head bilinear");
-                if (!dry) DAD_TRY(bilinear_nhwc(src, up, bf, nb, H1, W1, H, W, F2, st));
-                Epilogue eh; eh.bias = P(s + "output_conv2.0.bias"); eh.head_w = P(s + "output_conv2.2.weight");
-                eh.head_b = P(s + "output_conv2.2.bias"); eh.head_out = depth_out + static_cast<size_t>(b0) * H * W;
-                DAD_TRY(conv(mode, up, nb, H, W, F2, output_conv2_0, 9, eh, dry, st));
-                if (dry) break;   // sizing pass: one group is representative
-            }
+            Epilogue eh; eh.bias = P(s + "output_conv2.0.bias"); eh.head_w = P(s + "output_conv2.2.weight");
+            eh.head_b = P(s + "output_conv2.2.bias"); eh.head_out = depth_out;
+            DAD_TRY(conv(mode, up, B, H, W, F2, output_conv2_0, 9, eh, dry, st));
         } else {
-            debug_label("head bilinear");
-            if (!dry) DAD_TRY(bilinear_nhwc(o1, up, bf, B, H1, W1, H, W, F2, st));
             Epilogue eh; eh.bias = P(s + "output_conv2.0.bias"); eh.act = ACT_RELU; eh.out = t32;
             DAD_TRY(conv(mode, up, B, H, W, F2, output_conv2_0, 9, eh, dry, st));
             if (!dry) DAD_TRY(head1x1(t32, P(s + "output_conv2.2.weight"), P(s + "output_conv2.2.bias"), depth_out,

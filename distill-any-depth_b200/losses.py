@@ -382,6 +382,32 @@ def hdn_loss_dr(depth_preds, depth_gt, mask_valid=None, level=3, want_partials=F
 
 
 @_on_tensor_device
+def ssi_hdn_dr(depth_preds, depth_gt, mask_valid=None, level=3, want_partials=False):
+    """``(SSILoss()(p, g, mask), compute_hdn_loss(SSILoss(), p, g, get_contexts_dr(level, g, mask)))`` from ONE shared
+    sweep over the maps (``:449-542``, ``:544-576``, ``:686-707``): the step that reports both losses reads the maps five
+    times instead of ten.  ``mask_valid=None`` = all pixels valid (for SSILoss that equals an all-ones mask).
+    ``level`` 1..3.  With ``want_partials`` also returns the two float64 ``(numerator, denominator)`` pairs for the
+    multi-GPU all-reduce.  Forward only: when a gradient is wanted the two autograd-aware losses are evaluated instead."""
+    if _wants_grad(depth_preds) and not want_partials:
+        full = torch.ones_like(depth_gt, dtype=torch.bool) if mask_valid is None else mask_valid
+        return SSILoss()(depth_preds, depth_gt, full), hdn_loss_dr(depth_preds, depth_gt, mask_valid, level)
+    p, g = _f32(depth_preds, "depth_preds"), _f32(depth_gt, "depth_gt")
+    if p.dim() != 4 or p.shape[1] != 1 or g.shape != p.shape:
+        raise ValueError("ssi_hdn_dr expects maps of shape [B, 1, H, W]")
+    if not 1 <= int(level) <= 3:
+        raise NotImplementedError("ssi_hdn_dr: the fused path covers HDN levels 1..3")
+    B, L = p.shape[0], p.shape[2] * p.shape[3]
+    m = _mask_u8(mask_valid, p)
+    ssi, hdn = _new_scalar(p.device), _new_scalar(p.device)
+    ps, ph = _new_partials(p.device, want_partials), _new_partials(p.device, want_partials)
+    ws = _workspace(p.device, B, 8)
+    _lib.check(_lib.load().dad_ssi_hdn_dr_loss(int(level), _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), B, L, _lib.ptr(ssi),
+                                               _lib.ptr(hdn), _lib.ptr(ps), _lib.ptr(ph), _lib.ptr(ws), ws.numel(),
+                                               _lib.stream_ptr()), "ssi_hdn_dr")
+    return (ssi, hdn, ps, ph) if want_partials else (ssi, hdn)
+
+
+@_on_tensor_device
 def get_contexts_dp(level, depth_gt, mask_valid):
     """``:578-644`` -> bool ``[2**level - 1, B, 1, H, W]``: depth-percentile bins between the
     ``nanquantile`` values of the valid pixels (exact order statistics by radix select + ATen's lerp)."""

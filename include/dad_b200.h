@@ -124,6 +124,13 @@ int dad_contexts_ds(int level, const uint8_t* mask /*NULL = all valid*/, int B, 
  * materialised.                                                                          :544-576, :686-707 */
 int dad_hdn_loss_dr(int level, const float* pred, const float* gt, const uint8_t* mask, int B, int64_t L,
                     float* out_scalar, double* partials, void* workspace, size_t workspace_bytes, void* stream);
+/* BOTH of  SSILoss()(pred, gt, mask)  (:449-542)  and  compute_hdn_loss(SSILoss(), pred, gt, get_contexts_dr(level,
+ * gt, mask))  (:544-576, :686-707)  from one shared sweep over the maps (the loss half of a training / evaluation step
+ * that reports both): the 7 depth-range contexts and the full-mask row share every pass.  level 1..3; outputs /
+ * (numerator, denominator) partials may each be NULL.  workspace: dad_loss_workspace_bytes(B, 8). */
+int dad_ssi_hdn_dr_loss(int level, const float* pred, const float* gt, const uint8_t* mask, int B, int64_t L,
+                        float* out_ssi, float* out_hdn, double* partials_ssi, double* partials_hdn, void* workspace,
+                        size_t workspace_bytes, void* stream);
 /* compute_hdn_loss(SSILoss(), pred, gt, mask_valid_list) with explicit contexts [K, B, L], K <= 21  :686-707 */
 int dad_hdn_loss(const float* pred, const float* gt, const uint8_t* ctx, int K, int B, int64_t L, float* out_scalar,
                  double* partials, void* workspace, size_t workspace_bytes, void* stream);

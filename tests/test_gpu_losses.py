@@ -194,3 +194,65 @@ def test_contexts_dp_ds_bit_exact(level, B, H, W):
         if H == W and level <= 3:
             gs = d.get_contexts_ds(level, mk.cuda())
             assert torch.equal(gs.cpu(), oracle.get_contexts_ds(level, mk))
+
+
+def _fused_vs_parts(P, G, M, level, pred, gt, mask, tol=2e-5):
+    """ssi_hdn_dr against (a) the two separate device paths and (b) the oracle."""
+    d = dad()
+    ssi_f, hdn_f, ps, ph = d.ssi_hdn_dr(P, G, M, level, want_partials=True)
+    full = torch.ones_like(G, dtype=torch.bool) if M is None else M
+    ssi_s = d.SSILoss()(P, G, full)
+    hdn_s, ph_s = d.hdn_loss_dr(P, G, M, level, want_partials=True)
+    assert rel_scalar(ssi_f, ssi_s) <= tol, ("ssi", float(ssi_f), float(ssi_s))
+    assert rel_scalar(hdn_f, hdn_s) <= tol, ("hdn", float(hdn_f), float(hdn_s))
+    assert float(ph[1]) == float(ph_s[1]), "HDN valid-location counts differ"   # integer work: exact
+    mk = torch.ones_like(gt, dtype=torch.bool) if mask is None else mask
+    ssi_o = oracle.SSILoss()(pred, gt, mk)
+    hdn_o = oracle.compute_hdn_loss(oracle.SSILoss(), pred, gt, oracle.get_contexts_dr(level, gt, mask))
+    assert rel_scalar(ssi_f, ssi_o) <= TOL and rel_scalar(hdn_f, hdn_o) <= TOL
+    assert float(ps[1]) == float(mk.sum())
+    return float(ssi_f), float(hdn_f)
+
+
+@pytest.mark.parametrize("level", [1, 2, 3])
+@pytest.mark.parametrize("B,H,W,seed,masked", [(2, 64, 64, 7, True), (3, 56, 84, 8, False), (1, 14, 14, 3, True),
+                                              (2, 129, 71, 5, True)])
+def test_fused_ssi_hdn_matches_the_separate_paths_and_the_oracle(level, B, H, W, seed, masked):
+    """One shared sweep for SSILoss + HDN-DR (losses_fused.cu) == the two separate kernels' values == the oracle
+    (tools/train_distillation.py:449-576, 686-707); ties, the maximum pixel (outside every half-open bin) and
+    ragged sizes included."""
+    pred, gt, mask = _case(B, H, W, seed)
+    M = mask.cuda() if masked else None
+    _fused_vs_parts(pred.cuda(), gt.cuda(), M, level, pred, gt, mask if masked else None)
+
+
+def test_fused_ssi_hdn_degenerate_images():
+    """Images whose depth-range thresholds do not nest exactly (constant gt, all-zero gt, no valid pixel, heavy ties,
+    a huge dynamic range) take the row-per-unit path inside the same kernels; mixed with ordinary images in one batch."""
+    d = dad()
+    pred, gt, mask = _case(6, 40, 52, 21)
+    gt[1] = 0.5                                  # constant: every context collapses to [0.5, 0.5 + 1e-30)
+    gt[2] = 0.0                                  # all-zero: 1e-30 is NOT absorbed, every pixel is in every context
+    mask[3] = False                              # no valid pixel in image 3
+    gt[4] = torch.round(gt[4] * 3) / 3           # four distinct values: medians sit in heavy ties (list overflow path)
+    pred[4] = torch.round(pred[4] * 2) / 2
+    gt[5, 0, 0, 0] = 1e30                        # one outlier: almost everything in the first bin
+    for M, mk in ((mask.cuda(), mask), (None, None)):
+        _fused_vs_parts(pred.cuda(), gt.cuda(), M, 3, pred, gt, mk)
+    # a batch of only-degenerate images, and level 2
+    _fused_vs_parts(pred[1:3].cuda().contiguous(), gt[1:3].cuda().contiguous(), None, 2, pred[1:3], gt[1:3], None)
+
+
+def test_fused_ssi_hdn_at_baseline_size_and_gradient_fallback():
+    """BASELINE configs[2] shape (the benchmark's loss half): 4 x 518 x 518, full mask, level 3; with requires_grad the
+    autograd-aware separate losses are evaluated (same values)."""
+    d = dad()
+    pred, gt, _ = synthetic.make_depth_pair(4, 518, 518, seed=7)
+    P, G = pred.cuda(), gt.cuda()
+    ssi_f, hdn_f = _fused_vs_parts(P, G, None, 3, pred, gt, None)
+    Pg = P.clone().requires_grad_(True)
+    ssi_g, hdn_g = d.ssi_hdn_dr(Pg, G, None, 3)
+    assert ssi_g.requires_grad and hdn_g.requires_grad
+    assert rel_scalar(ssi_g, ssi_f) <= 2e-5 and rel_scalar(hdn_g, hdn_f) <= 2e-5
+    with pytest.raises(NotImplementedError):
+        d.ssi_hdn_dr(P, G, None, 4)
