@@ -253,9 +253,21 @@ def run_train(a):
     DESIGN.md's table; the headline metric stays the forward + loss workload."""
     import ctypes
     import torch
+    import torch.distributed as dist
     import distill_any_depth_b200 as d
     from distill_any_depth_b200 import synthetic, _lib
-    dev = torch.device("cuda", 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    real_stdout = os.dup(1)   # NCCL prints its banner to fd 1: keep stdout to the ONE JSON line
+    os.dup2(2, 1)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:   # data-parallel update (train4 only): images sharded by rank, exact full-batch gradient (step.py)
+        assert a.workload == "train4", "multi-GPU training is wired for --workload train4"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     B, H = a.batch, a.size
     kw = synthetic.MODEL_PRESETS[a.encoder]
@@ -264,8 +276,8 @@ def run_train(a):
     model = model.to(dev).train()
     model.precision = a.precision
     model.bf16_backward = True
-    x = synthetic.make_images(B, H, H, seed=1234).to(dev)
-    _, gt, _ = synthetic.make_depth_pair(B, H, H, seed=7)
+    x = synthetic.make_images(B, H, H, seed=1234 + rank).to(dev)
+    _, gt, _ = synthetic.make_depth_pair(B, H, H, seed=7 + rank)
     gt = gt.to(dev)
     full = torch.ones_like(gt, dtype=torch.bool)
 
@@ -277,7 +289,7 @@ def run_train(a):
         teacher.load_state_dict(student_to_teacher_keys(synthetic.make_state_dict(seed=2, head_bias=0.6, **tkw)), strict=True)
         teacher = teacher.to(dev).eval()
         teacher.precision = a.precision
-        x2 = synthetic.make_images(B, H, H, seed=4321).to(dev)
+        x2 = synthetic.make_images(B, H, H, seed=4321 + rank).to(dev)
         opt = torch.optim.SGD(model.parameters(), lr=1e-6)
 
     def step():
@@ -290,17 +302,25 @@ def run_train(a):
         loss.backward()
         return loss.detach()
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(max(a.warmup, 3)):
         step()
-    torch.cuda.synchronize()
+    barrier()
     l0 = lib.dad_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
         loss = step()
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.steps
+    barrier()
+    ms_t = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)   # device time, max over ranks
+    ms = ms_t.item()
     launches = lib.dad_launch_count() - l0
     lib.dad_profile_enable(1)
     step()
@@ -312,15 +332,21 @@ def run_train(a):
         if n.value:
             breakdown[name] = dict(ms_per_step=t.value, launches_per_step=n.value, work_per_step=w.value)
     lib.dad_profile_enable(0)
-    print(json.dumps(dict(metric="images/sec, student training step (forward + SSI/gradient loss + backward)", value=B / ms * 1e3,
-                          unit="images/s", n_gpus=1, steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms,
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    os.write(real_stdout, (json.dumps(dict(metric="images/sec, student training step (forward + SSI/gradient loss + backward)", value=world * B / ms * 1e3,
+                          unit="images/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms, scaling="weak",
                           higher_is_better=True, dtype=a.precision, data="synthetic",
                           config=dict(workload=(f"distillation update: ViT-L teacher forward + 2x {a.encoder} student forward + 5 losses + "
-                                                f"backward + SGD step, {H}x{H} batch {B} {a.precision} (BASELINE configs[3] per-GPU shard, "
-                                                f"training half; not the headline metric)") if teacher is not None else
+                                                f"backward + gradient all-reduce + SGD step, {H}x{H} batch {B}/GPU {a.precision}, dp{world} "
+                                                f"(BASELINE configs[3], training half; not the headline metric)") if teacher is not None else
                                                f"DepthAnythingV2 {a.encoder} {H}x{H} batch {B} {a.precision} train step "
                                                f"(SURVEY 8f N1; not the headline metric)"),
-                          loss=float(loss), gpu_launches=int(launches), kernel_breakdown=breakdown)))
+                          loss=float(loss), gpu_launches=int(launches), kernel_breakdown=breakdown)) + "\n").encode())
 
 
 # ---------------------------------------------------------------------------------- infer_image throughput (not a bench line)

@@ -298,8 +298,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     // S_{j+1} follows P V_{j-1} in the tensor pipe and lands about now: probe its barrier (non-blocking);
                     // the probe's latency hides behind the second half of the exponentials
                     if (j + 1 < T) next_ready = ptx::mbar_test_wait(&s_full[buf ^ 1], ((g + 1) >> 1) & 1);
-                    exp32<PP>(v_hi, sc2, nref2, pk);
-                    if (nvalid < BKV) mask16(pk, 32, nvalid);
+                    if (nvalid > 32) {
+                        exp32<PP>(v_hi, sc2, nref2, pk);
+                        if (nvalid < BKV) mask16(pk, 32, nvalid);
+                    } else {   // the last key tile ends inside its first half (N = 1370: 26 keys): no exponentials, P = 0
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                    }
                     ptx::tmem_st_32x16(tS + buf * BKV + 16, pk);
                 }
                 if (j + 1 < T) {                                       // request the next tile's first half before draining

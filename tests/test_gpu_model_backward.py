@@ -329,3 +329,71 @@ def test_distillation_train_step_matches_the_reference_loop():
     out2 = d.distillation_train_step(student, teacher, xg.cuda(), xl.cuda(), optimizer=opt, lambdas=lam)
     assert float(out2["batch_loss"]) != float(out["batch_loss"])
     assert all(p.grad is None for p in student.parameters())
+
+
+def _dp_worker(rank, world, port, q):
+    """One data-parallel rank of the distillation update.  Both ranks share cuda:0 (the test box has one GPU), so the
+    collectives go through gloo on CUDA tensors; the host logic under test is the same as under NCCL."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import distill_any_depth_b200 as d
+    from distill_any_depth_b200.dam import student_to_teacher_keys
+    from distill_any_depth_b200.dist import shard_batch
+    kws, kwl = synthetic.MODEL_PRESETS["vits"], synthetic.MODEL_PRESETS["vitl"]
+    student = d.DepthAnythingV2(**kws)
+    student.load_state_dict(synthetic.make_state_dict(seed=0, **kws), strict=True)
+    student = student.cuda().train()
+    student.precision = "fp32"
+    teacher = d.DepthAnything(**kwl)
+    teacher.load_state_dict(student_to_teacher_keys(synthetic.make_state_dict(seed=2, head_bias=0.6, **kwl)), strict=True)
+    teacher = teacher.cuda().eval()
+    teacher.precision = "fp32"
+    xg = shard_batch(synthetic.make_images(3, 56, 70, seed=11), rank, world).cuda().contiguous()   # 3 images: shards of 2 + 1
+    xl = shard_batch(synthetic.make_images(3, 56, 70, seed=12), rank, world).cuda().contiguous()
+    out = d.distillation_train_step(student, teacher, xg, xl, optimizer=None)
+    torch.cuda.synchronize()
+    if rank == 0:
+        q.put(({k: float(v) for k, v in out.items()},
+               {k: (None if p.grad is None else p.grad.cpu()) for k, p in student.named_parameters()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_train_step_equals_the_single_process_full_batch_update():
+    """SURVEY 8e x 8f N1: two ranks, uneven shards (2 + 1 images), shard-weighted losses + SUM all-reduce of the gradients
+    == the single-process update on the 3-image batch (tools/train_distillation.py:1503-1575): loss values and every
+    parameter gradient; parameters without a gradient stay None."""
+    import torch.multiprocessing as mp
+    d = dad()
+    from distill_any_depth_b200.dam import student_to_teacher_keys
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    losses_dp, grads_dp = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    kws, kwl = synthetic.MODEL_PRESETS["vits"], synthetic.MODEL_PRESETS["vitl"]
+    student = d.DepthAnythingV2(**kws)
+    student.load_state_dict(synthetic.make_state_dict(seed=0, **kws), strict=True)
+    student = student.cuda().train()
+    student.precision = "fp32"
+    teacher = d.DepthAnything(**kwl)
+    teacher.load_state_dict(student_to_teacher_keys(synthetic.make_state_dict(seed=2, head_bias=0.6, **kwl)), strict=True)
+    teacher = teacher.cuda().eval()
+    teacher.precision = "fp32"
+    out = d.distillation_train_step(student, teacher, synthetic.make_images(3, 56, 70, seed=11).cuda(),
+                                    synthetic.make_images(3, 56, 70, seed=12).cuda(), optimizer=None, data_parallel=False)
+    for k, v in out.items():
+        assert abs(losses_dp[k] - float(v)) <= 2e-5 * max(abs(float(v)), 1e-6), (k, losses_dp[k], float(v))
+    for k, p in student.named_parameters():
+        if p.grad is None:
+            assert grads_dp[k] is None, k
+            continue
+        g = p.grad.cpu()
+        assert grads_dp[k] is not None, k
+        assert float((grads_dp[k] - g).abs().max()) <= 2e-4 * float(g.abs().max()) + 1e-9, k
