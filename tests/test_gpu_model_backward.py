@@ -355,7 +355,7 @@ def _dp_worker(rank, world, port, q):
     torch.cuda.synchronize()
     if rank == 0:
         q.put(({k: float(v) for k, v in out.items()},
-               {k: (None if p.grad is None else p.grad.cpu()) for k, p in student.named_parameters()}))
+               {k: (None if p.grad is None else p.grad.cpu().numpy()) for k, p in student.named_parameters()}))   # by value
     dist.barrier()
     dist.destroy_process_group()
 
@@ -396,4 +396,4 @@ def test_data_parallel_train_step_equals_the_single_process_full_batch_update():
             continue
         g = p.grad.cpu()
         assert grads_dp[k] is not None, k
-        assert float((grads_dp[k] - g).abs().max()) <= 2e-4 * float(g.abs().max()) + 1e-9, k
+        assert float((torch.from_numpy(grads_dp[k]) - g).abs().max()) <= 2e-4 * float(g.abs().max()) + 1e-9, k
