@@ -87,7 +87,9 @@ int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, 
         const char* ep = getenv("DAD_ATT_POLY5");      // pairs of every 8 exponentiated on the FMA pipe (0, 2, 3, 4, 5)
         const int variant = ev ? atoi(ev) : 5;
         const int poly = ep ? atoi(ep) : 2;
-        if (variant == 3)
+        if (variant == 6)
+            DAD_TRY(attention_tc6(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, poly, st));
+        else if (variant == 3)
             DAD_TRY(attention_tc3(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, st));
         else if (variant == 2)
             DAD_TRY(attention_tc(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, st));

@@ -1,0 +1,386 @@
+// Variant of attention_tc5.cu (same persistent structure, roles, redo list and exponential mix - see that file) with THREE
+// score buffers and the row sums back in the softmax threads:
+//   TMEM (256 columns per CTA): S0/P0 [0,64) S1/P1 [64,128) S2/P2 [128,192) | O [192,256)   (no row-sum accumulator)
+// Why: in attention_tc5 the softmax warps spend ~9 % of all samples waiting for the NEXT score tile (ncu source page,
+// profiles/attention_r2.md): with two in-place buffers S_{g+2} can only be issued after P V_g.  With three, the tensor pipe
+// holds S_{g+1} and S_{g+2} while the exponentials of tile g run, so Q K^T is never on the softmax warps' critical path.
+// The price: no TMEM columns are left for the tensor-core row sum, so l = sum P is accumulated with packed FADD2 (one
+// issue slot per pair) in the softmax threads.
+#include <cstdlib>
+
+#include "elementwise.h"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace dad {
+
+namespace {
+
+constexpr int BQ = 128, BKV = 64, HD = 64;
+constexpr int Q_BYTES = BQ * HD * 2;      // 16 KB (x2: the next item's Q is prefetched)
+constexpr int KV_BYTES = BKV * HD * 2;    // 8 KB
+constexpr int KV_STAGES = 4;
+constexpr int ATT_THREADS = 192;
+constexpr int TMEM_COLS = 256;
+constexpr int NS = 3;                     // in-place score / probability buffers
+constexpr int S_COL = 0, O_COL = 192;
+constexpr int MAX_ITEMS_PER_CTA = 2048;   // redo bitmap: one bit per item of this CTA
+constexpr int ATT_SMEM = 2 * Q_BYTES + 2 * KV_STAGES * KV_BYTES + 512 + MAX_ITEMS_PER_CTA / 8 + 1024;
+constexpr float LOG2E = 1.4426950408889634f;
+
+enum : int { MODE_FAST = 0, MODE_MAXPASS = 1, MODE_EXACT = 2 };
+
+// exp2 of 32 scores against the reference -> 16 packed bf16 pairs; returns their sum.  PP of every 8 pairs use the FMA-pipe
+// cubic.  MASKED (last, partial key tile only): columns >= nvalid contribute P = 0.
+template <int PP, bool MASKED>
+__device__ __forceinline__ float exp32(const uint32_t (&x)[32], uint64_t sc2, uint64_t nref2, uint32_t (&pk)[16], int col0,
+                                       int nvalid) {
+    uint64_t acc = ptx::pack2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float a0, a1, p0, p1;
+        ptx::unpack2(ptx::ffma2(ptx::pack2(__uint_as_float(x[2 * i]), __uint_as_float(x[2 * i + 1])), sc2, nref2), a0, a1);
+        if (((i * PP) & 7) < PP) {
+            ptx::ex2_fma2(a0, a1, p0, p1);
+        } else {
+            p0 = ptx::ex2_approx(a0);
+            p1 = ptx::ex2_approx(a1);
+        }
+        if (MASKED) {
+            if (col0 + 2 * i >= nvalid) p0 = 0.f;
+            if (col0 + 2 * i + 1 >= nvalid) p1 = 0.f;
+        }
+        acc = ptx::fadd2(acc, ptx::pack2(p0, p1));
+        pk[i] = ptx::cvt_bf16x2(p0, p1);
+    }
+    float s0, s1;
+    ptx::unpack2(acc, s0, s1);
+    return s0 + s1;
+}
+
+__device__ __forceinline__ float max32(const uint32_t (&x)[32], int col0, int nvalid) {
+    float a = -INFINITY, b = -INFINITY, c = -INFINITY, d = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        a = fmaxf(a, (col0 + i < nvalid) ? __uint_as_float(x[i]) : -INFINITY);
+        b = fmaxf(b, (col0 + i + 1 < nvalid) ? __uint_as_float(x[i + 1]) : -INFINITY);
+        c = fmaxf(c, (col0 + i + 2 < nvalid) ? __uint_as_float(x[i + 2]) : -INFINITY);
+        d = fmaxf(d, (col0 + i + 3 < nvalid) ? __uint_as_float(x[i + 3]) : -INFINITY);
+    }
+    return fmaxf(fmaxf(a, b), fmaxf(c, d));
+}
+
+template <int PP>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_tc6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int N, int D, int heads, int total) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                   // [2][Q_BYTES]
+    uint8_t* sK = smem + 2 * Q_BYTES;
+    uint8_t* sV = sK + KV_STAGES * KV_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * KV_BYTES);
+    uint64_t* q_full = bars;                          // [2]
+    uint64_t* q_empty = bars + 2;                     // [2]
+    uint64_t* k_full = bars + 4;                      // [KV_STAGES]
+    uint64_t* v_full = k_full + KV_STAGES;            // [KV_STAGES]
+    uint64_t* kv_empty = v_full + KV_STAGES;          // [KV_STAGES]
+    uint64_t* s_full = kv_empty + KV_STAGES;          // [NS]
+    uint64_t* p_full = s_full + NS;                   // [NS], 128 arrivals
+    uint64_t* done = p_full + NS;                     // last P V of an item retired
+    uint64_t* main_done = done + 1;                   // softmax -> TMA / MMA warps: the redo bitmap is final
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(main_done + 1);
+    uint32_t* redo = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [MAX_ITEMS_PER_CTA / 32]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = (N + BKV - 1) / BKV;
+    const int QT = (N + BQ - 1) / BQ;
+    const int G = gridDim.x;
+    const int n_mine = (total - static_cast<int>(blockIdx.x) + G - 1) / G;   // items blockIdx.x, blockIdx.x + G, ...
+
+    if (warp == 4 && lane == 0) {
+        ptx::prefetch_tmap(&tmQ);
+        ptx::prefetch_tmap(&tmK);
+        ptx::prefetch_tmap(&tmV);
+    }
+    if (threadIdx.x < MAX_ITEMS_PER_CTA / 32) redo[threadIdx.x] = 0u;
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(&q_full[i], 1);
+                ptx::mbar_init(&q_empty[i], 1);
+            }
+            for (int i = 0; i < NS; ++i) {
+                ptx::mbar_init(&s_full[i], 1);
+                ptx::mbar_init(&p_full[i], 128);
+            }
+            for (int i = 0; i < KV_STAGES; ++i) {
+                ptx::mbar_init(&k_full[i], 1);
+                ptx::mbar_init(&v_full[i], 1);
+                ptx::mbar_init(&kv_empty[i], 1);
+            }
+            ptx::mbar_init(done, 1);
+            ptx::mbar_init(main_done, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_wait();  // prologue above overlaps the previous kernel's tail; global memory is touched only below
+
+    // Every role walks the same sequence of STREAMS: the main stream (all n_mine items back to back), then one
+    // single-item stream per redo pass.  g = running key-tile counter, it = running item counter over all streams:
+    // they index the ring stages and give every barrier its phase parity.
+    const auto redo_bit = [&](int i) { return (reinterpret_cast<volatile uint32_t*>(redo)[i >> 5] >> (i & 31)) & 1u; };
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- TMA producer
+            int g = 0, it = 0;
+            auto stream_item = [&](int w) {
+                const int qt = w % QT, bh = w / QT, h = bh % heads, b = bh / heads;
+                const int qb = it & 1;
+                ptx::mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&q_full[qb], Q_BYTES);
+                ptx::tma_load_3d(sQ + qb * Q_BYTES, &tmQ, &q_full[qb], h * HD, qt * BQ, b);
+                for (int j = 0; j < T; ++j, ++g) {
+                    const int s = g % KV_STAGES;
+                    ptx::mbar_wait(&kv_empty[s], ((g / KV_STAGES) & 1) ^ 1);
+                    ptx::mbar_arrive_expect_tx(&k_full[s], KV_BYTES);
+                    ptx::tma_load_3d(sK + s * KV_BYTES, &tmK, &k_full[s], h * HD, j * BKV, b);
+                    ptx::mbar_arrive_expect_tx(&v_full[s], KV_BYTES);
+                    ptx::tma_load_3d(sV + s * KV_BYTES, &tmV, &v_full[s], h * HD, j * BKV, b);
+                }
+                ++it;
+            };
+            for (int i = 0; i < n_mine; ++i) stream_item(blockIdx.x + i * G);
+            ptx::mbar_wait(main_done, 0);
+            for (int i = 0; i < n_mine; ++i)
+                if (redo_bit(i)) {
+                    stream_item(blockIdx.x + i * G);   // max-only pass
+                    stream_item(blockIdx.x + i * G);   // exact pass
+                }
+        }
+    } else if (warp == 5) {
+        // -------------------------------------------------------------------- MMA issuer
+        constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV);
+        constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_bmn(BQ, HD);
+        constexpr uint32_t kDescHiMn = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t q_lo0 = ptx::desc_lo_sw128(ptx::smem_u32(sQ));
+        const uint32_t k_lo0 = ptx::desc_lo_sw128(ptx::smem_u32(sK));
+        const uint32_t v_lo0 = ptx::desc_lo_mn_sw128(ptx::smem_u32(sV));
+        int g0 = 0, it = 0;
+        auto issue_qk = [&](int g, uint32_t q_lo) {  // S[g % NS] = Q K_g^T
+            const int s = g % KV_STAGES;
+            ptx::mbar_wait(&k_full[s], (g / KV_STAGES) & 1);
+            ptx::tc_fence_after();
+            const uint32_t k_lo = k_lo0 + s * (KV_BYTES >> 4);
+            if (ptx::elect_one()) {
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    ptx::umma_bf16(tmem + S_COL + (g % NS) * BKV, ptx::make_desc(q_lo + 2 * k, ptx::kDescHiSw128),
+                                   ptx::make_desc(k_lo + 2 * k, ptx::kDescHiSw128), idesc_qk, k != 0 ? 1u : 0u);
+                ptx::umma_commit(&s_full[g % NS]);
+            }
+            __syncwarp();
+        };
+        auto mma_item = [&]() {
+            const int qb = it & 1;
+            const uint32_t q_lo = q_lo0 + qb * (Q_BYTES >> 4);
+            ptx::mbar_wait(&q_full[qb], (it >> 1) & 1);
+            // the first three S tiles of an item are issued while the softmax warps may still be storing the previous
+            // item's output: S[g % NS] only has to be past P V of tile g - NS (in-order pipe); O is not touched here
+            issue_qk(g0, q_lo);
+            if (T > 1) issue_qk(g0 + 1, q_lo);
+            if (T > 2) issue_qk(g0 + 2, q_lo);
+            for (int j = 0; j < T; ++j) {
+                const int g = g0 + j;
+                const int s = g % KV_STAGES;
+                ptx::mbar_wait(&p_full[g % NS], (g / NS) & 1);      // P_g written in place of S[g % NS]; for j == 0 also:
+                ptx::mbar_wait(&v_full[s], (g / KV_STAGES) & 1);    // the previous item's O has been read out
+                ptx::tc_fence_after();
+                const uint32_t v_lo = v_lo0 + s * (KV_BYTES >> 4);
+                const uint32_t tP = tmem + S_COL + (g % NS) * BKV;
+                if (ptx::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BKV / 16; ++k)   // O += P V: 16 keys = 16 rows of 128 B per k-step
+                        ptx::umma_bf16_ts(tmem + O_COL, tP + k * 8, ptx::make_desc(v_lo + k * (16 * 128 >> 4), kDescHiMn),
+                                          idesc_pv, (j | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&kv_empty[s]);                  // K_g / V_g stage free once these retire
+                    if (j == T - 1) {
+                        ptx::umma_commit(done);
+                        ptx::umma_commit(&q_empty[qb]);              // every Q K^T of this item has retired
+                    }
+                }
+                __syncwarp();
+                if (j + NS < T) issue_qk(g + NS, q_lo);              // executes after P V_g (in-order pipe): S[g % NS] is free
+            }
+            g0 += T;
+            ++it;
+        };
+        for (int i = 0; i < n_mine; ++i) mma_item();
+        pdl_launch_dependents();
+        ptx::mbar_wait(main_done, 0);
+        for (int i = 0; i < n_mine; ++i)
+            if (redo_bit(i)) {
+                mma_item();
+                mma_item();
+            }
+    } else {
+        // -------------------------------------------------------------------- softmax (warps 0-3)
+        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+        const uint32_t tS = tmem + lane_base + S_COL, tO = tmem + lane_base + O_COL;
+        const uint64_t sc2 = ptx::pack2(LOG2E, LOG2E);
+        uint32_t v_lo[32], v_hi[32], pk[16];
+        int g0 = 0, it = 0;
+        float rmax = -INFINITY;   // MAXPASS result, consumed by the EXACT pass that follows it
+
+        auto softmax_item = [&](int w, int idx, int mode) {
+            const int qt = w % QT, bh = w / QT, h = bh % heads, b = bh / heads;
+            uint64_t nref2 = 0;
+            if (mode == MODE_EXACT) {
+                const float m = rmax * LOG2E;
+                nref2 = ptx::pack2(-m, -m);
+            }
+            if (mode == MODE_MAXPASS) rmax = -INFINITY;
+            float l = 0.f;
+            ptx::mbar_wait(&s_full[g0 % NS], (g0 / NS) & 1);
+            ptx::tc_fence_after();
+            ptx::tmem_ld_32x32(tS + (g0 % NS) * BKV, v_lo);
+            for (int j = 0; j < T; ++j) {
+                const int g = g0 + j;
+                const int buf = g % NS, nbuf = (g + 1) % NS;
+                const uint32_t nph = ((g + 1) / NS) & 1;
+                const int nvalid = min(BKV, N - j * BKV);
+                ptx::tmem_ld_wait();                                   // first half of tile j is in registers
+                ptx::tmem_ld_32x32(tS + buf * BKV + 32, v_hi);          // second half: in flight during the first exps
+                uint32_t next_ready = 1u;
+                if (mode == MODE_MAXPASS) {
+                    ptx::tmem_ld_wait();
+                    rmax = fmaxf(rmax, fmaxf(max32(v_lo, 0, nvalid), max32(v_hi, 32, nvalid)));
+                } else {
+                    if (j == 0 && mode == MODE_FAST) {                  // the first tile defines the reference
+                        ptx::tmem_ld_wait();
+                        const float m = fmaxf(max32(v_lo, 0, nvalid), max32(v_hi, 32, nvalid)) * LOG2E;
+                        nref2 = ptx::pack2(-m, -m);
+                    }
+                    l += nvalid < BKV ? exp32<PP, true>(v_lo, sc2, nref2, pk, 0, nvalid) : exp32<PP, false>(v_lo, sc2, nref2, pk, 0, nvalid);
+                    ptx::tmem_st_32x16(tS + buf * BKV, pk);             // P columns [0,16) <- keys [0,32) (S lo is in registers)
+                    ptx::tmem_ld_wait();                                // second half arrived
+                    // S_{j+1} follows P V_{j-1} in the tensor pipe and lands about now: probe its barrier (non-blocking);
+                    // the probe's latency hides behind the second half of the exponentials
+                    if (j + 1 < T) next_ready = ptx::mbar_test_wait(&s_full[nbuf], nph);
+                    if (nvalid > 32) {
+                        l += nvalid < BKV ? exp32<PP, true>(v_hi, sc2, nref2, pk, 32, nvalid) : exp32<PP, false>(v_hi, sc2, nref2, pk, 32, nvalid);
+                    } else {   // the last key tile ends inside its first half (N = 1370: 26 keys): no exponentials, P = 0
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                    }
+                    ptx::tmem_st_32x16(tS + buf * BKV + 16, pk);
+                }
+                if (j + 1 < T) {                                       // request the next tile's first half before draining
+                    if (mode == MODE_MAXPASS || !next_ready) ptx::mbar_wait(&s_full[nbuf], nph);
+                    ptx::tc_fence_after();
+                    ptx::tmem_ld_32x32(tS + nbuf * BKV, v_lo);
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&p_full[buf]);
+            }
+            g0 += T;
+            ptx::mbar_wait(done, it & 1);
+            ptx::tc_fence_after();
+            ++it;
+            if (mode == MODE_MAXPASS) return;
+            if (mode == MODE_FAST) {   // a non-finite row sum: the whole item goes on the redo list (rare)
+                const bool bad = !(l < 3.0e38f);
+                if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&redo[idx >> 5], 1u << (idx & 31));
+            }
+            // O / l -> bf16 -> global (each thread owns one 128-byte row segment); a redone item overwrites this later
+            const int row = qt * BQ + warp * 32 + lane;
+            const float inv = 1.0f / l;
+            bf16* dst = out + (static_cast<long long>(b) * N + row) * D + h * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD / 32; ++c) {
+                uint32_t o[32];
+                ptx::tmem_ld_32x32(tO + c * 32, o);
+                ptx::tmem_ld_wait();
+                if (row < N) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 wv;
+                        wv.x = ptx::cvt_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+                        wv.y = ptx::cvt_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                        wv.z = ptx::cvt_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                        wv.w = ptx::cvt_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + i) = wv;
+                    }
+                }
+            }
+            ptx::tc_fence_before();   // O / L reads are complete before this thread's next p_full arrive releases P V
+        };
+
+        for (int i = 0; i < n_mine; ++i) softmax_item(blockIdx.x + i * G, i, MODE_FAST);
+        ptx::named_bar_sync(1, 128);          // every softmax thread has published its redo bits
+        if (threadIdx.x == 0) ptx::mbar_arrive(main_done);
+        for (int i = 0; i < n_mine; ++i)
+            if (redo_bit(i)) {
+                softmax_item(blockIdx.x + i * G, i, MODE_MAXPASS);
+                softmax_item(blockIdx.x + i * G, i, MODE_EXACT);
+            }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, TMEM_COLS);
+    }
+}
+
+template <int PP>
+int launch6(const CUtensorMap* tm, bf16* out, int B, int N, int heads, cudaStream_t st) {
+    static bool configured = false;
+    static int sms = 0;
+    if (!configured) {
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc6_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        int dev = 0;
+        DAD_CHECK_CUDA(cudaGetDevice(&dev));
+        DAD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    const long long total = static_cast<long long>(B) * heads * cdiv(N, BQ);
+    const int grid = static_cast<int>(total < 2LL * sms ? total : 2LL * sms);
+    DAD_REQUIRE(cdiv(total, grid) <= MAX_ITEMS_PER_CTA, "attention: %lld work items exceed the per-CTA redo bitmap", total);
+    DAD_CHECK_CUDA(launch_pdl(attention_tc6_kernel<PP>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N,
+                              heads * HD, heads, static_cast<int>(total)));
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+}  // namespace
+
+// qkv [B*N, 3*D] bf16 (q pre-scaled) -> out [B*N, D] bf16.  poly_pairs = pairs of every 8 on the FMA pipe (0, 2..5).
+int attention_tc6(const bf16* qkv, bf16* out, int B, int N, int heads, int poly_pairs, cudaStream_t st) {
+    const int D = heads * HD;
+    CUtensorMap tm[3];
+    for (int i = 0; i < 3; ++i) {
+        const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)3 * D * 2, (cuuint64_t)3 * D * 2 * N};
+        const cuuint32_t box[3] = {(cuuint32_t)HD, (cuuint32_t)(i == 0 ? BQ : BKV), 1};
+        DAD_TRY(make_tmap_bf16(&tm[i], qkv + static_cast<long long>(i) * D, 3, dims, strides, box));
+    }
+    switch (poly_pairs) {
+        case 0: return launch6<0>(tm, out, B, N, heads, st);
+        case 3: return launch6<3>(tm, out, B, N, heads, st);
+        case 4: return launch6<4>(tm, out, B, N, heads, st);
+        case 5: return launch6<5>(tm, out, B, N, heads, st);
+        default: return launch6<2>(tm, out, B, N, heads, st);
+    }
+}
+
+}  // namespace dad

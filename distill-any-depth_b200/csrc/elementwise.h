@@ -31,6 +31,8 @@ int attention_tc(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream
 int attention_tc3(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStream_t st); // 4 CTAs / SM variant
 // round-2 default: FFMA2 + MUFU / FMA-pipe exponentials, tensor-core row sums, in-kernel exact fallback (attention_tc5.cu)
 int attention_tc5(const bf16* qkv, bf16* out, int B, int N, int heads, int poly_pairs, cudaStream_t st);
+// same with three in-place score buffers and the row sums in the softmax threads (attention_tc6.cu)
+int attention_tc6(const bf16* qkv, bf16* out, int B, int N, int heads, int poly_pairs, cudaStream_t st);
 int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, cudaStream_t st);
 
 }  // namespace dad

@@ -128,7 +128,7 @@ def full(tag):
 CLASSES = [("gemm_tc", ("gemm_tc", "conv_tc2")), ("attention", ("attention",)), ("layernorm", ("layernorm",)),
            ("elementwise", ("bilinear", "im2col", "patch_im2col", "head1x1")),
            ("loss", ("sel_", "mad_", "final_", "minmax", "init_minmax", "scale_", "ratio_", "sobel", "featcos", "l1_", "hyb_",
-                     "set_den", "contexts_"))]
+                     "set_den", "contexts_", "fz_"))]
 
 
 def klass(name):
