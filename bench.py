@@ -29,7 +29,7 @@ PROF_CLASSES = ["gemm_tc", "gemm_simt", "attention", "layernorm", "elementwise",
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (BASELINE configs[2]: 32)")
@@ -705,7 +705,9 @@ def run_b200(a):
                             losses=[float(v) for v in last.cpu()]),
                 e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=int(x_host.numel() * 4),
                          d2h_bytes_per_step=8, ms_per_step=ms_e2e / a.steps),
-                gpu_launches=int(launches), clocks=sampler.result(), roofline=roofline, kernel_breakdown=prof)
+                gpu_launches=int(launches), clocks=sampler.result(), roofline=roofline, kernel_breakdown=prof,
+                kernel_breakdown_source="separate pass after the timed loops: the same step launched from the host with a CUDA "
+                                        "event pair around every library launch (the timed loops replay a CUDA graph)")
     if world == 1 and not a.no_cpu_baseline and a.workload == "c3":
         line["cpu_baseline"] = cpu_baseline(a)
     if world == 1 and not a.no_gpu_eager and a.workload == "c3":
