@@ -25,6 +25,7 @@
 // TMEM (256 columns per CTA): S0/P0 [0,64) S1/P1 [64,128) | O [128,192) | L [192,208): P is written in place of S.
 // Roles (192 threads): warps 0-3 softmax (thread = query row), warp 4 TMA producer, warp 5 tcgen05.mma issuer.
 #include <cstdlib>
+#include <type_traits>
 
 #include "elementwise.h"
 #include "ptx.cuh"
@@ -86,7 +87,20 @@ __device__ __forceinline__ float max32(const uint32_t (&x)[32], int col0, int nv
     return fmaxf(fmaxf(a, b), fmaxf(c, d));
 }
 
-template <int PP>
+// PP / PPB: exponential mix (pairs of every 8 on the FMA pipe) of the CTAs in the first / second half of the grid.  CTA i and
+// CTA i + 148 share an SM, so PP != PPB gives the two co-resident softmax warps of a scheduler DIFFERENT pipe loads
+// (one MUFU-heavy, one FMA-heavy) instead of two identical streams that contend for the MUFU in lock-step.
+__device__ __forceinline__ float max32u(const uint32_t (&x)[32]) {   // full tile: no column masking
+    float a = __uint_as_float(x[0]), b = __uint_as_float(x[1]), c = __uint_as_float(x[2]), d = __uint_as_float(x[3]);
+#pragma unroll
+    for (int i = 4; i < 32; i += 4) {
+        a = fmaxf(a, __uint_as_float(x[i])); b = fmaxf(b, __uint_as_float(x[i + 1]));
+        c = fmaxf(c, __uint_as_float(x[i + 2])); d = fmaxf(d, __uint_as_float(x[i + 3]));
+    }
+    return fmaxf(fmaxf(a, b), fmaxf(c, d));
+}
+
+template <int PP, int PPB>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int N, int D, int heads, int total) {
@@ -264,7 +278,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         int g0 = 0, it = 0;
         float rmax = -INFINITY;   // MAXPASS result, consumed by the EXACT pass that follows it
 
-        auto softmax_item = [&](int w, int idx, int mode) {
+        // mode and the first / last position of a tile are compile-time: the steady-state tiles (neither first nor last) of
+        // the fast path carry no mode test, no column mask and no bounds arithmetic
+        auto softmax_item = [&](auto ppc, auto modec, int w, int idx) {
+            constexpr int PPX = decltype(ppc)::value;
+            constexpr int mode = decltype(modec)::value;
             const int qt = w % QT, bh = w / QT, h = bh % heads, b = bh / heads;
             uint64_t nref2 = 0;
             if (mode == MODE_EXACT) {
@@ -275,10 +293,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             ptx::mbar_wait(&s_full[g0 & 1], (g0 >> 1) & 1);
             ptx::tc_fence_after();
             ptx::tmem_ld_32x32(tS + (g0 & 1) * BKV, v_lo);
-            for (int j = 0; j < T; ++j) {
+            auto tile = [&](auto firstc, auto lastc, int j) {
+                constexpr bool FIRST = decltype(firstc)::value, LAST = decltype(lastc)::value;
                 const int g = g0 + j;
                 const int buf = g & 1;
-                const int nvalid = min(BKV, N - j * BKV);
+                const int nvalid = (FIRST || LAST) ? min(BKV, N - j * BKV) : BKV;
                 ptx::tmem_ld_wait();                                   // first half of tile j is in registers
                 ptx::tmem_ld_32x32(tS + buf * BKV + 32, v_hi);          // second half: in flight during the first exps
                 uint32_t next_ready = 1u;
@@ -286,28 +305,29 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     ptx::tmem_ld_wait();
                     rmax = fmaxf(rmax, fmaxf(max32(v_lo, 0, nvalid), max32(v_hi, 32, nvalid)));
                 } else {
-                    if (j == 0 && mode == MODE_FAST) {                  // the first tile defines the reference
+                    if (FIRST && mode == MODE_FAST) {                   // the first tile defines the reference
                         ptx::tmem_ld_wait();
-                        const float m = fmaxf(max32(v_lo, 0, nvalid), max32(v_hi, 32, nvalid)) * LOG2E;
+                        const float m = (nvalid == BKV ? fmaxf(max32u(v_lo), max32u(v_hi))
+                                                       : fmaxf(max32(v_lo, 0, nvalid), max32(v_hi, 32, nvalid))) * LOG2E;
                         nref2 = ptx::pack2(-m, -m);
                     }
-                    exp32<PP>(v_lo, sc2, nref2, pk);
-                    if (nvalid < BKV) mask16(pk, 0, nvalid);
+                    exp32<PPX>(v_lo, sc2, nref2, pk);
+                    if ((FIRST || LAST) && nvalid < BKV) mask16(pk, 0, nvalid);
                     ptx::tmem_st_32x16(tS + buf * BKV, pk);             // P columns [0,16) <- keys [0,32) (S lo is in registers)
                     ptx::tmem_ld_wait();                                // second half arrived
                     // S_{j+1} follows P V_{j-1} in the tensor pipe and lands about now: probe its barrier (non-blocking);
                     // the probe's latency hides behind the second half of the exponentials
-                    if (j + 1 < T) next_ready = ptx::mbar_test_wait(&s_full[buf ^ 1], ((g + 1) >> 1) & 1);
-                    if (nvalid > 32) {
-                        exp32<PP>(v_hi, sc2, nref2, pk);
-                        if (nvalid < BKV) mask16(pk, 32, nvalid);
+                    if (!LAST) next_ready = ptx::mbar_test_wait(&s_full[buf ^ 1], ((g + 1) >> 1) & 1);
+                    if (!(FIRST || LAST) || nvalid > 32) {
+                        exp32<PPX>(v_hi, sc2, nref2, pk);
+                        if ((FIRST || LAST) && nvalid < BKV) mask16(pk, 32, nvalid);
                     } else {   // the last key tile ends inside its first half (N = 1370: 26 keys): no exponentials, P = 0
 #pragma unroll
                         for (int i = 0; i < 16; ++i) pk[i] = 0u;
                     }
                     ptx::tmem_st_32x16(tS + buf * BKV + 16, pk);
                 }
-                if (j + 1 < T) {                                       // request the next tile's first half before draining
+                if (!LAST) {                                           // request the next tile's first half before draining
                     if (mode == MODE_MAXPASS || !next_ready) ptx::mbar_wait(&s_full[buf ^ 1], ((g + 1) >> 1) & 1);
                     ptx::tc_fence_after();
                     ptx::tmem_ld_32x32(tS + (buf ^ 1) * BKV, v_lo);
@@ -315,6 +335,15 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&p_full[buf]);
+            };
+            using Yes = std::true_type;
+            using No = std::false_type;
+            if (T == 1) {
+                tile(Yes{}, Yes{}, 0);
+            } else {
+                tile(Yes{}, No{}, 0);
+                for (int j = 1; j < T - 1; ++j) tile(No{}, No{}, j);
+                tile(No{}, Yes{}, T - 1);
             }
             g0 += T;
             ptx::mbar_wait(done, it & 1);
@@ -353,13 +382,16 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             ptx::tc_fence_before();   // O / L reads are complete before this thread's next p_full arrive releases P V
         };
 
-        for (int i = 0; i < n_mine; ++i) softmax_item(blockIdx.x + i * G, i, MODE_FAST);
+        const bool second_half = PP != PPB && blockIdx.x >= (gridDim.x >> 1);
+        using Fast = std::integral_constant<int, MODE_FAST>;
+        if (second_half) for (int i = 0; i < n_mine; ++i) softmax_item(std::integral_constant<int, PPB>{}, Fast{}, blockIdx.x + i * G, i);
+        else for (int i = 0; i < n_mine; ++i) softmax_item(std::integral_constant<int, PP>{}, Fast{}, blockIdx.x + i * G, i);
         ptx::named_bar_sync(1, 128);          // every softmax thread has published its redo bits
         if (threadIdx.x == 0) ptx::mbar_arrive(main_done);
         for (int i = 0; i < n_mine; ++i)
             if (redo_bit(i)) {
-                softmax_item(blockIdx.x + i * G, i, MODE_MAXPASS);
-                softmax_item(blockIdx.x + i * G, i, MODE_EXACT);
+                softmax_item(std::integral_constant<int, PP>{}, std::integral_constant<int, MODE_MAXPASS>{}, blockIdx.x + i * G, i);
+                softmax_item(std::integral_constant<int, PP>{}, std::integral_constant<int, MODE_EXACT>{}, blockIdx.x + i * G, i);
             }
     }
     ptx::tc_fence_before();
@@ -370,12 +402,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
 }
 
-template <int PP>
+template <int PP, int PPB = PP>
 int launch5(const CUtensorMap* tm, bf16* out, int B, int N, int heads, cudaStream_t st) {
     static bool configured = false;
     static int sms = 0;
     if (!configured) {
-        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        DAD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<PP, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         int dev = 0;
         DAD_CHECK_CUDA(cudaGetDevice(&dev));
         DAD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -384,7 +416,7 @@ int launch5(const CUtensorMap* tm, bf16* out, int B, int N, int heads, cudaStrea
     const long long total = static_cast<long long>(B) * heads * cdiv(N, BQ);
     const int grid = static_cast<int>(total < 2LL * sms ? total : 2LL * sms);
     DAD_REQUIRE(cdiv(total, grid) <= MAX_ITEMS_PER_CTA, "attention: %lld work items exceed the per-CTA redo bitmap", total);
-    DAD_CHECK_CUDA(launch_pdl(attention_tc5_kernel<PP>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N,
+    DAD_CHECK_CUDA(launch_pdl(attention_tc5_kernel<PP, PPB>, dim3(grid), dim3(ATT_THREADS), ATT_SMEM, st, tm[0], tm[1], tm[2], out, N,
                               heads * HD, heads, static_cast<int>(total)));
     DAD_CHECK_LAUNCH();
     return DAD_OK;
@@ -407,6 +439,9 @@ int attention_tc5(const bf16* qkv, bf16* out, int B, int N, int heads, int poly_
         case 3: return launch5<3>(tm, out, B, N, heads, st);
         case 4: return launch5<4>(tm, out, B, N, heads, st);
         case 5: return launch5<5>(tm, out, B, N, heads, st);
+        case 40: return launch5<4, 0>(tm, out, B, N, heads, st);   // asymmetric mixes: first / second half of the grid
+        case 50: return launch5<5, 0>(tm, out, B, N, heads, st);
+        case 31: return launch5<3, 1>(tm, out, B, N, heads, st);
         default: return launch5<2>(tm, out, B, N, heads, st);
     }
 }
