@@ -32,7 +32,20 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a sha
 struct Tc2Args {
     Epilogue epi;
     int M, N, num_k_blocks, num_m_tiles, num_n_tiles;  // tiles of 256 x 256
+    // Tail splitting: the last `tiles % pairs` tiles (the partial wave of the persistent grid) are cut along N into `split`
+    // sub-items of 256 x (256 / split) each, so that the partial wave costs 1 / split of a tile time.  Same K loop per
+    // output element, so results are bit-identical to the unsplit schedule.
+    int full_items, split, num_items;
 };
+
+// item -> (tile, first column inside the tile, item width)
+__device__ __forceinline__ void decode_item(const Tc2Args& g, int item, int& tile, int& sub0, int& width) {
+    if (item < g.full_items) { tile = item; sub0 = 0; width = BN; return; }
+    const int t = item - g.full_items;
+    tile = g.full_items + t / g.split;
+    width = BN / g.split;
+    sub0 = (t % g.split) * width;
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -71,7 +84,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ Tc2Args g) {
+                const __grid_constant__ CUtensorMap tmBs, const __grid_constant__ CUtensorMap tmC,
+                const __grid_constant__ Tc2Args g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -90,6 +104,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmB);
+        ptx::prefetch_tmap(&tmBs);
         ptx::prefetch_tmap(&tmC);
     }
     if (warp == 1) {
@@ -116,7 +131,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();  // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
-    const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+    const int num_items = g.num_items;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const int nkb = g.num_k_blocks;
 
@@ -125,17 +140,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // ------------------------------------------------ TMA producer (both CTAs)
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int item = cluster_id; item < num_items; item += num_clusters) {
+                int tile, sub0, width;
+                decode_item(g, item, tile, sub0, width);
                 const int mt = tile / g.num_n_tiles;
                 const int nt = tile - mt * g.num_n_tiles;
                 const int row0 = mt * (2 * BM) + static_cast<int>(rank) * BM;
-                const int nrow0 = nt * BN + static_cast<int>(rank) * BNH;
+                const int nrow0 = nt * BN + sub0 + static_cast<int>(rank) * (width >> 1);   // each CTA stages half of the B rows
+                const bool fullw = width == BN;
+                const uint32_t tx = 2 * (A_STAGE + (width >> 1) * BK * 2);
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     const uint32_t lbar = ptx::smem_u32(&full[stage]) & PEER_MASK;
-                    if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+                    if (leader) ptx::mbar_arrive_expect_tx(&full[stage], tx);
                     tma_load_2d_cg2(sA + stage * A_STAGE, &tmA, lbar, kb * BK, row0);
-                    tma_load_2d_cg2(sB + stage * B_STAGE, &tmB, lbar, kb * BK, nrow0);
+                    tma_load_2d_cg2(sB + stage * B_STAGE, fullw ? &tmB : &tmBs, lbar, kb * BK, nrow0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -145,13 +164,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (leader) {
             // ------------------------------------------------ MMA issuer (leader CTA; warp-uniform loop, one elected lane
             // issues for both SMs; descriptors = constant high word + (address >> 4))
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * BM, BN);
+            constexpr uint32_t idesc_full = ptx::make_idesc_bf16(2 * BM, BN);
             const uint32_t sA_lo = ptx::desc_lo_sw128(ptx::smem_u32(sA)), sB_lo = ptx::desc_lo_sw128(ptx::smem_u32(sB));
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int item = cluster_id; item < num_items; item += num_clusters) {
+                int tile, sub0, width;
+                decode_item(g, item, tile, sub0, width);
+                const uint32_t idesc = width == BN ? idesc_full : ptx::make_idesc_bf16(2 * BM, static_cast<uint32_t>(width));
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
@@ -181,22 +203,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ---------------------------------------------------- epilogue (warps 2..9, both CTAs): TMA store / reduce-add
         constexpr bool F32 = KIND == EK_RES_F32;
         constexpr int CW = F32 ? 32 : 64;
-        constexpr int NCHUNK = BN / CW;
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         const uint32_t tile_stg = ptx::smem_u32(smem + STAGING_OFF) + half * (BM * 128);
         const int r_tile = quarter * 32 + lane;
         const bool issuer = (quarter == 0) && (lane == 0);
         const uint32_t row_addr = tile_stg + r_tile * 128;
-        const int c_lo = half * (NCHUNK / 2), c_hi = c_lo + NCHUNK / 2;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        for (int item = cluster_id; item < num_items; item += num_clusters) {
+            int tile, sub0, width;
+            decode_item(g, item, tile, sub0, width);
             const int mt = tile / g.num_n_tiles;
-            const int n0 = (tile - mt * g.num_n_tiles) * BN;
+            const int n0 = (tile - mt * g.num_n_tiles) * BN + sub0;
             const int row0 = mt * (2 * BM) + static_cast<int>(rank) * BM;
+            // chunks of this item, split over the two column halves (a narrow item may leave half 1 without work)
+            const int nch = width / CW;
+            const int c_lo = half == 0 ? 0 : (nch + 1) / 2, c_hi = half == 0 ? (nch + 1) / 2 : nch;
             ptx::mbar_wait(&tfull[as], aphase);
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+            if (c_lo >= c_hi) {   // nothing to convert for this half: still release the TMEM stage (16 arrivals expected)
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ptx::smem_u32(&tempty[as]) & PEER_MASK);
+            }
 #pragma unroll 1
             for (int c = c_lo; c < c_hi; ++c) {
                 const int col0 = n0 + c * CW;
@@ -263,18 +293,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 template <int KIND>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Tc2Args& a, double flops,
-            cudaStream_t stream) {
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBs, const CUtensorMap& tmC, const Tc2Args& a,
+            double flops, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         DAD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
-    const int tiles = a.num_m_tiles * a.num_n_tiles;
     const int pairs = num_sms() / 2;
-    const int grid = 2 * (tiles < pairs ? tiles : pairs);
+    const int grid = 2 * (a.num_items < pairs ? a.num_items : pairs);
     ProfScope prof(PROF_GEMM_TC, flops, stream);
-    DAD_CHECK_CUDA(launch_pdl(gemm_tc2_kernel<KIND>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, tmC, a));
+    DAD_CHECK_CUDA(launch_pdl(gemm_tc2_kernel<KIND>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmA, tmB, tmBs, tmC, a));
     return DAD_OK;
 }
 
@@ -295,7 +324,20 @@ int gemm_tc2(const GemmProblem& p, cudaStream_t stream) {
     a.num_k_blocks = cdiv(p.K, BK);
     a.num_m_tiles = cdiv(p.M, 2 * BM);
     a.num_n_tiles = p.N / BN;
-    CUtensorMap tmA, tmB, tmC;
+    {   // tail splitting (see Tc2Args): the partial last wave of `rem` tiles becomes rem * split narrower items
+        const int tiles = a.num_m_tiles * a.num_n_tiles, pairs = num_sms() / 2;
+        const int rem = tiles % pairs;
+        static const bool off = getenv("DAD_NO_TAIL_SPLIT") != nullptr;   // A/B switch
+        int split = 1;
+        if (!off && rem > 0 && tiles > pairs) {
+            if (4 * rem <= pairs) split = 4;
+            else if (2 * rem <= pairs) split = 2;
+        }
+        a.split = split;
+        a.full_items = split > 1 ? tiles - rem : tiles;
+        a.num_items = a.full_items + (split > 1 ? rem * split : 0);
+    }
+    CUtensorMap tmA, tmB, tmBs, tmC;
     {
         const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
         const cuuint64_t strides[1] = {(cuuint64_t)p.lda * 2};
@@ -307,6 +349,8 @@ int gemm_tc2(const GemmProblem& p, cudaStream_t stream) {
         const cuuint64_t strides[1] = {(cuuint64_t)p.Kp * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BNH};
         DAD_TRY(make_tmap_bf16(&tmB, p.Wt, 2, dims, strides, box));
+        const cuuint32_t boxs[2] = {(cuuint32_t)BK, (cuuint32_t)(BNH / a.split)};   // B rows per CTA of a split item
+        DAD_TRY(make_tmap_bf16(&tmBs, p.Wt, 2, dims, strides, boxs));
     }
     {
         const bool f32 = kind == EK_RES_F32;
@@ -319,9 +363,9 @@ int gemm_tc2(const GemmProblem& p, cudaStream_t stream) {
     }
     const double flops = 2.0 * p.M * p.N * static_cast<double>(p.K);
     switch (kind) {
-        case EK_BIAS_BF16: return launch2<EK_BIAS_BF16>(tmA, tmB, tmC, a, flops, stream);
-        case EK_GELU_BF16: return launch2<EK_GELU_BF16>(tmA, tmB, tmC, a, flops, stream);
-        default: return launch2<EK_RES_F32>(tmA, tmB, tmC, a, flops, stream);
+        case EK_BIAS_BF16: return launch2<EK_BIAS_BF16>(tmA, tmB, tmBs, tmC, a, flops, stream);
+        case EK_GELU_BF16: return launch2<EK_GELU_BF16>(tmA, tmB, tmBs, tmC, a, flops, stream);
+        default: return launch2<EK_RES_F32>(tmA, tmB, tmBs, tmC, a, flops, stream);
     }
 }
 

@@ -56,7 +56,10 @@ def test_gemm_simt_matches_fp32_matmul(M, N, K):
     assert (out - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("M,N,K", [(1370, 1024, 1024), (2740, 3072, 1024), (785, 384, 384), (1000, 768, 3072)])
+# the last three shapes have more 256 x 256 tiles than SM pairs with a short partial wave: 75 tiles (tail 1 -> four 64-wide
+# items), 104 tiles (tail 30 -> 128-wide halves), 2 x 80 tiles (tail 12 -> quarters) - the tail-splitting schedule of gemm_tc2
+@pytest.mark.parametrize("M,N,K", [(1370, 1024, 1024), (2740, 3072, 1024), (785, 384, 384), (1000, 768, 3072),
+                                   (19200, 256, 128), (26500, 256, 192), (20480, 512, 64)])
 @pytest.mark.parametrize("kind", ["bias_bf16", "gelu_bf16", "res_f32", "res_bf16_relu"])
 def test_gemm_tc_fused_epilogues(M, N, K, kind):
     """The encoder epilogues (compile-time specialised) and a generic run-time one."""
