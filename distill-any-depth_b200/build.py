@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdad_b200.so")
-SOURCES = ["common.cu", "backward.cu", "tmap.cu", "attention_tc.cu", "attention_tc3.cu", "attention_tc5.cu", "attention_tc6.cu", "gemm_tc.cu", "gemm_tc2.cu", "conv_tc2.cu", "gemm_simt.cu", "attention.cu", "elementwise.cu", "imageproc.cu", "losses.cu", "losses_fused.cu", "model.cu", "api.cu"]
+SOURCES = ["common.cu", "backward.cu", "tmap.cu", "attention_tc.cu", "attention_tc3.cu", "attention_tc5.cu", "attention_tc6.cu", "attention_tc7.cu", "gemm_tc.cu", "gemm_tc2.cu", "conv_tc2.cu", "gemm_simt.cu", "attention.cu", "elementwise.cu", "imageproc.cu", "losses.cu", "losses_fused.cu", "model.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]

@@ -87,7 +87,9 @@ int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, 
         const char* ep = getenv("DAD_ATT_POLY5");      // pairs of every 8 exponentiated on the FMA pipe (0, 2, 3, 4, 5)
         const int variant = ev ? atoi(ev) : 5;
         const int poly = ep ? atoi(ep) : 2;
-        if (variant == 6)
+        if (variant == 7 || variant == 8)   // 8: two single-thread MMA issuers
+            DAD_TRY(attention_tc7(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, poly, variant == 8, st));
+        else if (variant == 6)
             DAD_TRY(attention_tc6(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, poly, st));
         else if (variant == 3)
             DAD_TRY(attention_tc3(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B, N, heads, st));

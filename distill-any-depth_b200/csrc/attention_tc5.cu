@@ -43,6 +43,7 @@ constexpr int KV_STAGES = 4;
 constexpr int ATT_THREADS = 192;
 constexpr int TMEM_COLS = 256;
 constexpr int S_COL = 0, O_COL = 128, L_COL = 192;
+static_assert(L_COL == O_COL + HD, "the row sums are columns 64..79 of the N = 80 accumulator [O | L]");
 constexpr int MAX_ITEMS_PER_CTA = 2048;   // redo bitmap: one bit per item of this CTA
 constexpr int ATT_SMEM = 2 * Q_BYTES + 2 * KV_STAGES * KV_BYTES + ONES_BYTES + 512 + MAX_ITEMS_PER_CTA / 8 + 1024;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -200,64 +201,69 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
     } else if (warp == 5) {
         // -------------------------------------------------------------------- MMA issuer
+        // This warp's instruction stream is on the critical path of every key tile (ncu, round 2: it waited for P only
+        // 22 % of the time), so it is kept short: O and the row sums L come from ONE N = 80 MMA per 16 keys (B = [V | 1]:
+        // the second 64-column block of the MN-major operand is the all-ones tile, reached through the descriptor's
+        // leading-dimension offset), every barrier of a tile is waited for up front, and one elected block issues
+        // P V_g, Q K_{g+2}^T and their commits.
         constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BQ, BKV);
-        constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_bmn(BQ, HD);
-        constexpr uint32_t idesc_l = ptx::make_idesc_bf16(BQ, 16);
+        constexpr uint32_t idesc_pvl = ptx::make_idesc_bf16_bmn(BQ, HD + 16);
         constexpr uint32_t kDescHiMn = (1024u >> 4) | (1u << 14) | (2u << 29);
         const uint32_t q_lo0 = ptx::desc_lo_sw128(ptx::smem_u32(sQ));
         const uint32_t k_lo0 = ptx::desc_lo_sw128(ptx::smem_u32(sK));
-        const uint32_t v_lo0 = ptx::desc_lo_mn_sw128(ptx::smem_u32(sV));
-        const uint32_t one_lo = ptx::desc_lo_sw128(ptx::smem_u32(sOnes));
-        int g0 = 0, it = 0;
-        auto issue_qk = [&](int g, uint32_t q_lo) {  // S[g & 1] = Q K_g^T
-            const int s = g % KV_STAGES;
-            ptx::mbar_wait(&k_full[s], (g / KV_STAGES) & 1);
-            ptx::tc_fence_after();
-            const uint32_t k_lo = k_lo0 + s * (KV_BYTES >> 4);
-            if (ptx::elect_one()) {
+        const uint32_t v_a0 = (ptx::smem_u32(sV) & 0x3FFFF) >> 4;
+        const uint32_t ones_a = (ptx::smem_u32(sOnes) & 0x3FFFF) >> 4;
+        uint32_t g0 = 0, it = 0;
+        auto qk4 = [&](uint32_t g, uint32_t q_lo) {  // (elected thread) S[g & 1] = Q K_g^T
+            const uint32_t k_lo = k_lo0 + (g % KV_STAGES) * (KV_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    ptx::umma_bf16(tmem + S_COL + (g & 1) * BKV, ptx::make_desc(q_lo + 2 * k, ptx::kDescHiSw128),
-                                   ptx::make_desc(k_lo + 2 * k, ptx::kDescHiSw128), idesc_qk, k != 0 ? 1u : 0u);
-                ptx::umma_commit(&s_full[g & 1]);
-            }
-            __syncwarp();
+            for (int k = 0; k < HD / 16; ++k)
+                ptx::umma_bf16(tmem + S_COL + (g & 1) * BKV, ptx::make_desc(q_lo + 2 * k, ptx::kDescHiSw128),
+                               ptx::make_desc(k_lo + 2 * k, ptx::kDescHiSw128), idesc_qk, k != 0 ? 1u : 0u);
+            ptx::umma_commit(&s_full[g & 1]);
         };
         auto mma_item = [&]() {
-            const int qb = it & 1;
+            const uint32_t qb = it & 1;
             const uint32_t q_lo = q_lo0 + qb * (Q_BYTES >> 4);
+            const uint32_t Tu = static_cast<uint32_t>(T);
             ptx::mbar_wait(&q_full[qb], (it >> 1) & 1);
             // the first two S tiles of an item are issued while the softmax warps may still be storing the previous
             // item's output: S[g & 1] only has to be past P V of tile g - 2 (in-order pipe); O / L are not touched here
-            issue_qk(g0, q_lo);
-            if (T > 1) issue_qk(g0 + 1, q_lo);
-            for (int j = 0; j < T; ++j) {
-                const int g = g0 + j;
-                const int s = g % KV_STAGES;
+            ptx::mbar_wait(&k_full[g0 % KV_STAGES], (g0 / KV_STAGES) & 1);
+            if (Tu > 1) ptx::mbar_wait(&k_full[(g0 + 1) % KV_STAGES], ((g0 + 1) / KV_STAGES) & 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                qk4(g0, q_lo);
+                if (Tu > 1) qk4(g0 + 1, q_lo);
+            }
+            __syncwarp();
+            for (uint32_t j = 0; j < Tu; ++j) {
+                const uint32_t g = g0 + j;
+                const uint32_t st = g % KV_STAGES;
+                const bool more = j + 2 < Tu;
                 ptx::mbar_wait(&p_full[g & 1], (g >> 1) & 1);       // P_g written in place of S[g & 1]; for j == 0 also:
-                ptx::mbar_wait(&v_full[s], (g / KV_STAGES) & 1);    // the previous item's O / L have been read out
+                ptx::mbar_wait(&v_full[st], (g / KV_STAGES) & 1);   // the previous item's O / L have been read out
+                if (more) ptx::mbar_wait(&k_full[(g + 2) % KV_STAGES], ((g + 2) / KV_STAGES) & 1);
                 ptx::tc_fence_after();
-                const uint32_t v_lo = v_lo0 + s * (KV_BYTES >> 4);
-                const uint32_t tP = tmem + S_COL + (g & 1) * BKV;
                 if (ptx::elect_one()) {
+                    const uint32_t tP = tmem + S_COL + (g & 1) * BKV;
+                    const uint32_t v_a = v_a0 + st * (KV_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k)   // O += P V: 16 keys = 16 rows of 128 B per k-step
-                        ptx::umma_bf16_ts(tmem + O_COL, tP + k * 8, ptx::make_desc(v_lo + k * (16 * 128 >> 4), kDescHiMn),
-                                          idesc_pv, (j | k) != 0 ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k)   // L += P 1: the row sums, on the tensor core
-                        ptx::umma_bf16_ts(tmem + L_COL, tP + k * 8, ptx::make_desc(one_lo + 2 * k, ptx::kDescHiSw128),
-                                          idesc_l, (j | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit(&kv_empty[s]);                  // K_g / V_g stage free once these retire
-                    if (j == T - 1) {
+                    for (int k = 0; k < BKV / 16; ++k) {   // [O | L] += P [V | 1]: 16 keys = 16 rows of 128 B per k-step
+                        const uint32_t a = v_a + k * (16 * 128 >> 4);
+                        ptx::umma_bf16_ts(tmem + O_COL, tP + k * 8, ptx::make_desc(a | ((ones_a - a) << 16), kDescHiMn),
+                                          idesc_pvl, (j | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&kv_empty[st]);                 // K_g / V_g stage free once these retire
+                    if (more) qk4(g + 2, q_lo);                      // executes after P V_g (in-order pipe): S[g & 1] is free
+                    if (j == Tu - 1) {
                         ptx::umma_commit(done);
                         ptx::umma_commit(&q_empty[qb]);              // every Q K^T of this item has retired
                     }
                 }
                 __syncwarp();
-                if (j + 2 < T) issue_qk(g + 2, q_lo);                // executes after P V_g (in-order pipe): S[g & 1] is free
             }
-            g0 += T;
+            g0 += Tu;
             ++it;
         };
         for (int i = 0; i < n_mine; ++i) mma_item();

@@ -33,6 +33,8 @@ int attention_tc3(const bf16* qkv, bf16* out, int B, int N, int heads, cudaStrea
 int attention_tc5(const bf16* qkv, bf16* out, int B, int N, int heads, int poly_pairs, cudaStream_t st);
 // same with three in-place score buffers and the row sums in the softmax threads (attention_tc6.cu)
 int attention_tc6(const bf16* qkv, bf16* out, int B, int N, int heads, int poly_pairs, cudaStream_t st);
+// one CTA per SM, two softmax warpgroups alternating the key tiles of one item (attention_tc7.cu)
+int attention_tc7(const bf16* qkv, bf16* out, int B, int N, int heads, int poly_pairs, int split_issuers, cudaStream_t st);
 int attention(const void* qkv, void* out, int is_bf16, int B, int N, int heads, cudaStream_t st);
 
 }  // namespace dad

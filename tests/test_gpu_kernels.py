@@ -158,7 +158,7 @@ def test_conv_stride2_matches_conv2d(B, H, W, C, Co):
 
 
 # 5 = attention_tc5.cu (the default), 2 / 3 = the round-1 kernels kept for A/B measurements
-_ATT_VARIANTS = {5: "tc5", 6: "tc6_three_buffers", 2: "pipelined2cta", 3: "serial4cta"}
+_ATT_VARIANTS = {5: "tc5", 6: "tc6_three_buffers", 7: "tc7_two_groups", 8: "tc7_split_issuers", 2: "pipelined2cta", 3: "serial4cta"}
 
 
 @pytest.fixture(params=list(_ATT_VARIANTS), ids=list(_ATT_VARIANTS.values()))
@@ -210,7 +210,7 @@ def test_attention_lazy_rescale_path(att_variant):
     assert (out.float() - ref).abs().max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("variant", [5, 6])
+@pytest.mark.parametrize("variant", [5, 6, 7, 8])
 @pytest.mark.parametrize("poly", [0, 2, 3, 4, 5])
 def test_attention_tc5_overflow_falls_back_to_exact_passes(poly, variant, monkeypatch):
     """attention_tc5 exponentiates against the FIRST key tile's row maximum; later logits more than 127 log2 units above
