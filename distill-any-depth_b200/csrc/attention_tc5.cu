@@ -113,9 +113,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES);
     uint64_t* q_full = bars;                          // [2]
     uint64_t* q_empty = bars + 2;                     // [2]
-    uint64_t* k_full = bars + 4;                      // [KV_STAGES]
-    uint64_t* v_full = k_full + KV_STAGES;            // [KV_STAGES]
-    uint64_t* kv_empty = v_full + KV_STAGES;          // [KV_STAGES]
+    uint64_t* kv_full = bars + 4;                     // [KV_STAGES]: K_g and V_g of a stage land on ONE barrier
+    uint64_t* kv_empty = kv_full + KV_STAGES;         // [KV_STAGES]
     uint64_t* s_full = kv_empty + KV_STAGES;          // [2]
     uint64_t* p_full = s_full + 2;                    // [2], 128 arrivals
     uint64_t* done = p_full + 2;                      // last P V / L of an item retired
@@ -148,8 +147,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 ptx::mbar_init(&p_full[i], 128);
             }
             for (int i = 0; i < KV_STAGES; ++i) {
-                ptx::mbar_init(&k_full[i], 1);
-                ptx::mbar_init(&v_full[i], 1);
+                ptx::mbar_init(&kv_full[i], 1);
                 ptx::mbar_init(&kv_empty[i], 1);
             }
             ptx::mbar_init(done, 1);
@@ -184,10 +182,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 for (int j = 0; j < T; ++j, ++g) {
                     const int s = g % KV_STAGES;
                     ptx::mbar_wait(&kv_empty[s], ((g / KV_STAGES) & 1) ^ 1);
-                    ptx::mbar_arrive_expect_tx(&k_full[s], KV_BYTES);
-                    ptx::tma_load_3d(sK + s * KV_BYTES, &tmK, &k_full[s], h * HD, j * BKV, b);
-                    ptx::mbar_arrive_expect_tx(&v_full[s], KV_BYTES);
-                    ptx::tma_load_3d(sV + s * KV_BYTES, &tmV, &v_full[s], h * HD, j * BKV, b);
+                    ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
+                    ptx::tma_load_3d(sK + s * KV_BYTES, &tmK, &kv_full[s], h * HD, j * BKV, b);
+                    ptx::tma_load_3d(sV + s * KV_BYTES, &tmV, &kv_full[s], h * HD, j * BKV, b);
                 }
                 ++it;
             };
@@ -214,13 +211,24 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t v_a0 = (ptx::smem_u32(sV) & 0x3FFFF) >> 4;
         const uint32_t ones_a = (ptx::smem_u32(sOnes) & 0x3FFFF) >> 4;
         uint32_t g0 = 0, it = 0;
-        auto qk4 = [&](uint32_t g, uint32_t q_lo) {  // (elected thread) S[g & 1] = Q K_g^T
+        auto qk4 = [&](uint32_t g, uint32_t q_lo) {  // (elected thread) S[g & 1] = Q K_g^T; the caller waited for kv_full
             const uint32_t k_lo = k_lo0 + (g % KV_STAGES) * (KV_BYTES >> 4);
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k)
                 ptx::umma_bf16(tmem + S_COL + (g & 1) * BKV, ptx::make_desc(q_lo + 2 * k, ptx::kDescHiSw128),
                                ptx::make_desc(k_lo + 2 * k, ptx::kDescHiSw128), idesc_qk, k != 0 ? 1u : 0u);
             ptx::umma_commit(&s_full[g & 1]);
+        };
+        auto pvl4 = [&](uint32_t g, bool first) {   // (elected thread) [O | L] (+)= P_g [V_g | 1]; frees the K / V stage
+            const uint32_t tP = tmem + S_COL + (g & 1) * BKV;
+            const uint32_t v_a = v_a0 + (g % KV_STAGES) * (KV_BYTES >> 4);
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k) {          // 16 keys = 16 rows of 128 B per k-step
+                const uint32_t a = v_a + k * (16 * 128 >> 4);
+                ptx::umma_bf16_ts(tmem + O_COL, tP + k * 8, ptx::make_desc(a | ((ones_a - a) << 16), kDescHiMn), idesc_pvl,
+                                  (first && k == 0) ? 0u : 1u);
+            }
+            ptx::umma_commit(&kv_empty[g % KV_STAGES]);
         };
         auto mma_item = [&]() {
             const uint32_t qb = it & 1;
@@ -229,34 +237,32 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             ptx::mbar_wait(&q_full[qb], (it >> 1) & 1);
             // the first two S tiles of an item are issued while the softmax warps may still be storing the previous
             // item's output: S[g & 1] only has to be past P V of tile g - 2 (in-order pipe); O / L are not touched here
-            ptx::mbar_wait(&k_full[g0 % KV_STAGES], (g0 / KV_STAGES) & 1);
-            if (Tu > 1) ptx::mbar_wait(&k_full[(g0 + 1) % KV_STAGES], ((g0 + 1) / KV_STAGES) & 1);
+            ptx::mbar_wait(&kv_full[g0 % KV_STAGES], (g0 / KV_STAGES) & 1);
+            if (Tu > 1) ptx::mbar_wait(&kv_full[(g0 + 1) % KV_STAGES], ((g0 + 1) / KV_STAGES) & 1);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
                 qk4(g0, q_lo);
                 if (Tu > 1) qk4(g0 + 1, q_lo);
             }
             __syncwarp();
-            for (uint32_t j = 0; j < Tu; ++j) {
-                const uint32_t g = g0 + j;
-                const uint32_t st = g % KV_STAGES;
-                const bool more = j + 2 < Tu;
-                ptx::mbar_wait(&p_full[g & 1], (g >> 1) & 1);       // P_g written in place of S[g & 1]; for j == 0 also:
-                ptx::mbar_wait(&v_full[st], (g / KV_STAGES) & 1);   // the previous item's O / L have been read out
-                if (more) ptx::mbar_wait(&k_full[(g + 2) % KV_STAGES], ((g + 2) / KV_STAGES) & 1);
+            uint32_t g = g0;
+            for (const uint32_t gs = g0 + Tu - 2; static_cast<int32_t>(gs - g) > 0; ++g) {   // tiles with a Q K^T two ahead
+                ptx::mbar_wait(&p_full[g & 1], (g >> 1) & 1);       // P_g written in place of S[g & 1]; for the first
+                                                                    // tile also: the previous item's O / L have been read out
+                ptx::mbar_wait(&kv_full[(g + 2) % KV_STAGES], ((g + 2) / KV_STAGES) & 1);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
-                    const uint32_t tP = tmem + S_COL + (g & 1) * BKV;
-                    const uint32_t v_a = v_a0 + st * (KV_BYTES >> 4);
-#pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k) {   // [O | L] += P [V | 1]: 16 keys = 16 rows of 128 B per k-step
-                        const uint32_t a = v_a + k * (16 * 128 >> 4);
-                        ptx::umma_bf16_ts(tmem + O_COL, tP + k * 8, ptx::make_desc(a | ((ones_a - a) << 16), kDescHiMn),
-                                          idesc_pvl, (j | k) != 0 ? 1u : 0u);
-                    }
-                    ptx::umma_commit(&kv_empty[st]);                 // K_g / V_g stage free once these retire
-                    if (more) qk4(g + 2, q_lo);                      // executes after P V_g (in-order pipe): S[g & 1] is free
-                    if (j == Tu - 1) {
+                    pvl4(g, g == g0);
+                    qk4(g + 2, q_lo);                               // executes after P V_g (in-order pipe): S[g & 1] is free
+                }
+                __syncwarp();
+            }
+            for (; g != g0 + Tu; ++g) {                             // the last two tiles (one if T == 1)
+                ptx::mbar_wait(&p_full[g & 1], (g >> 1) & 1);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    pvl4(g, g == g0);
+                    if (g + 1 == g0 + Tu) {
                         ptx::umma_commit(done);
                         ptx::umma_commit(&q_empty[qb]);              // every Q K^T of this item has retired
                     }
