@@ -167,4 +167,9 @@ int dad_attention(const void* qkv, void* out, int B, int N, int heads, int mode,
     return dad::attention(qkv, out, mode == 0, B, N, heads, ST(stream));
 }
 
+int dad_layernorm(const float* in, const float* weight, const float* bias, void* out, float* out_f32, long long rows, int D,
+                  int out_period, int in_period, int in_offset, float eps, int mode, void* stream) {
+    return dad::layernorm(in, weight, bias, out, mode == 0, out_f32, rows, D, out_period, in_period, in_offset, eps, ST(stream));
+}
+
 }  // extern "C"

@@ -52,6 +52,9 @@ __global__ void __launch_bounds__(256) patch_im2col_kernel(const float* x, T* A,
 
 // ---------------------------------------------------------------- LayerNorm (K3, K9)
 // one warp per output row; in row = (r / out_period) * in_period + in_offset + r % out_period
+// (Round 2 measured two persistent streaming restructurings of this kernel on the headline step, bit-identical results:
+// a producer thread filling an mbarrier ring with 64 KB cp.async.bulk copies - 0.47 of the HBM peak - and per-warp rings
+// of 16-byte cp.async copies two rows ahead, 2 CTAs / SM - 0.62; this one-shot kernel: 0.70 - 0.72.  Kept as is.)
 template <typename T, int VPT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* in, const float* w, const float* bvec, T* out,
                                                         float* out_f32, long long rows, int D, int out_period,

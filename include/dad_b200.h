@@ -210,6 +210,12 @@ int dad_conv_nhwc_ex(const void* in, const void* Wpacked, const float* bias, flo
                      int Co, int taps, int stride, int mode, void* stream);
 /* attention over qkv [B*N, 3*heads*64] (q pre-scaled) -> out [B*N, heads*64]; bf16 bits (mode 0) or fp32. */
 int dad_attention(const void* qkv, void* out, int B, int N, int heads, int mode, void* stream);
+/* LayerNorm over the last dimension (dinov2.py:213-214 norm1 / norm2 of every block, :304-305 the shared final norm;
+ * torch.nn.LayerNorm, biased variance, eps inside the square root).  in: fp32 rows of D; output row r reads input row
+ * (r / out_period) * in_period + in_offset + r % out_period (the final norm drops the class token this way).  out (bf16 bits
+ * in mode 0, fp32 in mode 1) and / or out_f32 may be NULL.  Kernel-level test entry (the model calls the same function). */
+int dad_layernorm(const float* in, const float* weight, const float* bias, void* out, float* out_f32, long long rows, int D,
+                  int out_period, int in_period, int in_offset, float eps, int mode, void* stream);
 
 /* ------------------------------------------------------------------ measurement hooks (bench.py)
  * Launch counter of this library's kernels, and optional per-kernel-class CUDA-event timing

@@ -158,6 +158,32 @@ def test_conv_stride2_matches_conv2d(B, H, W, C, Co):
 
 
 # 5 = attention_tc5.cu (the default), 2 / 3 = the round-1 kernels kept for A/B measurements
+@pytest.mark.parametrize("rows,D,period", [(2740, 1024, None), (4 * 1369, 1024, (1369, 1370, 1)), (2049, 768, None),
+                                            (2 * 1024, 384, (1024, 1025, 1)), (2100, 1536, None), (100, 1024, None)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_layernorm_kernel(rows, D, period, mode):
+    """dinov2.py:213-214 / :304-305 (torch.nn.LayerNorm): torch.layer_norm within fp32 / bf16 rounding; the period arguments
+    drop the class-token row of every image, as the shared final norm of the intermediate layers does."""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(rows + D)
+    out_period, in_period, in_offset = period if period else (rows, rows, 0)
+    in_rows = (rows // out_period) * in_period if period else rows
+    x = torch.randn(in_rows, D, device="cuda", generator=g) * 3 + torch.randn(in_rows, 1, device="cuda", generator=g)
+    w = torch.randn(D, device="cuda", generator=g)
+    b = torch.randn(D, device="cuda", generator=g)
+    out = torch.full((rows, D), float("nan"), device="cuda", dtype=torch.bfloat16 if mode == 0 else torch.float32)
+    out32 = torch.full((rows, D), float("nan"), device="cuda")
+    L.check(lib.dad_layernorm(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(out), L.ptr(out32), rows, D, out_period, in_period,
+                              in_offset, 1e-6, mode, L.stream_ptr()), "dad_layernorm")
+    torch.cuda.synchronize()
+    xs = x.view(-1, in_period, D)[:, in_offset:in_offset + out_period].reshape(rows, D) if period else x
+    ref = torch.nn.functional.layer_norm(xs, (D,), w, b, 1e-6)
+    assert (out32 - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    tol = 8e-3 if mode == 0 else 2e-5
+    assert (out.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
 _ATT_VARIANTS = {5: "tc5", 6: "tc6_three_buffers", 7: "tc7_two_groups", 8: "tc7_split_issuers", 2: "pipelined2cta", 3: "serial4cta"}
 
 
