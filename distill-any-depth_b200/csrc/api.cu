@@ -125,6 +125,18 @@ int dad_gemm_splitk(const void* A, const void* W, const float* zeros, const floa
     return dad::gemm_tc(p, ST(stream));
 }
 
+int dad_gemm_shifted(const void* A, const void* W, const float* zeros, const float* ones, float* out, int M, int rows, int K,
+                     int lda, int taps, int ld, const int* offsets, int ksplit, void* stream) {
+    if (!offsets || taps < 1 || taps > 9) return dad::set_error(DAD_ERR_INVALID, "dad_gemm_shifted: 1..9 taps with their offsets");
+    dad::GemmProblem p;
+    p.A = A; p.M = M; p.K = K; p.lda = lda; p.Wt = W; p.N = taps * ld; p.Kp = lda;
+    p.shift_taps = taps; p.shift_rows = rows; p.shift_ld = ld;
+    for (int t = 0; t < taps; ++t) p.shift_off[t] = offsets[t];   // (all views start at row 0 here)
+    p.epi.bias = zeros; p.epi.gamma = ones; p.epi.res1 = out; p.epi.out = out; p.epi.ldc = p.N;
+    p.ksplit = ksplit;
+    return dad::gemm_tc(p, ST(stream));
+}
+
 int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
                   int Co, int taps, int mode, void* stream) {
     dad::GemmProblem p;

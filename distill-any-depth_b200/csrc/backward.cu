@@ -370,13 +370,15 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const bf16* in, long
 }
 
 // out[(c * taps + tap)][p] = window(X)[p, tap, c], p = output pixel (b, oy, ox); 0 for P <= p < Pp and outside the image
+// taps == 1 with (shift_y, shift_x) and a larger (Ho, Wo) frame writes the channel-major copy of X over ZERO-PADDED pixel
+// space: frame pixel (oy, ox) holds X(oy - shift_y, ox - shift_x)
 __global__ void __launch_bounds__(256) im2colT_kernel(const bf16* X, int H, int W, int Ci, int taps, int stride, int Ho, int Wo,
-                                                      long long P, bf16* out, long long Pp) {
+                                                      long long P, bf16* out, long long Pp, int shift_y, int shift_x) {
     __shared__ T64 s;
     const long long p0 = static_cast<long long>(blockIdx.x) * 64;
     const int c0 = blockIdx.y * 64, tap = blockIdx.z;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int dy = taps == 9 ? tap / 3 - 1 : 0, dx = taps == 9 ? tap % 3 - 1 : 0;
+    const int dy = taps == 9 ? tap / 3 - 1 : -shift_y, dx = taps == 9 ? tap % 3 - 1 : -shift_x;
     const long long hw = static_cast<long long>(Ho) * Wo;
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
@@ -905,15 +907,33 @@ int transpose_pad_batched(const void* in, long long ld, int R, int C, void* out,
     return DAD_OK;
 }
 
+// dW[(co * Ci + ci) * taps + t] += S[co * (taps * ld) + t * ld + ci]: the (tap, ci)-ordered result of the shifted-view
+// weight-gradient GEMM back into the reference's [Co, Ci, kh, kw] layout
+__global__ void __launch_bounds__(256) wgrad_unshift_kernel(const float* S, float* dW, int Co, int Ci, int taps, int ld) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= Co * Ci * taps) return;
+    const int t = i % taps, ci = (i / taps) % Ci, co = i / (taps * Ci);
+    dW[i] += S[static_cast<long long>(co) * taps * ld + t * ld + ci];
+}
+
+int wgrad_unshift(const float* S, float* dW, int Co, int Ci, int taps, int ld, cudaStream_t st) {
+    DAD_REQUIRE(S && dW && Co > 0 && Ci > 0 && taps > 0 && ld >= Ci, "wgrad_unshift: bad arguments");
+    debug_label("wgrad_unshift");
+    wgrad_unshift_kernel<<<cdiv(Co * Ci * taps, 256), 256, 0, st>>>(S, dW, Co, Ci, taps, ld);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
 int im2colT(const void* X, int B, int H, int W, int Ci, int taps, int stride, int Ho, int Wo, void* out, long long Pp,
-            cudaStream_t st) {
+            cudaStream_t st, int shift_y, int shift_x) {
     const long long P = static_cast<long long>(B) * Ho * Wo;
     DAD_REQUIRE(X && out && Pp >= P && (taps == 1 || taps == 9) && Ci % 2 == 0 && Pp % 2 == 0, "im2colT: bad arguments");
     const dim3 grid(static_cast<unsigned>(cdivl(Pp, 64)), cdiv(Ci, 64), taps);
     debug_label("im2colT");
     ProfScope prof(PROF_ELEM, static_cast<double>(Pp) * Ci * taps * 4, st);
+    DAD_REQUIRE((shift_y == 0 && shift_x == 0) || taps == 1, "im2colT: the padded-space copy is a single-tap operation");
     im2colT_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(X), H, W, Ci, taps, stride, Ho, Wo, P,
-                                         reinterpret_cast<bf16*>(out), Pp);
+                                         reinterpret_cast<bf16*>(out), Pp, shift_y, shift_x);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

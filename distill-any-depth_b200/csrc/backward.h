@@ -55,7 +55,9 @@ int transpose_pad(const void* in, long long ld, int R, int C, void* out, int Rp,
 int transpose_pad_batched(const void* in, long long ld, int R, int C, void* out, int Rp, int Z, long long zin, long long zout,
                           cudaStream_t st);
 // bf16 only: out[(c*taps + tap)][p] = window(X)[p, tap, c] over output pixels p (zero padded to Pp columns)
-int im2colT(const void* X, int B, int H, int W, int Ci, int taps, int stride, int Ho, int Wo, void* out, long long Pp, cudaStream_t st);
+int im2colT(const void* X, int B, int H, int W, int Ci, int taps, int stride, int Ho, int Wo, void* out, long long Pp, cudaStream_t st,
+            int shift_y = 0, int shift_x = 0);
+int wgrad_unshift(const float* S, float* dW, int Co, int Ci, int taps, int ld, cudaStream_t st);
 // w [N][K] fp32 -> out [K][Np] bf16
 int pack_linear_T(const float* w, void* out, int N, int K, int Np, cudaStream_t st);
 int head1x1_any(const void* in, int bf, const float* w, const float* bias, float* out, long long P, cudaStream_t st);

@@ -65,6 +65,15 @@ struct GemmProblem {
     long long a_sh = 0, a_sb = 0, w_sh = 0, w_sb = 0;
     int w_rows = 0;
     long long ldw = 0;        // batched only: elements between rows of Wt (0 = Kp)
+    // gemm_tc, linear split-K only: the N rows of the B operand are `shift_taps` SHIFTED VIEWS of one [shift_rows, Kp] matrix
+    // Wt: output column n = tap * shift_ld + r reads row shift_row[tap] + r of Wt at K coordinate k + shift_off[tap] (rows >=
+    // shift_rows and coordinates outside [0, Kp) read as zero).  N = shift_taps * shift_ld, shift_ld % 128 == 0, every
+    // shift_off a multiple of 8 (TMA needs a 16-byte aligned box start in the contiguous dimension - measured: an odd offset
+    // raises an illegal-instruction fault).  This is the 3x3 convolution weight gradient over zero-padded pixel space, where
+    // a vertical tap is a constant offset (train.inl conv_wgrad).
+    int shift_taps = 0, shift_rows = 0, shift_ld = 0;
+    int shift_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int shift_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long c_row_b = 0, c_row_h = 0;
     int c_col_h = 0;
     Epilogue epi;

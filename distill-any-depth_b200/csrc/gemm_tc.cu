@@ -46,6 +46,7 @@ struct TcArgs {
     int ksplit, kb_per_split;  // split-K (linear + TMA reduce-add epilogue only): work item = (k slice, tile)
     int batch_h, mt_per_batch, rows_per_batch, c_col_h;   // batched linear problems (batch_h > 0): m tile -> (image, head, local tile)
     long long c_row_b, c_row_h;
+    int shift_ld, shift_off[9], shift_row[9];   // B rows are shifted views of one matrix (GemmProblem::shift_*); 0 = off
     double flops;           // algorithmic 2*M*N*K of this launch (host-side bookkeeping only)
 };
 
@@ -145,6 +146,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int kb0 = ks * g.kb_per_split, kb1 = min(nkb, kb0 + g.kb_per_split);
                 const int mt = tile / g.num_n_tiles;
                 const int n0 = (tile - mt * g.num_n_tiles) * BN;
+                int brow = n0, bk = 0;   // B operand: first row / K-coordinate offset of this tile
+                if (g.shift_ld) {
+                    const int tap = n0 / g.shift_ld;
+                    brow = g.shift_row[tap] + n0 - tap * g.shift_ld;
+                    bk = g.shift_off[tap];
+                }
                 int b = 0, y0 = 0, x0 = 0;
                 if (g.conv) {
                     const int per_img = g.tiles_x * g.tiles_y;
@@ -190,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else {
                         ptx::tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, mt * BM);
                     }
-                    ptx::tma_load_2d(sB + stage * C::B_STAGE_BYTES, &tmB, &full[stage], kb * BK, n0);
+                    ptx::tma_load_2d(sB + stage * C::B_STAGE_BYTES, &tmB, &full[stage], kb * BK + bk, brow);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 }
@@ -577,6 +584,18 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     a.ksplit = 1;
     int bn = pick_bn(p.N);
     if (p.ksplit > 1 && bn < 128) bn = 128;   // split-K needs the TMA reduce-add epilogue (wide tiles only)
+    if (p.shift_taps) {
+        DAD_REQUIRE(!p.conv && p.batch_h == 0 && p.ksplit > 1 && p.shift_taps <= 9 && p.shift_rows > 0 && p.shift_ld % 128 == 0 &&
+                        p.N == p.shift_taps * p.shift_ld,
+                    "gemm_tc: bad shifted-view problem");
+        bn = 128;   // a tile must not straddle two taps
+        a.shift_ld = p.shift_ld;
+        for (int t = 0; t < 9; ++t) {
+            DAD_REQUIRE(p.shift_off[t] % 8 == 0 && p.shift_row[t] >= 0, "gemm_tc: shifted views need 16-byte aligned offsets");
+            a.shift_off[t] = p.shift_off[t];
+            a.shift_row[t] = p.shift_row[t];
+        }
+    }
     if (p.epi.head_out) {
         DAD_REQUIRE(p.N == 32 && p.epi.bias && p.epi.head_w, "gemm_tc: fused head needs N == 32, bias and head_w");
         bn = 32;
@@ -671,7 +690,7 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bn, 1, 1};
         DAD_TRY(make_tmap(&tmB, 0, p.Wt, 4, dims, strides, box));
     } else {
-        const cuuint64_t dims[2] = {(cuuint64_t)p.Kp, (cuuint64_t)p.N};
+        const cuuint64_t dims[2] = {(cuuint64_t)p.Kp, (cuuint64_t)(p.shift_taps ? p.shift_rows : p.N)};
         const cuuint64_t strides[1] = {(cuuint64_t)p.Kp * 2};
         const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
         DAD_TRY(make_tmap_bf16(&tmB, p.Wt, 2, dims, strides, box));

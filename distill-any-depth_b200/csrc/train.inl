@@ -326,8 +326,49 @@ struct Trainer {
             g.cmap = 1;
             return sgemm(g, st);
         }
-        // rows of the im2col^T operand are ordered (ci, tap), so the GEMM output [Co][Ci*taps] IS the weight layout
         const size_t mk = ar.used;
+        static const bool wgrad_im2col = getenv("DAD_WGRAD_IM2COL") != nullptr;   // A/B switch: materialised 9x operand
+        if (taps == 9 && stride == 1 && Ho == Hin && Wo == Win && !wgrad_im2col) {
+            // 3x3 / stride 1: no 9x im2col operand.  Both operands are channel-major copies over ZERO-PADDED pixel space
+            // q = (b, y + 1, x + 1) of an (H + 2) x Wp frame (Wp = W + 2 rounded up to 8): there a vertical tap is the constant
+            // offset (dy - 1) * Wp, which TMA applies as a shifted K coordinate of ONE matrix (GemmProblem::shift_*); the
+            // horizontal taps would be offsets of +-1 element, which TMA cannot fetch (the box start must be 16-byte aligned),
+            // so X is written three times, pre-shifted by dx.  dY is zero on the frame, which removes every product the
+            // convolution's zero padding does not contain.  The GEMM result is (tap, ci)-ordered; wgrad_unshift adds it
+            // into the [Co, Ci, 3, 3] gradient.
+            const int Wp = rup(Win + 2, 8);
+            const long long Q = static_cast<long long>(B) * (Hin + 2) * Wp;
+            const int Qp = rup(Q, 64);
+            const int CiP = rup(Ci, 128);
+            void* dOt = ar.bytes(static_cast<size_t>(Co) * Qp * 2);
+            bf16* Xt = reinterpret_cast<bf16*>(ar.bytes(static_cast<size_t>(3) * CiP * Qp * 2));
+            float* S = ar.f(static_cast<size_t>(Co) * 9 * CiP);
+            if (!dry) {
+                DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
+                DAD_REQUIRE(9 * CiP <= 16384, "backward: weight-gradient width %d exceeds the epilogue vectors", 9 * CiP);
+                DAD_TRY(im2colT(dOut, B, Hin, Win, Co, 1, 1, Hin + 2, Wp, dOt, Qp, st, 1, 1));
+                for (int dx = 0; dx < 3; ++dx) {   // block dx, frame pixel (oy, ox) = X(oy - 1, ox - 1 + dx - 1)
+                    bf16* blk = Xt + static_cast<size_t>(dx) * CiP * Qp;
+                    DAD_TRY(im2colT(X, B, Hin, Win, Ci, 1, 1, Hin + 2, Wp, blk, Qp, st, 1, 2 - dx));
+                    if (CiP > Ci) DAD_CHECK_CUDA(cudaMemsetAsync(blk + static_cast<size_t>(Ci) * Qp, 0, static_cast<size_t>(CiP - Ci) * Qp * 2, st));
+                }
+                DAD_CHECK_CUDA(cudaMemsetAsync(S, 0, static_cast<size_t>(Co) * 9 * CiP * 4, st));
+                GemmProblem p;
+                p.A = dOt; p.M = Co; p.K = static_cast<int>(Q); p.lda = Qp; p.Wt = Xt; p.N = 9 * CiP; p.Kp = Qp;
+                p.shift_taps = 9; p.shift_rows = 3 * CiP; p.shift_ld = CiP;
+                for (int t = 0; t < 9; ++t) {
+                    p.shift_off[t] = (t / 3 - 1) * Wp;
+                    p.shift_row[t] = (t % 3) * CiP;
+                }
+                p.epi.bias = zeros; p.epi.gamma = ones; p.epi.res1 = S; p.epi.out = S; p.epi.ldc = 9 * CiP;
+                p.ksplit = std::max(2, ksplit_for(Co, 9 * CiP, Q));
+                DAD_TRY(gemm_tc(p, st));
+                DAD_TRY(wgrad_unshift(S, dW, Co, Ci, 9, CiP, st));
+            }
+            ar.used = mk;
+            return DAD_OK;
+        }
+        // rows of the im2col^T operand are ordered (ci, tap), so the GEMM output [Co][Ci*taps] IS the weight layout
         const int Pp = rup(P, 64);
         void* dOt = ar.bytes(static_cast<size_t>(Co) * Pp * 2);
         void* Xc = ar.bytes(static_cast<size_t>(Ci) * taps * Pp * 2);

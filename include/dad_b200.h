@@ -201,6 +201,13 @@ int dad_gemm_ex(const void* A, const void* W, const float* bias, const float* ga
  * are reduce-added through TMA.  zeros / ones: device vectors of N floats (the epilogue's bias / scale). */
 int dad_gemm_splitk(const void* A, const void* W, const float* zeros, const float* ones, float* out, int M, int N, int K,
                     int lda, int ksplit, void* stream);
+/* The 3x3 convolution weight gradient's form of the same GEMM: the B operand's rows are `taps` SHIFTED VIEWS of one
+ * [rows, lda] matrix W: out[m, t * ld + r] (fp32) += sum_k A[m, k] * W[r, k + offsets[t]] (zero outside [0, lda) and for
+ * r >= rows); ld % 128 == 0, ksplit >= 2, offsets is a HOST array.  Over zero-padded pixel space a convolution tap is such a
+ * constant offset, so no im2col operand is materialised (train.inl conv_wgrad; reference: autograd of torch.nn.Conv2d,
+ * dpt.py / blocks.py convolutions). */
+int dad_gemm_shifted(const void* A, const void* W, const float* zeros, const float* ones, float* out, int M, int rows, int K,
+                     int lda, int taps, int ld, const int* offsets, int ksplit, void* stream);
 /* conv3x3 / 1x1 (stride 1, zero padding) on NHWC input [B,H,W,C] with packed weights [Co, taps*Cp]. */
 int dad_conv_nhwc(const void* in, const void* Wpacked, const float* bias, float* out, int B, int H, int W, int C,
                   int Co, int taps, int mode, void* stream);

@@ -158,6 +158,41 @@ def test_conv_stride2_matches_conv2d(B, H, W, C, Co):
 
 
 # 5 = attention_tc5.cu (the default), 2 / 3 = the round-1 kernels kept for A/B measurements
+@pytest.mark.parametrize("M,rows,K,ld,offs", [(64, 64, 5000, 128, [0, 64, -64]), (256, 200, 20000, 256, [-232, -232, -232, 0, 0, 0, 232, 232, 232]),
+                                              (128, 128, 3000, 128, [8, -8, 16, -4096])])
+def test_gemm_shifted_views_match_torch(M, rows, K, ld, offs):
+    """The 3x3 weight gradient's GEMM (train.inl conv_wgrad): out[m, t*ld + r] += sum_k A[m, k] W[r, k + off_t], zero outside
+    the matrix, rows >= `rows` of every view zero.  Offsets are multiples of 8 elements (TMA box starts are 16-byte aligned)."""
+    import ctypes
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Kp = (K + 63) // 64 * 64
+    A = torch.zeros(M, Kp, device="cuda", dtype=torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = torch.zeros(rows, Kp, device="cuda", dtype=torch.bfloat16)
+    W[:, :K] = torch.randn(rows, K, device="cuda", generator=g).bfloat16()
+    taps = len(offs)
+    out = torch.zeros(M, taps * ld, device="cuda")
+    zeros, ones = torch.zeros(16384, device="cuda"), torch.ones(16384, device="cuda")
+    L.check(lib.dad_gemm_shifted(L.ptr(A), L.ptr(W), L.ptr(zeros), L.ptr(ones), L.ptr(out), M, rows, K, Kp, taps, ld,
+                                 (ctypes.c_int * taps)(*offs), 4, L.stream_ptr()), "dad_gemm_shifted")
+    torch.cuda.synchronize()
+    ref = torch.zeros(M, taps * ld, device="cuda", dtype=torch.float64)
+    Ad, Wd = A.double(), W.double()
+    for t, o in enumerate(offs):
+        Ws = torch.zeros_like(Wd)
+        if 0 <= o < Kp:
+            Ws[:, :Kp - o] = Wd[:, o:]
+        elif -Kp < o < 0:
+            Ws[:, -o:] = Wd[:, :Kp + o]
+        ref[:, t * ld:t * ld + rows] = Ad @ Ws.t()
+    assert (out.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    with pytest.raises(ValueError):   # an odd offset is rejected on the host instead of faulting in TMA
+        L.check(lib.dad_gemm_shifted(L.ptr(A), L.ptr(W), L.ptr(zeros), L.ptr(ones), L.ptr(out), M, rows, K, Kp, 1, ld,
+                                     (ctypes.c_int * 1)(1), 4, L.stream_ptr()), "dad_gemm_shifted")
+
+
 @pytest.mark.parametrize("rows,D,period", [(2740, 1024, None), (4 * 1369, 1024, (1369, 1370, 1)), (2049, 768, None),
                                             (2 * 1024, 384, (1024, 1025, 1)), (2100, 1536, None), (100, 1024, None)])
 @pytest.mark.parametrize("mode", [0, 1])
