@@ -58,6 +58,8 @@ PROTOTYPES = {
     "dad_conv_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dad_conv_nhwc_ex": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dad_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "dad_gemm_splitk_mn": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "dad_conv_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dad_gemm_shifted": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _c.POINTER(_c.c_int), _i, _vp]),
     "dad_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _c.c_longlong, _i, _i, _i, _i, _c.c_float, _i, _vp]),
     "dad_launch_count": (_c.c_longlong, []),

@@ -125,6 +125,26 @@ int dad_gemm_splitk(const void* A, const void* W, const float* zeros, const floa
     return dad::gemm_tc(p, ST(stream));
 }
 
+int dad_gemm_splitk_mn(const void* A, const void* W, const float* zeros, const float* ones, float* out, int M, int N, int K,
+                       int lda, int ldw, int ksplit, void* stream) {
+    dad::GemmProblem p;
+    p.mn = 1; p.A = A; p.M = M; p.K = K; p.lda = lda; p.Wt = W; p.N = N; p.ldw = ldw;
+    p.epi.bias = zeros; p.epi.gamma = ones; p.epi.res1 = out; p.epi.out = out; p.epi.ldc = N;
+    p.ksplit = ksplit;
+    return dad::gemm_tc(p, ST(stream));
+}
+
+int dad_conv_wgrad(const void* dY, const void* X, const float* zeros, const float* ones, float* out, int B, int H, int W, int Co,
+                   int Ci, int ksplit, void* stream) {
+    dad::GemmProblem p;
+    const int CiP = dad::cdiv(Ci, 128) * 128;
+    p.mn = 2; p.A = dY; p.M = Co; p.lda = Co; p.Wt = X; p.ldw = Ci; p.B = B; p.H = H; p.W = W;
+    p.shift_rows = Ci; p.shift_ld = CiP; p.N = 9 * CiP;
+    p.epi.bias = zeros; p.epi.gamma = ones; p.epi.res1 = out; p.epi.out = out; p.epi.ldc = 9 * CiP;
+    p.ksplit = ksplit;
+    return dad::gemm_tc(p, ST(stream));
+}
+
 int dad_gemm_shifted(const void* A, const void* W, const float* zeros, const float* ones, float* out, int M, int rows, int K,
                      int lda, int taps, int ld, const int* offsets, int ksplit, void* stream) {
     if (!offsets || taps < 1 || taps > 9) return dad::set_error(DAD_ERR_INVALID, "dad_gemm_shifted: 1..9 taps with their offsets");

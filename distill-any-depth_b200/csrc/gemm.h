@@ -74,6 +74,15 @@ struct GemmProblem {
     int shift_taps = 0, shift_rows = 0, shift_ld = 0;
     int shift_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int shift_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // gemm_tc, split-K only: MN-MAJOR operands - the contraction index is the OUTER dimension of both operands, i.e. they
+    // are read in the layout the activations already have (no transposed copies for the weight gradients):
+    //   mn == 1  linear: A is [K rows][lda] with M valid columns, Wt is [K rows][ldw] with N valid columns
+    //            (D[m, n] = sum_k A[k, m] Wt[k, n]: dW = dY^T X straight from dY [rows, Nout] and X [rows, Kin]);
+    //   mn == 2  3x3 / stride-1 convolution weight gradient: A = dY, Wt = X, both NHWC [B, H, W, C] (pixel pitches lda /
+    //            ldw), M = Co, shift_rows = Ci, shift_ld = Ci rounded up to 128, N = 9 * shift_ld; the contraction runs over
+    //            8 x 8 pixel patches, tap t = n / shift_ld reads X shifted by (t / 3 - 1, t % 3 - 1) with TMA's zero fill as
+    //            the convolution padding: out[co, t * shift_ld + ci] += sum_p dY[p, co] X[p + shift_t, ci].
+    int mn = 0;
     long long c_row_b = 0, c_row_h = 0;
     int c_col_h = 0;
     Epilogue epi;

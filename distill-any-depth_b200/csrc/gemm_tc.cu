@@ -47,6 +47,7 @@ struct TcArgs {
     int batch_h, mt_per_batch, rows_per_batch, c_col_h;   // batched linear problems (batch_h > 0): m tile -> (image, head, local tile)
     long long c_row_b, c_row_h;
     int shift_ld, shift_off[9], shift_row[9];   // B rows are shifted views of one matrix (GemmProblem::shift_*); 0 = off
+    int mn;                 // MN-major operands (GemmProblem::mn): 0 off, 1 linear, 2 conv weight gradient over 8 x 8 patches
     double flops;           // algorithmic 2*M*N*K of this launch (host-side bookkeeping only)
 };
 
@@ -180,6 +181,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                    if (g.mn) {
+                        // MN-major: a stage holds 64 contraction rows; per 64 columns of M / N one [64 rows][128 B] atom
+                        uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+                        uint8_t* b_dst = sB + stage * C::B_STAGE_BYTES;
+                        if (g.mn == 1) {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j)
+                                ptx::tma_load_2d(a_dst + j * 8192, &tmA, &full[stage], mt * BM + j * 64, kb * BK);
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                ptx::tma_load_2d(b_dst + j * 8192, &tmB, &full[stage], n0 + j * 64, kb * BK);
+                        } else {
+                            const int per_img = g.tiles_x * g.tiles_y;
+                            const int pb = kb / per_img, pr = kb - pb * per_img;
+                            const int py = pr / g.tiles_x, px = pr - py * g.tiles_x;
+                            const int tap = n0 / g.shift_ld, c0 = n0 - tap * g.shift_ld;
+                            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j)
+                                ptx::tma_load_4d(a_dst + j * 8192, &tmA, &full[stage], mt * BM + j * 64, px * 8, py * 8, pb);
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                ptx::tma_load_4d(b_dst + j * 8192, &tmB, &full[stage], c0 + j * 64, px * 8 + dx, py * 8 + dy, pb);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (g.conv) {
                         const int tap = kb / g.cchunks;
                         const int cc = kb - tap * g.cchunks;
@@ -253,10 +281,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t a_lo = sA_lo + stage * (A_STAGE_BYTES >> 4);
                     const uint32_t b_lo = sB_lo + stage * (C::B_STAGE_BYTES >> 4);
                     if (ptx::elect_one()) {
+                        if (g.mn) {
+                            // MN-major operands: 64-column atoms 8 KB apart (leading offset), 8 contraction rows = 1024 B
+                            // (stride offset); a K step of 16 rows advances the start address by 2048 B
+                            constexpr uint32_t idesc_mn = idesc | (1u << 15) | (1u << 16);
+                            constexpr uint32_t kHiMn = (1024u >> 4) | (1u << 14) | (2u << 29);
+                            constexpr uint32_t kLbo = (8192u >> 4) << 16;
+                            const uint32_t am = ((a_lo & 0xFFFFu) | kLbo), bm = ((b_lo & 0xFFFFu) | kLbo);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                ptx::umma_bf16(d_tmem, ptx::make_desc(am + k * (2048 >> 4), kHiMn), ptx::make_desc(bm + k * (2048 >> 4), kHiMn),
+                                               idesc_mn, ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        } else {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             ptx::umma_bf16(d_tmem, ptx::make_desc(a_lo + 2 * k, ptx::kDescHiSw128),
                                            ptx::make_desc(b_lo + 2 * k, ptx::kDescHiSw128), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        }
                         ptx::umma_commit(&empty[stage]);
                     }
                     __syncwarp();
@@ -605,7 +646,42 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
 
     CUtensorMap tmA, tmB;
     bool halo = false;
-    if (p.conv) {
+    if (p.mn) {
+        // MN-major operands (weight gradients straight from the activation layouts): 64 x 64 boxes, contraction rows outer
+        DAD_REQUIRE(!p.conv && p.batch_h == 0 && p.ksplit > 1 && p.M > 0 && p.lda % 8 == 0 && p.ldw % 8 == 0 && p.ldw > 0,
+                    "gemm_tc: bad MN-major problem");
+        a.mn = p.mn;
+        a.M = p.M;
+        a.num_m_tiles = cdiv(p.M, BM);
+        const cuuint32_t box2[2] = {64u, 64u};
+        const cuuint32_t box4[4] = {64u, 8u, 8u, 1u};
+        if (p.mn == 1) {
+            DAD_REQUIRE(p.K > 0 && p.lda >= p.M && p.ldw >= p.N && !p.shift_taps, "gemm_tc: bad MN-major linear problem");
+            a.num_k_blocks = cdiv(p.K, BK);
+            a.flops = 2.0 * p.M * p.N * static_cast<double>(p.K);
+            const cuuint64_t dA[2] = {(cuuint64_t)p.M, (cuuint64_t)p.K}, sA1[1] = {(cuuint64_t)p.lda * 2};
+            const cuuint64_t dB[2] = {(cuuint64_t)p.N, (cuuint64_t)p.K}, sB1[1] = {(cuuint64_t)p.ldw * 2};
+            DAD_TRY(make_tmap_bf16(&tmA, p.A, 2, dA, sA1, box2));
+            DAD_TRY(make_tmap_bf16(&tmB, p.Wt, 2, dB, sB1, box2));
+        } else {
+            DAD_REQUIRE(p.mn == 2 && p.B > 0 && p.H > 0 && p.W > 0 && p.shift_rows > 0 && p.shift_ld % 128 == 0 &&
+                            p.shift_rows <= p.shift_ld && p.N == 9 * p.shift_ld && p.lda >= p.M && p.ldw >= p.shift_rows,
+                        "gemm_tc: bad convolution weight-gradient problem");
+            bn = 128;   // a tile must not straddle two taps
+            a.num_n_tiles = cdiv(p.N, bn);
+            a.shift_ld = p.shift_ld;
+            a.tiles_x = cdiv(p.W, 8);
+            a.tiles_y = cdiv(p.H, 8);
+            a.num_k_blocks = p.B * a.tiles_x * a.tiles_y;
+            a.flops = 2.0 * p.M * 9.0 * p.shift_rows * (static_cast<double>(p.B) * p.H * p.W);
+            const cuuint64_t dA[4] = {(cuuint64_t)p.M, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+            const cuuint64_t sA3[3] = {(cuuint64_t)p.lda * 2, (cuuint64_t)p.lda * 2 * p.W, (cuuint64_t)p.lda * 2 * p.W * p.H};
+            const cuuint64_t dB[4] = {(cuuint64_t)p.shift_rows, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+            const cuuint64_t sB3[3] = {(cuuint64_t)p.ldw * 2, (cuuint64_t)p.ldw * 2 * p.W, (cuuint64_t)p.ldw * 2 * p.W * p.H};
+            DAD_TRY(make_tmap(&tmA, 0, p.A, 4, dA, sA3, box4));
+            DAD_TRY(make_tmap(&tmB, 0, p.Wt, 4, dB, sB3, box4));
+        }
+    } else if (p.conv) {
         DAD_REQUIRE(p.taps == 1 || p.taps == 9, "gemm_tc: taps must be 1 or 9");
         DAD_REQUIRE(p.C % 8 == 0 && p.ldp % 8 == 0, "gemm_tc: conv C/ldp must be multiples of 8");
         DAD_REQUIRE(p.stride == 1 || (p.stride == 2 && p.taps == 9), "gemm_tc: stride %d unsupported", p.stride);
@@ -684,7 +760,9 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
         DAD_TRY(make_tmap_bf16(&tmA, p.A, 2, dims, strides, box));
         }
     }
-    if (a.batch_h) {
+    if (p.mn) {
+        // (both maps were built above)
+    } else if (a.batch_h) {
         const cuuint64_t dims[4] = {(cuuint64_t)p.K, (cuuint64_t)p.w_rows, (cuuint64_t)p.batch_h, (cuuint64_t)p.batch_b};
         const cuuint64_t strides[3] = {(cuuint64_t)(p.ldw ? p.ldw : p.Kp) * 2, (cuuint64_t)p.w_sh * 2, (cuuint64_t)p.w_sb * 2};
         const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bn, 1, 1};

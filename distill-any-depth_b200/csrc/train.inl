@@ -251,6 +251,13 @@ struct Trainer {
         const long long maxs = std::max<long long>(1, cdivl(K, 64) / 4);   // at least 4 k-blocks per slice
         return static_cast<int>(std::max<long long>(1, std::min(want, maxs)));
     }
+    // Weight-gradient operand path (A/B switch DAD_WGRAD_PATH): 2 (default) MN-major operands read in the activations' own
+    // layouts (no copies), 1 channel-major copies over zero-padded pixel space (3x3 convolutions; linear as 0), 0 transposed
+    // copies + the materialised 9x im2col^T operand.
+    static int wgrad_path() {
+        static const int v = [] { const char* e = getenv("DAD_WGRAD_PATH"); return e ? atoi(e) : 2; }();
+        return v;
+    }
     // out[Mo, No] (fp32) += At[Mo, K] Bt[No, K]^T on the tensor cores, split over K, partial tiles reduce-added through TMA
     int tc_accumulate(const void* At, const void* Bt, int Mo, int No, long long K, int Kp, float* out) {
         DAD_REQUIRE(No <= 16384, "backward: weight-gradient width %d exceeds the epilogue vectors", No);
@@ -271,6 +278,16 @@ struct Trainer {
             g.sbk = ldx; g.sbn = 1; g.C = dW; g.scm = Kin; g.scn = 1;
             g.M = Nout; g.N = Kin; g.K = static_cast<int>(rows); g.accumulate = 1;
             return sgemm(g, st);
+        }
+        if (wgrad_path() == 2 && ldy % 8 == 0 && ldx % 8 == 0 && Kin % 8 == 0) {
+            // dY [rows, Nout] and X [rows, Kin] ARE the MN-major operands of dW = dY^T X: no transposed copies
+            if (dry) return DAD_OK;
+            DAD_REQUIRE(Kin <= 16384, "backward: weight-gradient width %d exceeds the epilogue vectors", Kin);
+            GemmProblem p;
+            p.mn = 1; p.A = dY; p.M = Nout; p.lda = ldy; p.Wt = X; p.N = Kin; p.ldw = ldx; p.K = static_cast<int>(rows);
+            p.epi.bias = zeros; p.epi.gamma = ones; p.epi.res1 = dW; p.epi.out = dW; p.epi.ldc = Kin;
+            p.ksplit = std::max(2, ksplit_for(Nout, Kin, rows));
+            return gemm_tc(p, st);
         }
         const size_t mk = ar.used;
         const int Rp = rup(rows, 64);
@@ -327,8 +344,27 @@ struct Trainer {
             return sgemm(g, st);
         }
         const size_t mk = ar.used;
-        static const bool wgrad_im2col = getenv("DAD_WGRAD_IM2COL") != nullptr;   // A/B switch: materialised 9x operand
-        if (taps == 9 && stride == 1 && Ho == Hin && Wo == Win && !wgrad_im2col) {
+        if (taps == 9 && stride == 1 && Ho == Hin && Wo == Win && wgrad_path() == 2 && Ci % 8 == 0 && Co % 8 == 0) {
+            // 3x3 / stride 1, MN-major: dY and X (NHWC) are read as they are; the contraction runs over 8 x 8 pixel patches,
+            // tap (dy, dx) is the same TMA box moved by (dy - 1, dx - 1) pixels with out-of-image pixels zero-filled.
+            const int CiP = rup(Ci, 128);
+            float* S = ar.f(static_cast<size_t>(Co) * 9 * CiP);
+            if (!dry) {
+                DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
+                DAD_REQUIRE(9 * CiP <= 16384, "backward: weight-gradient width %d exceeds the epilogue vectors", 9 * CiP);
+                DAD_CHECK_CUDA(cudaMemsetAsync(S, 0, static_cast<size_t>(Co) * 9 * CiP * 4, st));
+                GemmProblem p;
+                p.mn = 2; p.A = dOut; p.M = Co; p.lda = Co; p.Wt = X; p.ldw = Ci; p.B = B; p.H = Hin; p.W = Win;
+                p.shift_rows = Ci; p.shift_ld = CiP; p.N = 9 * CiP;
+                p.epi.bias = zeros; p.epi.gamma = ones; p.epi.res1 = S; p.epi.out = S; p.epi.ldc = 9 * CiP;
+                p.ksplit = std::max(2, ksplit_for(Co, 9 * CiP, static_cast<long long>(B) * cdiv(Hin, 8) * cdiv(Win, 8) * 64));
+                DAD_TRY(gemm_tc(p, st));
+                DAD_TRY(wgrad_unshift(S, dW, Co, Ci, 9, CiP, st));
+            }
+            ar.used = mk;
+            return DAD_OK;
+        }
+        if (taps == 9 && stride == 1 && Ho == Hin && Wo == Win && wgrad_path() >= 1) {
             // 3x3 / stride 1: no 9x im2col operand.  Both operands are channel-major copies over ZERO-PADDED pixel space
             // q = (b, y + 1, x + 1) of an (H + 2) x Wp frame (Wp = W + 2 rounded up to 8): there a vertical tap is the constant
             // offset (dy - 1) * Wp, which TMA applies as a shifted K coordinate of ONE matrix (GemmProblem::shift_*); the

@@ -201,7 +201,18 @@ int dad_gemm_ex(const void* A, const void* W, const float* bias, const float* ga
  * are reduce-added through TMA.  zeros / ones: device vectors of N floats (the epilogue's bias / scale). */
 int dad_gemm_splitk(const void* A, const void* W, const float* zeros, const float* ones, float* out, int M, int N, int K,
                     int lda, int ksplit, void* stream);
-/* The 3x3 convolution weight gradient's form of the same GEMM: the B operand's rows are `taps` SHIFTED VIEWS of one
+/* The same weight-gradient GEMM with MN-MAJOR operands, i.e. read in the layout the activations already have:
+ * out[M,N] (fp32) += sum_k A[k, m] W[k, n], A = [K rows][lda] (M valid columns), W = [K rows][ldw] (N valid columns), bf16:
+ * dW = dY^T X straight from dY [tokens, Nout] and X [tokens, Kin], no transposed copies (train.inl wgrad_linear). */
+int dad_gemm_splitk_mn(const void* A, const void* W, const float* zeros, const float* ones, float* out, int M, int N, int K,
+                       int lda, int ldw, int ksplit, void* stream);
+/* 3x3 / stride-1 / zero-padded convolution weight gradient straight from the NHWC bf16 tensors dY [B,H,W,Co] and X [B,H,W,Ci]
+ * (autograd of torch.nn.Conv2d for the decoder convolutions, blocks.py / dpt.py): out[co, t * CiP + ci] (fp32, CiP = Ci
+ * rounded up to 128, t = ky * 3 + kx) += sum_pixels dY[p, co] X[p + (ky - 1, kx - 1), ci]; the contraction runs over 8 x 8
+ * pixel patches fetched by TMA (zero fill = the padding); no im2col operand, no transposes (train.inl conv_wgrad). */
+int dad_conv_wgrad(const void* dY, const void* X, const float* zeros, const float* ones, float* out, int B, int H, int W, int Co,
+                   int Ci, int ksplit, void* stream);
+/* An earlier form of the 3x3 convolution weight gradient's GEMM (DAD_WGRAD_PATH=1): the B operand's rows are `taps` SHIFTED VIEWS of one
  * [rows, lda] matrix W: out[m, t * ld + r] (fp32) += sum_k A[m, k] * W[r, k + offsets[t]] (zero outside [0, lda) and for
  * r >= rows); ld % 128 == 0, ksplit >= 2, offsets is a HOST array.  Over zero-padded pixel space a convolution tap is such a
  * constant offset, so no im2col operand is materialised (train.inl conv_wgrad; reference: autograd of torch.nn.Conv2d,

@@ -158,6 +158,48 @@ def test_conv_stride2_matches_conv2d(B, H, W, C, Co):
 
 
 # 5 = attention_tc5.cu (the default), 2 / 3 = the round-1 kernels kept for A/B measurements
+@pytest.mark.parametrize("M,N,K", [(128, 128, 4096), (768, 2304, 1570), (96, 768, 3140), (200, 72, 777)])
+def test_gemm_splitk_mn_major_operands(M, N, K):
+    """dW = dY^T X read straight from dY [K, M] and X [K, N] (padded row pitches): MN-major UMMA operands, no transposes."""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    lda, ldw = (M + 15) // 8 * 8, (N + 23) // 8 * 8
+    A = torch.randn(K, lda, device="cuda", generator=g).bfloat16()
+    W = torch.randn(K, ldw, device="cuda", generator=g).bfloat16()
+    out0 = torch.randn(M, N, device="cuda", generator=g)
+    out = out0.clone()
+    zeros, ones = torch.zeros(16384, device="cuda"), torch.ones(16384, device="cuda")
+    L.check(lib.dad_gemm_splitk_mn(L.ptr(A), L.ptr(W), L.ptr(zeros), L.ptr(ones), L.ptr(out), M, N, K, lda, ldw, 3,
+                                   L.stream_ptr()), "dad_gemm_splitk_mn")
+    torch.cuda.synchronize()
+    ref = out0.double() + A[:, :M].double().t() @ W[:, :N].double()
+    assert (out.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("B,H,W,Co,Ci", [(2, 16, 16, 128, 128), (2, 37, 29, 64, 96), (1, 9, 70, 256, 32), (3, 8, 8, 32, 200)])
+def test_conv_wgrad_from_nhwc_matches_autograd(B, H, W, Co, Ci):
+    """3x3 / stride 1 / padding 1 weight gradient from the NHWC tensors (no im2col, no transposes) against autograd of
+    torch.nn.functional.conv2d in float64; ragged patches, channel counts below and between the 64 / 128 tile sizes."""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(B * H + Ci)
+    X = torch.randn(B, H, W, Ci, device="cuda", generator=g).bfloat16()
+    dY = torch.randn(B, H, W, Co, device="cuda", generator=g).bfloat16()
+    CiP = (Ci + 127) // 128 * 128
+    out = torch.zeros(Co, 9 * CiP, device="cuda")
+    zeros, ones = torch.zeros(16384, device="cuda"), torch.ones(16384, device="cuda")
+    L.check(lib.dad_conv_wgrad(L.ptr(dY), L.ptr(X), L.ptr(zeros), L.ptr(ones), L.ptr(out), B, H, W, Co, Ci, 2, L.stream_ptr()),
+            "dad_conv_wgrad")
+    torch.cuda.synchronize()
+    w = torch.zeros(Co, Ci, 3, 3, device="cuda", dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(X.double().permute(0, 3, 1, 2), w, padding=1)
+    y.backward(dY.double().permute(0, 3, 1, 2))
+    got = out.view(Co, 9, CiP)[:, :, :Ci].permute(0, 2, 1).reshape(Co, Ci, 3, 3).double()
+    assert (got - w.grad).abs().max().item() <= 1e-4 * w.grad.abs().max().item()
+    assert out.view(Co, 9, CiP)[:, :, Ci:].abs().max().item() == 0 if CiP > Ci else True
+
+
 @pytest.mark.parametrize("M,rows,K,ld,offs", [(64, 64, 5000, 128, [0, 64, -64]), (256, 200, 20000, 256, [-232, -232, -232, 0, 0, 0, 232, 232, 232]),
                                               (128, 128, 3000, 128, [8, -8, 16, -4096])])
 def test_gemm_shifted_views_match_torch(M, rows, K, ld, offs):
