@@ -82,6 +82,9 @@ struct GemmProblem {
     //            ldw), M = Co, shift_rows = Ci, shift_ld = Ci rounded up to 128, N = 9 * shift_ld; the contraction runs over
     //            8 x 8 pixel patches, tap t = n / shift_ld reads X shifted by (t / 3 - 1, t % 3 - 1) with TMA's zero fill as
     //            the convolution padding: out[co, t * shift_ld + ci] += sum_p dY[p, co] X[p + shift_t, ci].
+    //   mn == 3  as 1, but only Wt is MN-major; A stays K-major ([M rows][lda]) - dQ = dS K of the attention backward.
+    // mn 1 / 3 also take a BATCH of problems (batch_h > 0, generic epilogue, no split-K): the strides a_sh / a_sb / w_sh / w_sb
+    // are then between the heads / images of the [rows][ld] operands and w_rows is the number of valid Wt COLUMNS.
     int mn = 0;
     long long c_row_b = 0, c_row_h = 0;
     int c_col_h = 0;

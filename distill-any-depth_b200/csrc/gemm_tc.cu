@@ -185,13 +185,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // MN-major: a stage holds 64 contraction rows; per 64 columns of M / N one [64 rows][128 B] atom
                         uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
                         uint8_t* b_dst = sB + stage * C::B_STAGE_BYTES;
-                        if (g.mn == 1) {
+                        if (g.mn != 2) {
+                            int zh = 0, zb = 0, ml = mt * BM;
+                            if (g.batch_h) {
+                                const int z = mt / g.mt_per_batch;
+                                zb = z / g.batch_h;
+                                zh = z - zb * g.batch_h;
+                                ml = (mt - z * g.mt_per_batch) * BM;
+                            }
+                            if (g.mn == 1) {
 #pragma unroll
-                            for (int j = 0; j < BM / 64; ++j)
-                                ptx::tma_load_2d(a_dst + j * 8192, &tmA, &full[stage], mt * BM + j * 64, kb * BK);
+                                for (int j = 0; j < BM / 64; ++j) {
+                                    if (g.batch_h) ptx::tma_load_4d(a_dst + j * 8192, &tmA, &full[stage], ml + j * 64, kb * BK, zh, zb);
+                                    else ptx::tma_load_2d(a_dst + j * 8192, &tmA, &full[stage], ml + j * 64, kb * BK);
+                                }
+                            } else if (g.batch_h) {   // mn == 3: A is K-major
+                                ptx::tma_load_4d(a_dst, &tmA, &full[stage], kb * BK, ml, zh, zb);
+                            } else {
+                                ptx::tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, ml);
+                            }
 #pragma unroll
-                            for (int j = 0; j < BN / 64; ++j)
-                                ptx::tma_load_2d(b_dst + j * 8192, &tmB, &full[stage], n0 + j * 64, kb * BK);
+                            for (int j = 0; j < BN / 64; ++j) {
+                                if (g.batch_h) ptx::tma_load_4d(b_dst + j * 8192, &tmB, &full[stage], n0 + j * 64, kb * BK, zh, zb);
+                                else ptx::tma_load_2d(b_dst + j * 8192, &tmB, &full[stage], n0 + j * 64, kb * BK);
+                            }
                         } else {
                             const int per_img = g.tiles_x * g.tiles_y;
                             const int pb = kb / per_img, pr = kb - pb * per_img;
@@ -284,14 +301,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (g.mn) {
                             // MN-major operands: 64-column atoms 8 KB apart (leading offset), 8 contraction rows = 1024 B
                             // (stride offset); a K step of 16 rows advances the start address by 2048 B
-                            constexpr uint32_t idesc_mn = idesc | (1u << 15) | (1u << 16);
                             constexpr uint32_t kHiMn = (1024u >> 4) | (1u << 14) | (2u << 29);
                             constexpr uint32_t kLbo = (8192u >> 4) << 16;
                             const uint32_t am = ((a_lo & 0xFFFFu) | kLbo), bm = ((b_lo & 0xFFFFu) | kLbo);
+                            if (g.mn == 3) {   // A K-major, B MN-major
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k)
-                                ptx::umma_bf16(d_tmem, ptx::make_desc(am + k * (2048 >> 4), kHiMn), ptx::make_desc(bm + k * (2048 >> 4), kHiMn),
-                                               idesc_mn, ((kb - kb0) | k) != 0 ? 1u : 0u);
+                                for (int k = 0; k < BK / 16; ++k)
+                                    ptx::umma_bf16(d_tmem, ptx::make_desc(a_lo + 2 * k, ptx::kDescHiSw128), ptx::make_desc(bm + k * (2048 >> 4), kHiMn),
+                                                   idesc | (1u << 16), ((kb - kb0) | k) != 0 ? 1u : 0u);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    ptx::umma_bf16(d_tmem, ptx::make_desc(am + k * (2048 >> 4), kHiMn), ptx::make_desc(bm + k * (2048 >> 4), kHiMn),
+                                                   idesc | (1u << 15) | (1u << 16), ((kb - kb0) | k) != 0 ? 1u : 0u);
+                            }
                         } else {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
@@ -648,21 +671,49 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
     bool halo = false;
     if (p.mn) {
         // MN-major operands (weight gradients straight from the activation layouts): 64 x 64 boxes, contraction rows outer
-        DAD_REQUIRE(!p.conv && p.batch_h == 0 && p.ksplit > 1 && p.M > 0 && p.lda % 8 == 0 && p.ldw % 8 == 0 && p.ldw > 0,
+        DAD_REQUIRE(!p.conv && (p.batch_h > 0 ? p.ksplit <= 1 && p.mn != 2 : p.ksplit > 1) && p.M > 0 && p.lda % 8 == 0 &&
+                        p.ldw % 8 == 0 && p.ldw > 0,
                     "gemm_tc: bad MN-major problem");
         a.mn = p.mn;
         a.M = p.M;
         a.num_m_tiles = cdiv(p.M, BM);
         const cuuint32_t box2[2] = {64u, 64u};
         const cuuint32_t box4[4] = {64u, 8u, 8u, 1u};
-        if (p.mn == 1) {
-            DAD_REQUIRE(p.K > 0 && p.lda >= p.M && p.ldw >= p.N && !p.shift_taps, "gemm_tc: bad MN-major linear problem");
+        if (p.mn == 1 || p.mn == 3) {
+            DAD_REQUIRE(p.K > 0 && !p.shift_taps, "gemm_tc: bad MN-major linear problem");
             a.num_k_blocks = cdiv(p.K, BK);
             a.flops = 2.0 * p.M * p.N * static_cast<double>(p.K);
-            const cuuint64_t dA[2] = {(cuuint64_t)p.M, (cuuint64_t)p.K}, sA1[1] = {(cuuint64_t)p.lda * 2};
-            const cuuint64_t dB[2] = {(cuuint64_t)p.N, (cuuint64_t)p.K}, sB1[1] = {(cuuint64_t)p.ldw * 2};
-            DAD_TRY(make_tmap_bf16(&tmA, p.A, 2, dA, sA1, box2));
-            DAD_TRY(make_tmap_bf16(&tmB, p.Wt, 2, dB, sB1, box2));
+            const cuuint32_t boxk2[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+            if (p.batch_h > 0) {
+                DAD_REQUIRE(p.batch_b > 0 && p.w_rows > 0 && p.w_rows <= p.N && p.a_sh % 8 == 0 && p.a_sb % 8 == 0 && p.w_sh % 8 == 0 &&
+                                p.w_sb % 8 == 0 && !p.epi.bias && !p.epi.res1 && !p.epi.scat_k && !p.epi.rowtab && !p.epi.res2 &&
+                                !p.epi.head_out,
+                            "gemm_tc: bad batched MN-major problem");
+                const int nz = p.batch_h * p.batch_b;
+                a.batch_h = p.batch_h;
+                a.mt_per_batch = cdiv(p.M, BM);
+                a.rows_per_batch = p.M;
+                a.num_m_tiles = a.mt_per_batch * nz;
+                a.c_row_b = p.c_row_b; a.c_row_h = p.c_row_h; a.c_col_h = p.c_col_h;
+                a.flops *= nz;
+                const cuuint32_t box44[4] = {64u, 64u, 1u, 1u}, boxk4[4] = {(cuuint32_t)BK, (cuuint32_t)BM, 1u, 1u};
+                const cuuint64_t sA3[3] = {(cuuint64_t)p.lda * 2, (cuuint64_t)p.a_sh * 2, (cuuint64_t)p.a_sb * 2};
+                const cuuint64_t sB3[3] = {(cuuint64_t)p.ldw * 2, (cuuint64_t)p.w_sh * 2, (cuuint64_t)p.w_sb * 2};
+                const cuuint64_t dAm[4] = {(cuuint64_t)p.M, (cuuint64_t)p.K, (cuuint64_t)p.batch_h, (cuuint64_t)p.batch_b};
+                const cuuint64_t dAk[4] = {(cuuint64_t)p.K, (cuuint64_t)p.M, (cuuint64_t)p.batch_h, (cuuint64_t)p.batch_b};
+                const cuuint64_t dB[4] = {(cuuint64_t)p.w_rows, (cuuint64_t)p.K, (cuuint64_t)p.batch_h, (cuuint64_t)p.batch_b};
+                if (p.mn == 1) DAD_TRY(make_tmap(&tmA, 0, p.A, 4, dAm, sA3, box44));
+                else DAD_TRY(make_tmap(&tmA, 0, p.A, 4, dAk, sA3, boxk4));
+                DAD_TRY(make_tmap(&tmB, 0, p.Wt, 4, dB, sB3, box44));
+            } else {
+                DAD_REQUIRE(p.ldw >= p.N && p.lda >= (p.mn == 1 ? p.M : p.K), "gemm_tc: bad MN-major row pitch");
+                const cuuint64_t dAm[2] = {(cuuint64_t)p.M, (cuuint64_t)p.K}, dAk[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+                const cuuint64_t sA1[1] = {(cuuint64_t)p.lda * 2};
+                const cuuint64_t dB[2] = {(cuuint64_t)p.N, (cuuint64_t)p.K}, sB1[1] = {(cuuint64_t)p.ldw * 2};
+                if (p.mn == 1) DAD_TRY(make_tmap_bf16(&tmA, p.A, 2, dAm, sA1, box2));
+                else DAD_TRY(make_tmap_bf16(&tmA, p.A, 2, dAk, sA1, boxk2));
+                DAD_TRY(make_tmap_bf16(&tmB, p.Wt, 2, dB, sB1, box2));
+            }
         } else {
             DAD_REQUIRE(p.mn == 2 && p.B > 0 && p.H > 0 && p.W > 0 && p.shift_rows > 0 && p.shift_ld % 128 == 0 &&
                             p.shift_rows <= p.shift_ld && p.N == 9 * p.shift_ld && p.lda >= p.M && p.ldw >= p.shift_rows,

@@ -344,6 +344,8 @@ struct Trainer {
             return sgemm(g, st);
         }
         const size_t mk = ar.used;
+        if (taps == 1 && stride == 1 && Ho == Hin && Wo == Win && wgrad_path() == 2 && Ci % 8 == 0 && Co % 8 == 0)
+            return wgrad_linear(dOut, Co, X, Ci, P, Co, Ci, dW, ar);   // a 1x1 convolution is a linear layer over the pixels
         if (taps == 9 && stride == 1 && Ho == Hin && Wo == Win && wgrad_path() == 2 && Ci % 8 == 0 && Co % 8 == 0) {
             // 3x3 / stride 1, MN-major: dY and X (NHWC) are read as they are; the contraction runs over 8 x 8 pixel patches,
             // tap (dy, dx) is the same TMA box moved by (dy - 1, dx - 1) pixels with out-of-image pixels zero-filled.
@@ -478,13 +480,48 @@ struct Trainer {
         float* S = ar.f(static_cast<size_t>(Z) * tt);
         float* dPf = ar.f(static_cast<size_t>(Z) * tt);
         void* Pn = ar.bytes(static_cast<size_t>(Z) * tt * 2);    // P  [z][i][j]
-        void* Pt = ar.bytes(static_cast<size_t>(Z) * sq * 2);    // P  [z][j][i]
         void* dS = ar.bytes(static_cast<size_t>(Z) * tt * 2);    // dS [z][i][j]
-        void* dSt = ar.bytes(static_cast<size_t>(Z) * sq * 2);   // dS [z][j][i]
-        void* Qt = ar.bytes(static_cast<size_t>(Z) * 64 * Tp * 2);
-        void* Kt = ar.bytes(static_cast<size_t>(Z) * 64 * Tp * 2);
-        void* dOt = ar.bytes(static_cast<size_t>(Z) * 64 * Tp * 2);
-        if (!dry) {
+        // MN-major operands (default): P / dS, q / k / v and dO are read where they lie - a contraction over the rows of a
+        // row-major matrix IS an MN-major operand - so the transposed copies below exist only on the A/B path
+        const bool mnp = wgrad_path() == 2;
+        void* Pt = mnp ? nullptr : ar.bytes(static_cast<size_t>(Z) * sq * 2);    // P  [z][j][i]
+        void* dSt = mnp ? nullptr : ar.bytes(static_cast<size_t>(Z) * sq * 2);   // dS [z][j][i]
+        void* Qt = mnp ? nullptr : ar.bytes(static_cast<size_t>(Z) * 64 * Tp * 2);
+        void* Kt = mnp ? nullptr : ar.bytes(static_cast<size_t>(Z) * 64 * Tp * 2);
+        void* dOt = mnp ? nullptr : ar.bytes(static_cast<size_t>(Z) * 64 * Tp * 2);
+        if (!dry && mnp) {
+            DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
+            const bf16* q = reinterpret_cast<const bf16*>(bt.qkv);
+            bf16* dq = reinterpret_cast<bf16*>(dqkv);
+            const long long zrows = static_cast<long long>(Z) * T;
+            auto scores = [&](const void* A, long long lda, long long a_sb, const void* Wt, float* out) -> int {
+                DAD_CHECK_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(Z) * tt * 4, st));
+                GemmProblem p;
+                p.A = A; p.M = T; p.K = 64; p.lda = lda; p.a_sh = 64; p.a_sb = a_sb;
+                p.Wt = Wt; p.N = Tp; p.Kp = 64; p.ldw = ld; p.w_sh = 64; p.w_sb = T * ld; p.w_rows = T;
+                p.batch_h = heads; p.batch_b = B; p.c_row_b = static_cast<long long>(heads) * T; p.c_row_h = T;
+                p.epi.bias = zeros; p.epi.gamma = ones; p.epi.res1 = out; p.epi.out = out; p.epi.ldc = Tp;
+                return gemm_tc(p, st);
+            };
+            // out[z][row, 0:64] (a 64-column slice of dqkv) = scale * op(A)[z] W[z]: A = P / dS [z][T][Tp] read MN-major (mn 1:
+            // the contraction runs over its rows) or K-major (mn 3), W = a [T][64] head slice of q / k / dO read MN-major
+            auto apply = [&](int mn, const void* A, const bf16* Wm, long long ldw, bf16* out, const float* scale) -> int {
+                GemmProblem p;
+                p.mn = mn; p.A = A; p.M = T; p.K = T; p.lda = Tp; p.a_sh = tt; p.a_sb = heads * tt;
+                p.Wt = Wm; p.N = 64; p.ldw = ldw; p.w_sh = 64; p.w_sb = T * ldw; p.w_rows = 64;
+                p.batch_h = heads; p.batch_b = B; p.c_row_b = T; p.c_row_h = 0; p.c_col_h = 64;
+                p.epi.out = out; p.epi.out_bf16 = 1; p.epi.ldc = ld; p.epi.gamma = scale;
+                return gemm_tc(p, st);
+            };
+            DAD_TRY(scores(q, ld, T * ld, q + Dm, S));                                           // S  = Q' K^T
+            DAD_TRY(scores(datt, Dm, static_cast<long long>(T) * Dm, q + 2 * Dm, dPf));          // dP = dO V^T
+            DAD_TRY(softmax_rows_bf16(S, Pn, zrows, T, Tp, st));
+            DAD_TRY(apply(1, Pn, reinterpret_cast<const bf16*>(datt), Dm, dq + 2 * Dm, nullptr));   // dV = P^T dO
+            DAD_TRY(softmax_bwd_bf16(Pn, dPf, dS, zrows, T, Tp, st));
+            DAD_TRY(apply(3, dS, q + Dm, ld, dq, eighths));                                      // dq = 0.125 dS K
+            DAD_TRY(apply(1, dS, q, ld, dq + Dm, nullptr));                                      // dK = dS^T Q'
+        }
+        if (!dry && !mnp) {
             DAD_REQUIRE(!ar.overflow, "backward: workspace too small");
             const bf16* q = reinterpret_cast<const bf16*>(bt.qkv);
             bf16* dq = reinterpret_cast<bf16*>(dqkv);
