@@ -88,6 +88,10 @@ struct GemmProblem {
     int mn = 0;
     long long c_row_b = 0, c_row_h = 0;
     int c_col_h = 0;
+    // batched + the fp32 `out += gamma * (acc + bias)` epilogue only: c_store = 1 writes each tile with a plain TMA STORE clipped
+    // to its problem's M rows (3-D output map) instead of the reduce-add - the destination needs no zero fill and is not
+    // read.  Needs contiguous problems (c_row_b == batch_h * c_row_h == batch_h * M) and one work item per output tile.
+    int c_store = 0;
     Epilogue epi;
 };
 

@@ -47,6 +47,7 @@ struct TcArgs {
     int batch_h, mt_per_batch, rows_per_batch, c_col_h;   // batched linear problems (batch_h > 0): m tile -> (image, head, local tile)
     long long c_row_b, c_row_h;
     int shift_ld, shift_off[9], shift_row[9];   // B rows are shifted views of one matrix (GemmProblem::shift_*); 0 = off
+    int c_store;            // batched fp32 epilogue: plain clipped TMA store instead of reduce-add (GemmProblem::c_store)
     int mn;                 // MN-major operands (GemmProblem::mn): 0 off, 1 linear, 2 conv weight gradient over 8 x 8 patches
     double flops;           // algorithmic 2*M*N*K of this launch (host-side bookkeeping only)
 };
@@ -457,6 +458,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (g.batch_h) {   // batched problems: rows of problem (b, h) start at b * c_row_b + h * c_row_h
                                 const int z = mt / g.mt_per_batch, zb = z / g.batch_h;
                                 row0 = static_cast<int>(zb * g.c_row_b + (z - zb * g.batch_h) * g.c_row_h) + (mt - z * g.mt_per_batch) * BM;
+                                if (g.c_store) {   // {columns, rows of the problem, problem}: rows past the problem are clipped
+                                    ptx::tma_store_4d(&tmC, tile_stg, col0, (mt - z * g.mt_per_batch) * BM, z, 0);
+                                    ptx::bulk_commit();
+                                    continue;
+                                }
                             }
                             ptx::tma_reduce_add_2d(&tmC, tile_stg, col0, row0);
                         } else {
@@ -863,6 +869,15 @@ int gemm_tc(const GemmProblem& p, cudaStream_t stream) {
                                            (cuuint64_t)p.epi.ldc * es * a.W * a.H};
             const cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)tw, (cuuint32_t)a.th, 1};
             DAD_TRY(make_tmap(&tmC, f32 ? 1 : 0, p.epi.out, 4, dims, strides, box));
+        } else if (p.c_store) {
+            DAD_REQUIRE(a.batch_h && f32 && p.ksplit <= 1 && p.c_row_h == p.M && p.c_row_b == static_cast<long long>(p.batch_h) * p.M &&
+                            p.c_col_h == 0,
+                        "gemm_tc: c_store needs contiguous batched problems and the fp32 epilogue");
+            a.c_store = 1;
+            const cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.M, (cuuint64_t)(p.batch_h * p.batch_b), 1};
+            const cuuint64_t strides[3] = {(cuuint64_t)p.epi.ldc * 4, (cuuint64_t)p.epi.ldc * 4 * p.M, (cuuint64_t)p.epi.ldc * 4 * p.M * p.batch_h * p.batch_b};
+            const cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)BM, 1, 1};
+            DAD_TRY(make_tmap(&tmC, 1, p.epi.out, 4, dims, strides, box));
         } else {
             const cuuint64_t out_rows = a.batch_h ? (cuuint64_t)(p.batch_b * p.c_row_b) : (cuuint64_t)p.M;
             const cuuint64_t dims[2] = {(cuuint64_t)p.N, out_rows};

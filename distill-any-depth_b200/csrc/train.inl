@@ -495,8 +495,8 @@ struct Trainer {
             bf16* dq = reinterpret_cast<bf16*>(dqkv);
             const long long zrows = static_cast<long long>(Z) * T;
             auto scores = [&](const void* A, long long lda, long long a_sb, const void* Wt, float* out) -> int {
-                DAD_CHECK_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(Z) * tt * 4, st));
-                GemmProblem p;
+                GemmProblem p;   // plain clipped stores (c_store): no zero fill of the 2 x Z x T x Tp fp32 destinations, no read
+                p.c_store = 1;
                 p.A = A; p.M = T; p.K = 64; p.lda = lda; p.a_sh = 64; p.a_sb = a_sb;
                 p.Wt = Wt; p.N = Tp; p.Kp = 64; p.ldw = ld; p.w_sh = 64; p.w_sb = T * ld; p.w_rows = T;
                 p.batch_h = heads; p.batch_b = B; p.c_row_b = static_cast<long long>(heads) * T; p.c_row_h = T;
