@@ -560,6 +560,54 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const void* gout, int
     }
 }
 
+// Gather form of the same adjoint: one thread per INPUT pixel (and 4 channels) sums the output pixels whose bilinear footprint
+// contains it - the rows oy with y0(oy) in {iy - 1, iy} and the columns likewise, found by re-evaluating the forward's own
+// fp32 index expressions (so the weights are bit-identical to the scatter form's) - and writes the gradient once in the
+// activation type: no zero fill, no atomics (deterministic), no fp32 staging + convert pass.
+__device__ __forceinline__ int bil_first(int i, int n_out, float s) {   // smallest o with (int)(s * o) >= i - 1
+    int e = s > 0.f ? static_cast<int>(static_cast<float>(i - 1) / s) : 0;
+    e = e < 0 ? 0 : (e > n_out - 1 ? n_out - 1 : e);
+    while (e > 0 && static_cast<int>(s * (e - 1)) >= i - 1) --e;
+    while (e < n_out && static_cast<int>(s * e) < i - 1) ++e;
+    return e;
+}
+__device__ __forceinline__ float bil_weight(int o, int i, int n_in, float s) {   // weight of input index i in output index o
+    const float f = s * o;
+    const int i0 = static_cast<int>(f);
+    const int i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    const float l = f - i0, h = 1.f - l;
+    return (i0 == i ? h : 0.f) + (i1 == i ? l : 0.f);
+}
+__global__ void __launch_bounds__(256) bilinear_bwd_gather_kernel(const void* gout, int bf, void* gin, int B, int Hi, int Wi, int Ho,
+                                                                  int Wo, int C, float sh, float sw) {
+    const int cv = C / 4;
+    const long long total = static_cast<long long>(B) * Hi * Wi * cv;
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % cv);
+    long long p = i / cv;
+    const int ix = static_cast<int>(p % Wi);
+    p /= Wi;
+    const int iy = static_cast<int>(p % Hi);
+    const int b = static_cast<int>(p / Hi);
+    const int ox_a = bil_first(ix, Wo, sw);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int oy = bil_first(iy, Ho, sh); oy < Ho && static_cast<int>(sh * oy) <= iy; ++oy) {
+        const float wy = bil_weight(oy, iy, Hi, sh);
+        if (wy == 0.f) continue;
+        const long long row = (static_cast<long long>(b) * Ho + oy) * Wo;
+        for (int ox = ox_a; ox < Wo && static_cast<int>(sw * ox) <= ix; ++ox) {
+            // the scatter form adds (hy * hx) g etc.: the product of the two 1-D weights, formed the same way
+            const float w = wy * bil_weight(ox, ix, Wi, sw);
+            if (w == 0.f) continue;
+            const float4 g = ldf4(gout, (row + ox) * C + c * 4, bf);
+            acc.x += w * g.x; acc.y += w * g.y; acc.z += w * g.z; acc.w += w * g.w;
+        }
+    }
+    const long long o = ((static_cast<long long>(b) * Hi + iy) * Wi + ix) * C + c * 4;
+    stf4(gin, o, bf, acc);
+}
+
 // ---------------------------------------------------------------- output head adjoint
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* gdepth, const float* depth, const void* t32, int bf, const float* w2,
                                                        void* dt32, float* dw2, float* db2, long long P) {
@@ -979,6 +1027,18 @@ int bilinear_bwd(const void* gout, int bf, float* gin, int B, int Hi, int Wi, in
     debug_label("bilinear_bwd");
     ProfScope prof(PROF_ELEM, static_cast<double>(B) * C * 4 * (static_cast<double>(Hi) * Wi + static_cast<double>(Ho) * Wo), st);
     bilinear_bwd_kernel<<<blocks_for(total), 256, 0, st>>>(gout, bf, gin, B, Hi, Wi, Ho, Wo, C, sh, sw);
+    DAD_CHECK_LAUNCH();
+    return DAD_OK;
+}
+
+int bilinear_bwd_gather(const void* gout, int bf, void* gin, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st) {
+    DAD_REQUIRE(C % 4 == 0, "bilinear_bwd: C=%d must be a multiple of 4", C);
+    const float sh = Ho > 1 ? static_cast<float>(Hi - 1) / static_cast<float>(Ho - 1) : 0.f;
+    const float sw = Wo > 1 ? static_cast<float>(Wi - 1) / static_cast<float>(Wo - 1) : 0.f;
+    const long long total = static_cast<long long>(B) * Hi * Wi * (C / 4);
+    debug_label("bilinear_bwd_gather");
+    ProfScope prof(PROF_ELEM, static_cast<double>(B) * C * (bf ? 2 : 4) * (static_cast<double>(Hi) * Wi + static_cast<double>(Ho) * Wo), st);
+    bilinear_bwd_gather_kernel<<<blocks_for(total), 256, 0, st>>>(gout, bf, gin, B, Hi, Wi, Ho, Wo, C, sh, sw);
     DAD_CHECK_LAUNCH();
     return DAD_OK;
 }

@@ -73,6 +73,8 @@ int cvt_tiles(const float* src, void* dstN, void* dstT, int Z, int T, int ld, cu
 int head_transpose(const void* src, long long lds, void* dst, int B, int T, int heads, int ld, cudaStream_t st);
 // adjoint of bilinear_nhwc (align_corners=True): gin [B,Hi,Wi,C] must be zero-filled by the caller
 int bilinear_bwd(const void* gout, int bf, float* gin, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st);
+// the same adjoint in gather form: writes gin (activation type) once, deterministic, no zero fill / atomics
+int bilinear_bwd_gather(const void* gout, int bf, void* gin, int B, int Hi, int Wi, int Ho, int Wo, int C, cudaStream_t st);
 // output head: depth = relu(dot(t32, w2) + b2), t32 = relu(conv + b) saved.  dt32 [P,32]; dw2 [32] / db2 [1] accumulate
 int head_bwd(const float* gdepth, const float* depth, const void* t32, int bf, const float* w2, void* dt32, float* dw2,
              float* db2, long long P, cudaStream_t st);

@@ -437,6 +437,8 @@ struct Trainer {
     // gin (activation type, [B,Hi,Wi,C]) = adjoint of the bilinear resampling applied to gout [B,Ho,Wo,C]
     int bilinear_adjoint(const void* gout, void* gin, int Hi, int Wi, int Ho, int Wo, int C, Bump& ar) {
         const long long n = static_cast<long long>(B) * Hi * Wi * C;
+        static const bool scatter = getenv("DAD_BILINEAR_SCATTER") != nullptr;   // A/B switch: round 1's atomicAdd form
+        if (!scatter) return dry ? DAD_OK : bilinear_bwd_gather(gout, bf, gin, B, Hi, Wi, Ho, Wo, C, st);
         const size_t mk = ar.used;
         float* acc = bf ? ar.f(n) : reinterpret_cast<float*>(gin);
         if (!dry) {

@@ -15,4 +15,8 @@ for k, v in d["kernel_breakdown"].items():
 print("eager", d.get("gpu_eager_baseline"))
 print("cpu", d.get("cpu_baseline"))
 PYEOF
+for w in train train4; do
+  timeout 300 python bench.py --workload $w --no-cpu-baseline --no-gpu-eager --steps 8 --warmup 3 > gpurun_out/bench_${w}_$TAG.json 2> gpurun_out/bench_${w}_$TAG.err
+  python -c "import json; d = json.load(open('gpurun_out/bench_${w}_$TAG.json')); print('$w', round(d['value'], 1), d['unit'], round(d['ms_per_step'], 2), 'ms/step', {k: round(v['ms_per_step'], 2) for k, v in d.get('kernel_breakdown', {}).items()})"
+done
 SCALES=0.5 POLYS="2" bash tools/attn_ab.sh > /dev/null 2>&1; tail -4 gpurun_out/attn_ab/summary.txt
