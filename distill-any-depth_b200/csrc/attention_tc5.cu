@@ -8,8 +8,9 @@
 //        FFMA2 + MUFU + CVT, part of the pairs on the FMA pipe   17.6 - 19.4   (MUFU alone: 16 by construction)
 //      so the softmax threads execute nothing but  a = s * log2e - ref  (one packed FFMA2 per pair), the exponential
 //      (MUFU for some pairs, a packed cubic on the FMA pipe for the others) and the bf16 pack:
-//        * the row sum  l = sum_j P  is computed by the TENSOR CORE: a third MMA per key tile multiplies P (TMEM) by a
-//          constant all-ones [64 x 16] operand into 16 extra accumulator columns;
+//        * the row sum  l = sum_j P  is computed by the TENSOR CORE, in the SAME MMA as O: the B operand is [V | 1]
+//          (N = 80; the all-ones tile is the second 64-column block of the MN-major operand, reached through the
+//          descriptor's leading-dimension offset), so [O | L] are 80 adjacent accumulator columns;
 //        * no running maximum and no rescale in the loop: P is taken relative to the row maximum of the FIRST key tile
 //          (floating point keeps full relative precision for P up to 2^127).  A later score more than 127 log2 units
 //          above that reference makes the row sum non-finite; the work item is then put on the CTA's redo list and
@@ -22,6 +23,10 @@
 //  (3) two further restructurings were built and measured and are NOT used (profiles/attention_r2.md): releasing the score
 //      buffer as soon as S is in registers (Q K^T of tile g+2 issued at the start of tile g) with P in its own
 //      single / double buffer ran 0.42 - 0.43 ms per ViT-L launch against 0.333 ms for this kernel.
+//  (4) ncu source pages (attention_tc7's and this kernel's): the MMA-issuing warp is busy ~80 % of a tile - its
+//      instruction stream (waits, descriptor set-up, 12 tiny MMAs, commits) is co-critical with the softmax warps.  Hence
+//      8 MMAs per tile instead of 12 (the [V | 1] operand above), ONE barrier per K / V stage, all waits of a tile before
+//      one elected issue block, and the last two tiles of an item peeled out of the steady loop: 0.324 -> 0.301 ms.
 // TMEM (256 columns per CTA): S0/P0 [0,64) S1/P1 [64,128) | O [128,192) | L [192,208): P is written in place of S.
 // Roles (192 threads): warps 0-3 softmax (thread = query row), warp 4 TMA producer, warp 5 tcgen05.mma issuer.
 #include <cstdlib>
